@@ -1,0 +1,137 @@
+/* mmgpu.h -- C ABI of the B200 (sm_100a) multi-model 360 MC + block-matching distortion path.
+ *
+ * Drop-in boundary for FAU-LMS/vvc-extension-mm (VTM-17.2 + MM).  Each entry point names the
+ * reference interface whose body it replaces; INTEGRATION.md shows the C++ stubs a maintainer
+ * adds inside the reference.  Plain pointers and sizes only, `int` return (0 = ok, <0 = error,
+ * text via mmgpu_last_error); no exceptions cross the boundary.  One context per
+ * InterPrediction/InterSearch instance; a context is thread-compatible, not thread-safe
+ * (the reference is single threaded).  There is no CPU fallback: every compute entry point
+ * fails with MMGPU_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MMGPU_H
+#define MMGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMGPU_OK 0
+#define MMGPU_ERR_ARG (-1)
+#define MMGPU_ERR_CUDA (-2)
+#define MMGPU_ERR_STATE (-3)
+
+/* MotionModelID, source/Lib/CommonLib/TypeDef.h:865-880 */
+enum mmgpu_model {
+  MMGPU_CLASSIC = 0, MMGPU_MPA_FRONT_BACK = 1, MMGPU_MPA_LEFT_RIGHT = 2, MMGPU_MPA_TOP_BOTTOM = 3,
+  MMGPU_TANGENTIAL = 4, MMGPU_THREE_D_TRANSLATIONAL = 5, MMGPU_ROTATIONAL = 6, MMGPU_GEODESIC_X = 7,
+  MMGPU_GEODESIC_Y = 8, MMGPU_GEODESIC_Z = 9, MMGPU_GEODESIC_CAMPOSE = 10
+};
+enum mmgpu_oob { MMGPU_OOB_PRED = 0 /* InterPrediction.cpp:776-780 */, MMGPU_OOB_ME = 1 /* InterSearch.cpp:6329-6332 */ };
+enum mmgpu_dist { MMGPU_DIST_SAD = 0 /* RdCost::xGetSAD*, DF_SAD.. */, MMGPU_DIST_HAD = 1 /* RdCost::xGetHADs, DF_HAD.. */ };
+enum mmgpu_had_mode { MMGPU_HAD_SCALAR = 0 /* RdCost.cpp:2637 */, MMGPU_HAD_SIMD = 1 /* x86/RdCostX86.h:2661 (AVX2/SSE hosts) */ };
+
+typedef struct mmgpu_ctx mmgpu_ctx;
+
+/* What EncLib::init (EncLib.cpp:327-357) / DecLib::activateParameterSets (DecLib.cpp:2014-2063) know
+ * when they call MVReprojection::init (MVReprojection.cpp:7-65). */
+typedef struct {
+  int32_t pic_w, pic_h;  /* luma picture size (ERP) */
+  int32_t chroma_fmt;    /* ChromaFormat: 0=400 1=420 2=422 3=444 */
+  int32_t bit_depth;     /* internal bit depth (<= 10: the SIMD distortion functions' domain) */
+  int32_t max_cu;        /* sps->getMaxCUWidth() (128) */
+  int32_t margin;        /* luma margin of reference planes, Picture.cpp:91 (288) */
+  float offset4x4;       /* MMOffset4x4 as float (EncApp.cpp:758 -> 1.0) */
+  int32_t ged_flavor;    /* 0 = VISHWANATH_ORIGINAL, 1 = VISHWANATH_MODULATED (EncApp.cpp:755) */
+  int32_t max_refs;      /* reference-picture slots kept resident in HBM */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t libm_fma;      /* which glibc sinf/cosf build the host CPU selects: 1 = __sinf_fma, 0 = sse2, -1 = detect */
+  int32_t had_mode;      /* mmgpu_had_mode; -1 = MMGPU_HAD_SIMD */
+} mmgpu_config;
+
+typedef struct { int32_t hor, ver; } mmgpu_mv; /* Mv, source/Lib/CommonLib/Mv.h */
+
+/* One block of a batch: pu.blocks[COMPONENT_Y] plus what IntTZSearchStruct carries
+ * (InterSearch.h: blkPos, blkSize, motionModel, curPOC/refPOC -> rot_slot, pcPatternKey -> org_x/y). */
+typedef struct {
+  int32_t x, y, w, h;     /* luma position / size */
+  int32_t model;          /* mmgpu_model (CLASSIC allowed: translational candidates, a8) */
+  int32_t ref_slot;       /* reference picture slot set by mmgpu_set_ref* */
+  int32_t rot_slot;       /* rotation slot for GEODESIC_CAMPOSE (mmgpu_set_rotation); ignored otherwise */
+  int32_t cand_first;     /* first candidate MV of this block in the mv array */
+  int32_t cand_count;     /* number of candidate MVs */
+  int32_t org_x, org_y;   /* top-left of the original block inside the org plane (mmgpu_set_org*) */
+  int32_t reserved;
+} mmgpu_block;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out);  /* MVReprojection::init + fillCache on device */
+void mmgpu_destroy(mmgpu_ctx* ctx);
+const char* mmgpu_last_error(const mmgpu_ctx* ctx);          /* ctx may be NULL: error of the last create */
+int mmgpu_sync(mmgpu_ctx* ctx);
+/* cudaStream_t the context launches on (for event timing by the caller) */
+void* mmgpu_stream(mmgpu_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+uint64_t mmgpu_launch_count(const mmgpu_ctx* ctx);
+
+/* ---- reference pictures: Picture::getRecoBuf(compID, wrapRef) after extendPicBorder (Picture.cpp:988-1092) */
+/* plane00[c] points at sample (0,0) of component c in HOST memory; the margins around it are copied too. */
+int mmgpu_set_ref(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3]);
+/* same, but plane00[c] are DEVICE pointers owned by the caller (kept resident, zero copy): used when the
+ * picture arrives by ncclBroadcast or was reconstructed on the device. */
+int mmgpu_set_ref_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3]);
+/* un-padded planes in host memory: upload + Picture::extendPicBorder on the device. */
+int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3], const int32_t stride[3]);
+
+/* ---- geodesic epipole: GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46) ------------ */
+void mmgpu_rodrigues(const float epipole[3], float R[9]);          /* host helper, row-major R */
+float mmgpu_fixed_to_float(int32_t fixed, int32_t precision);     /* Coordinate.cpp:75-77 (EPIPOLE_PRECISION_FIXED=24) */
+int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9]);
+
+/* ---- a1: MVReprojection::reprojectMotionVectorSubblocks (MVReprojection.cpp:80-166) --------------- */
+/* out_x/out_y: (h/sbH)*(w/sbW) ints, column-major like the reference's ArrayXXi (idx = col*rows + row). */
+int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
+                    int rot_slot, int32_t* out_x, int32_t* out_y);
+
+/* ---- a5/a6/a8: InterPrediction::xPredInterBlkMM (InterPrediction.cpp:683-856), xPredInterBlk (:928-1096),
+ *      InterSearch::xMVReprojectionInterpolation (InterSearch.cpp:6277-6385) --------------------------- */
+/* x,y,w,h in units of component `comp`; mv in 1/16 luma pel (MV_PRECISION_INTERNAL); bi!=0 keeps the
+ * 14-bit intermediate (rndRes = !bi); dst is HOST memory (dst_stride in samples). */
+int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
+             int rot_slot, int bi, int clp_min, int clp_max, int oob_mode, int16_t* dst, int dst_stride);
+
+/* ---- a13: InterPrediction::xWeightedAverage -> PelBuf::addAvg (Buffer.cpp:551-587) ------------------ */
+int mmgpu_add_avg(mmgpu_ctx* ctx, const int16_t* src0, int s0_stride, const int16_t* src1, int s1_stride, int16_t* dst,
+                  int dst_stride, int w, int h, int clp_min, int clp_max);
+
+/* ---- a9-a11 + a6: candidate evaluation, xTZSearchHelp/xPatternRefinementProjected's
+ *      xMVReprojectionInterpolation + m_cDistParam.distFunc pair (InterSearch.cpp:363-453, 6222-6249) --- */
+/* original samples (pcPatternKey or the whole current picture), HOST memory */
+int mmgpu_set_org(mmgpu_ctx* ctx, const int16_t* org, int stride, int w, int h);
+int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stride, int w, int h);
+/* Evaluate every candidate MV of every block: dist[i] = distFunc(org block, MC(block, mvs[i])).
+ * mv_prec_shift: mvs are given in MV_PRECISION_INT (4), HALF (3), QUARTER (2) or INTERNAL (0) units
+ * (Mv::changePrecision, InterSearch.cpp:6294).  dist_kind/sub_shift as set by RdCost::setDistParam
+ * (RdCost.cpp:225-311).  All pointers HOST memory; the call returns when dist[] is filled. */
+int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* blocks, int n_cands, const mmgpu_mv* mvs,
+                   int mv_prec_shift, int dist_kind, int sub_shift, int clp_min, int clp_max, uint64_t* dist);
+
+/* Frame-wide microbench entry (SURVEY 8b mmgpu_frame_batch): the same evaluation with blocks, mvs and dist
+ * already resident in HBM; asynchronous on mmgpu_stream().  `plan` comes from mmgpu_plan_create (host-built
+ * work list for these blocks, uploaded once) and can be reused while the block list is unchanged. */
+typedef struct mmgpu_plan mmgpu_plan;
+int mmgpu_plan_create(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* blocks, int n_cands, mmgpu_plan** out);
+void mmgpu_plan_destroy(mmgpu_plan* plan);
+int mmgpu_me_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int dist_kind,
+                          int sub_shift, int clp_min, int clp_max, uint64_t* d_dist);
+/* number of luma sample-candidates (sum over blocks of w*h*cand_count) a plan evaluates */
+uint64_t mmgpu_plan_samples(const mmgpu_plan* plan);
+
+/* MC of a whole batch (one MV per block: the first candidate), predictions written into a device picture
+ * buffer at (x,y): final-MC / merge-candidate shape of the path (EncCu.cpp:2375-2600). */
+int mmgpu_mc_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int clp_min,
+                          int clp_max, int16_t* d_dst, int dst_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,657 @@
+// mmgpu.cu -- C ABI (include/mmgpu.h) over the sm_100a kernels in mm_kernels.cuh.
+// Host side is plain C++ + CUDA runtime; no torch types, no CPU fallback of the compute path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "mm_kernels.cuh"
+
+#define MM_MAX_ROT 64
+
+struct mmgpu_plan
+{
+  mmgpu_ctx* ctx;
+  int nBlocks, nCands, nItems;
+  uint64_t samples;
+  mmgpu_block* dBlocks;
+  MmItem* dItems;
+  int32_t* dCandBlock;
+  MmCand* dCands;
+  size_t capBlocks, capItems, capCands, capCandParams;
+};
+
+struct mmgpu_ctx
+{
+  mmgpu_config cfg;
+  MmGeom g;
+  MmFir fir;
+  cudaStream_t stream;
+  std::string err;
+  uint64_t launches;
+  // reference slots
+  MmRef* dRefs;
+  std::vector<MmRef> hRefs;
+  std::vector<int16_t*> ownedPlanes;  // [slot*3+c] base allocations owned by the context
+  // rotations
+  float* dRot;
+  // MPA caches
+  float2* dMpa[3];
+  uint8_t* dMpaVip[3];
+  // original picture
+  int16_t* dOrgOwned;
+  size_t orgCap;
+  const int16_t* dOrg;
+  int orgStride, orgW, orgH;
+  // scratch
+  mmgpu_plan scratchPlan;
+  mmgpu_mv* dMvs;
+  size_t capMvs;
+  unsigned long long* dDist;
+  size_t capDist;
+  int16_t* dTmp;  // small device buffers for mmgpu_mc / reproject / add_avg
+  size_t capTmp;
+};
+
+static std::string g_createErr;
+
+static int fail(mmgpu_ctx* c, int code, const std::string& msg)
+{
+  if (c) c->err = msg;
+  else g_createErr = msg;
+  return code;
+}
+#define CU(call)                                                                                           \
+  do                                                                                                       \
+  {                                                                                                        \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+      return fail(ctx, MMGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+static int scaleX(int comp, int fmt) { return (comp == 0) ? 0 : ((fmt == 1 || fmt == 2) ? 1 : 0); }
+static int scaleY(int comp, int fmt) { return (comp == 0) ? 0 : ((fmt == 1) ? 1 : 0); }
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static MmParams baseParams(mmgpu_ctx* ctx)
+{
+  MmParams P;
+  memset(&P, 0, sizeof(P));
+  P.g = ctx->g;
+  P.fir = ctx->fir;
+  P.refs = ctx->dRefs;
+  P.rot = ctx->dRot;
+  for (int i = 0; i < 3; ++i) { P.mpa[i] = ctx->dMpa[i]; P.mpaVip[i] = ctx->dMpaVip[i]; }
+  P.org = ctx->dOrg;
+  P.orgStride = ctx->orgStride;
+  P.hadMode = ctx->cfg.had_mode;
+  P.picW = ctx->cfg.pic_w;
+  P.picH = ctx->cfg.pic_h;
+  P.maxCU = ctx->cfg.max_cu;
+  P.clpMin = 0;
+  P.clpMax = (1 << ctx->cfg.bit_depth) - 1;
+  return P;
+}
+
+extern "C" const char* mmgpu_last_error(const mmgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
+
+extern "C" void mmgpu_rodrigues(const float e[3], float R[9])
+{
+  // GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:25-45); Eigen fixed 3x3 lazy products
+  // evaluate each coefficient as a0*b0 + (a1*b1 + a2*b2).
+  const float norm = sqrtf((e[0] * e[0] + e[1] * e[1] + e[2] * e[2]));
+  const float px = e[0] / norm, py = e[1] / norm, pz = e[2] / norm;
+  const float cx = -py, cy = px, cz = 0.0f;
+  const float s = sqrtf(cx * cx + cy * cy + cz * cz);
+  float M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (s == 0)
+  {
+    if (pz < 0) M[8] = -1;
+    memcpy(R, M, sizeof(M));
+    return;
+  }
+  const float one = 1.0f, mone = -1.0f;
+  const float mn = (pz < one) ? pz : one;        // std::min(TCoord(1), z)
+  const float cc = (mone < mn) ? mn : mone;      // std::max(TCoord(-1), .)
+  float K[9] = {0, -cz, cy, cz, 0, -cx, -cy, cx, 0};
+  float KK[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+    {
+      const float p0 = K[i * 3 + 0] * K[0 * 3 + j], p1 = K[i * 3 + 1] * K[1 * 3 + j], p2 = K[i * 3 + 2] * K[2 * 3 + j];
+      const float s12 = p1 + p2;
+      KK[i * 3 + j] = p0 + s12;
+    }
+  const float f = (1 - cc) / (s * s);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+    {
+      const float id = (i == j) ? 1.0f : 0.0f;
+      const float t = id + K[i * 3 + j];
+      const float u = KK[i * 3 + j] * f;
+      M[i * 3 + j] = t + u;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = M[j * 3 + i];  // transposeInPlace
+}
+
+extern "C" float mmgpu_fixed_to_float(int32_t fixed, int32_t precision)
+{
+  return (float)(fixed >> precision) + (float)(fixed & ((1 << precision) - 1)) / (float)(1 << precision);
+}
+
+extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
+{
+  mmgpu_ctx* ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, MMGPU_ERR_ARG, "null argument");
+  if (cfg->pic_w <= 0 || cfg->pic_h <= 0 || (cfg->pic_w & 7) || (cfg->pic_h & 7))
+    return fail(nullptr, MMGPU_ERR_ARG, "picture size must be a positive multiple of 8");
+  if (cfg->bit_depth < 8 || cfg->bit_depth > 10) return fail(nullptr, MMGPU_ERR_ARG, "bit_depth must be 8..10");
+  if (cfg->max_refs <= 0 || cfg->max_refs > 1024) return fail(nullptr, MMGPU_ERR_ARG, "max_refs out of range");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, MMGPU_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MMGPU_ERR_ARG, "bad device ordinal");
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, MMGPU_ERR_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10)
+    return fail(nullptr, MMGPU_ERR_CUDA, "device is not sm_100 (this library carries sm_100a code only)");
+
+  ctx = new mmgpu_ctx();
+  ctx->cfg = *cfg;
+  if (ctx->cfg.had_mode < 0) ctx->cfg.had_mode = MMGPU_HAD_SIMD;
+  if (ctx->cfg.libm_fma < 0)
+  {
+    __builtin_cpu_init();
+    ctx->cfg.libm_fma = (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
+  }
+  ctx->launches = 0;
+  MmGeom& g = ctx->g;
+  g.picW = (float)cfg->pic_w;
+  g.picH = (float)cfg->pic_h;
+  g.focal = (float)(1. / tan(M_PI / cfg->pic_h));   // Projection.h:128, evaluated by the host libm like the reference
+  g.angRes = (float)(M_PI / cfg->pic_h);            // MVReprojection.cpp:27
+  g.off = cfg->offset4x4;
+  g.rows4 = cfg->pic_h / 4;
+  g.cols4 = cfg->pic_w / 4;
+  g.gedModulated = cfg->ged_flavor == 1;
+  g.fmaBuild = ctx->cfg.libm_fma;
+  const int hr = (14 - cfg->bit_depth) < 2 ? 2 : (14 - cfg->bit_depth);
+  MmFir& f = ctx->fir;
+  f.shift1 = 6 - hr;
+  f.off1 = -8192 * (1 << f.shift1);
+  f.shift2 = 6 + hr;
+  f.off2 = (1 << (f.shift2 - 1)) + (8192 << 6);
+  f.shift2bi = 6;
+  f.shift1l = 6;
+  f.off1l = 32;
+  f.cpShift = hr;
+
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->hRefs.assign(cfg->max_refs, MmRef());
+  ctx->ownedPlanes.assign((size_t)cfg->max_refs * 3, nullptr);
+  CU(cudaMalloc(&ctx->dRefs, sizeof(MmRef) * cfg->max_refs));
+  CU(cudaMemset(ctx->dRefs, 0, sizeof(MmRef) * cfg->max_refs));
+  CU(cudaMalloc(&ctx->dRot, sizeof(float) * 9 * (MM_ROT_USER0 + MM_MAX_ROT)));
+  {
+    std::vector<float> rot(9 * (MM_ROT_USER0 + MM_MAX_ROT));
+    const float ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1}, e0[3] = {0, 0, 0};
+    mmgpu_rodrigues(ex, &rot[0]);   // MVReprojection.cpp:42-52
+    mmgpu_rodrigues(ey, &rot[9]);
+    mmgpu_rodrigues(ez, &rot[18]);
+    for (int s = 0; s < MM_MAX_ROT; ++s) mmgpu_rodrigues(e0, &rot[9 * (MM_ROT_USER0 + s)]);  // EpipoleList.h:15-17
+    CU(cudaMemcpy(ctx->dRot, rot.data(), rot.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  const int n4 = g.rows4 * g.cols4;
+  for (int m = 0; m < 3; ++m)
+  {
+    CU(cudaMalloc(&ctx->dMpa[m], sizeof(float2) * n4));
+    CU(cudaMalloc(&ctx->dMpaVip[m], n4));
+    k_mpa_cache<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(g, m + 1, ctx->dMpa[m], ctx->dMpaVip[m]);
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = ctx;
+  return MMGPU_OK;
+}
+
+static void freePlan(mmgpu_plan* p)
+{
+  cudaFree(p->dBlocks);
+  cudaFree(p->dItems);
+  cudaFree(p->dCandBlock);
+  cudaFree(p->dCands);
+  p->dBlocks = nullptr; p->dItems = nullptr; p->dCandBlock = nullptr; p->dCands = nullptr;
+  p->capBlocks = p->capItems = p->capCands = p->capCandParams = 0;
+}
+
+extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto p : ctx->ownedPlanes) cudaFree(p);
+  cudaFree(ctx->dRefs);
+  cudaFree(ctx->dRot);
+  for (int m = 0; m < 3; ++m) { cudaFree(ctx->dMpa[m]); cudaFree(ctx->dMpaVip[m]); }
+  cudaFree(ctx->dOrgOwned);
+  freePlan(&ctx->scratchPlan);
+  cudaFree(ctx->dMvs);
+  cudaFree(ctx->dDist);
+  cudaFree(ctx->dTmp);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int mmgpu_sync(mmgpu_ctx* ctx)
+{
+  if (!ctx) return MMGPU_ERR_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+extern "C" void* mmgpu_stream(mmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t mmgpu_launch_count(const mmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- reference pictures --------------------------------------------------------------------------
+static int compDims(const mmgpu_ctx* ctx, int c, int* w, int* h, int* mx, int* my)
+{
+  const int sx = scaleX(c, ctx->cfg.chroma_fmt), sy = scaleY(c, ctx->cfg.chroma_fmt);
+  *w = ctx->cfg.pic_w >> sx;
+  *h = ctx->cfg.pic_h >> sy;
+  *mx = ctx->cfg.margin >> sx;
+  *my = ctx->cfg.margin >> sy;
+  return 0;
+}
+static int numComps(const mmgpu_ctx* ctx) { return ctx->cfg.chroma_fmt == 0 ? 1 : 3; }
+
+static int ensureOwnedPlane(mmgpu_ctx* ctx, int slot, int c, int16_t** plane00, int* pitch)
+{
+  int w, h, mx, my;
+  compDims(ctx, c, &w, &h, &mx, &my);
+  const int p = (w + 2 * mx + 63) / 64 * 64;  // pitch in samples: 128-byte multiple
+  int16_t*& base = ctx->ownedPlanes[(size_t)slot * 3 + c];
+  if (!base) CU(cudaMalloc(&base, sizeof(int16_t) * (size_t)p * (h + 2 * my)));
+  *plane00 = base + (size_t)my * p + mx;
+  *pitch = p;
+  return MMGPU_OK;
+}
+static int publishRef(mmgpu_ctx* ctx, int slot)
+{
+  CU(cudaMemcpyAsync(ctx->dRefs + slot, &ctx->hRefs[slot], sizeof(MmRef), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // hRefs may change right after
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_set_ref(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3])
+{
+  if (!ctx || !plane00 || !stride) return MMGPU_ERR_ARG;
+  if (slot < 0 || slot >= ctx->cfg.max_refs) return fail(ctx, MMGPU_ERR_ARG, "ref slot out of range");
+  cudaSetDevice(ctx->cfg.device);
+  MmRef r;
+  memset(&r, 0, sizeof(r));
+  r.poc = poc;
+  for (int c = 0; c < numComps(ctx); ++c)
+  {
+    if (!plane00[c]) return fail(ctx, MMGPU_ERR_ARG, "null plane");
+    int w, h, mx, my, pitch;
+    int16_t* d00;
+    compDims(ctx, c, &w, &h, &mx, &my);
+    int rc = ensureOwnedPlane(ctx, slot, c, &d00, &pitch);
+    if (rc) return rc;
+    const int16_t* src = plane00[c] - (ptrdiff_t)my * stride[c] - mx;
+    CU(cudaMemcpy2DAsync(d00 - (size_t)my * pitch - mx, sizeof(int16_t) * pitch, src, sizeof(int16_t) * stride[c],
+                         sizeof(int16_t) * (w + 2 * mx), h + 2 * my, cudaMemcpyHostToDevice, ctx->stream));
+    r.plane00[c] = d00;
+    r.stride[c] = pitch;
+  }
+  ctx->hRefs[slot] = r;
+  return publishRef(ctx, slot);
+}
+
+extern "C" int mmgpu_set_ref_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3],
+                                    const int32_t stride[3])
+{
+  if (!ctx || !plane00 || !stride) return MMGPU_ERR_ARG;
+  if (slot < 0 || slot >= ctx->cfg.max_refs) return fail(ctx, MMGPU_ERR_ARG, "ref slot out of range");
+  cudaSetDevice(ctx->cfg.device);
+  MmRef r;
+  memset(&r, 0, sizeof(r));
+  r.poc = poc;
+  for (int c = 0; c < numComps(ctx); ++c)
+  {
+    if (!plane00[c]) { if (c == 0) return fail(ctx, MMGPU_ERR_ARG, "null luma plane"); continue; }
+    if (((uintptr_t)plane00[c] & 3) || (stride[c] & 1)) return fail(ctx, MMGPU_ERR_ARG, "device plane must be 4-byte aligned with even stride");
+    r.plane00[c] = plane00[c];
+    r.stride[c] = stride[c];
+  }
+  ctx->hRefs[slot] = r;
+  return publishRef(ctx, slot);
+}
+
+extern "C" int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3],
+                                      const int32_t stride[3])
+{
+  if (!ctx || !plane || !stride) return MMGPU_ERR_ARG;
+  if (slot < 0 || slot >= ctx->cfg.max_refs) return fail(ctx, MMGPU_ERR_ARG, "ref slot out of range");
+  cudaSetDevice(ctx->cfg.device);
+  MmRef r;
+  memset(&r, 0, sizeof(r));
+  r.poc = poc;
+  for (int c = 0; c < numComps(ctx); ++c)
+  {
+    if (!plane[c]) return fail(ctx, MMGPU_ERR_ARG, "null plane");
+    int w, h, mx, my, pitch;
+    int16_t* d00;
+    compDims(ctx, c, &w, &h, &mx, &my);
+    int rc = ensureOwnedPlane(ctx, slot, c, &d00, &pitch);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(d00, sizeof(int16_t) * pitch, plane[c], sizeof(int16_t) * stride[c], sizeof(int16_t) * w, h,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    dim3 tb(32, 8), gr((w + 2 * mx + 31) / 32, (h + 2 * my + 7) / 8);
+    k_extend_border<<<gr, tb, 0, ctx->stream>>>(d00, pitch, w, h, mx, my);
+    ctx->launches++;
+    r.plane00[c] = d00;
+    r.stride[c] = pitch;
+  }
+  CU(cudaGetLastError());
+  ctx->hRefs[slot] = r;
+  return publishRef(ctx, slot);
+}
+
+extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9])
+{
+  if (!ctx || !R) return MMGPU_ERR_ARG;
+  if (rot_slot < 0 || rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "rotation slot out of range");
+  cudaSetDevice(ctx->cfg.device);
+  CU(cudaMemcpyAsync(ctx->dRot + 9 * (MM_ROT_USER0 + rot_slot), R, 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+// ---- scratch -------------------------------------------------------------------------------------
+template <typename T>
+static int ensureCap(mmgpu_ctx* ctx, T** p, size_t* cap, size_t need)
+{
+  if (*cap >= need) return MMGPU_OK;
+  size_t n = need + need / 2 + 1024;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU(cudaMalloc(p, sizeof(T) * n));
+  *cap = n;
+  return MMGPU_OK;
+}
+
+static int checkBlockShape(mmgpu_ctx* ctx, int comp, int fmt, int x, int y, int w, int h)
+{
+  const int sx = scaleX(comp, fmt), sy = scaleY(comp, fmt);
+  const int sbw = 4 >> sx, sbh = 4 >> sy;
+  if (w < sbw || h < sbh || (w % sbw) || (h % sbh) || (x % sbw) || (y % sbh) || x < 0 || y < 0)
+    return fail(ctx, MMGPU_ERR_ARG, "block must be aligned to the sub-block grid");
+  if (!pow2(w) || !pow2(h) || (w << sx) > 128 || (h << sy) > 128) return fail(ctx, MMGPU_ERR_ARG, "block size must be a power of two <= 128");
+  if (((x + w) << sx) > ctx->cfg.pic_w || ((y + h) << sy) > ctx->cfg.pic_h) return fail(ctx, MMGPU_ERR_ARG, "block outside the picture");
+  return MMGPU_OK;
+}
+
+// ---- a1 ------------------------------------------------------------------------------------------
+extern "C" int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
+                               int rot_slot, int32_t* out_x, int32_t* out_y)
+{
+  if (!ctx || !out_x || !out_y) return MMGPU_ERR_ARG;
+  if (model <= MMGPU_CLASSIC || model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "reproject: model must be a non-classic motion model");
+  if (comp < 0 || comp > 2 || rot_slot < 0 || rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad comp/rot_slot");
+  int rc = checkBlockShape(ctx, comp, chroma_fmt, x, y, w, h);
+  if (rc) return rc;
+  cudaSetDevice(ctx->cfg.device);
+  const int csx = scaleX(comp, chroma_fmt), csy = scaleY(comp, chroma_fmt);
+  const int n = (w / (4 >> csx)) * (h / (4 >> csy));
+  rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)n * 4 + 64);
+  if (rc) return rc;
+  int32_t* dx = reinterpret_cast<int32_t*>(ctx->dTmp);
+  int32_t* dy = dx + n;
+  MmParams P = baseParams(ctx);
+  k_reproject<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P, comp, csx, csy, x, y, w, h, mv, model, rot_slot, dx, dy);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_x, dx, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_y, dy, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+// ---- a5/a6/a8 ------------------------------------------------------------------------------------
+extern "C" int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv,
+                        int model, int rot_slot, int bi, int clp_min, int clp_max, int oob_mode, int16_t* dst, int dst_stride)
+{
+  if (!ctx || !dst) return MMGPU_ERR_ARG;
+  if (model < MMGPU_CLASSIC || model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "bad model");
+  if (comp < 0 || comp > 2 || rot_slot < 0 || rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad comp/rot_slot");
+  if (ref_slot < 0 || ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[ref_slot].plane00[comp])
+    return fail(ctx, MMGPU_ERR_STATE, "reference slot not set");
+  int rc = checkBlockShape(ctx, comp, chroma_fmt, x, y, w, h);
+  if (rc) return rc;
+  cudaSetDevice(ctx->cfg.device);
+  const int csx = scaleX(comp, chroma_fmt), csy = scaleY(comp, chroma_fmt);
+  const int n = (w / (4 >> csx)) * (h / (4 >> csy));
+  rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)w * h + 64);
+  if (rc) return rc;
+  MmParams P = baseParams(ctx);
+  P.clpMin = clp_min;
+  P.clpMax = clp_max;
+  P.oobMode = oob_mode;
+  k_mc_generic<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P, ref_slot, comp, csx, csy, x, y, w, h, mv, model, rot_slot, bi,
+                                                      ctx->dTmp, w);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2DAsync(dst, sizeof(int16_t) * dst_stride, ctx->dTmp, sizeof(int16_t) * w, sizeof(int16_t) * w, h,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_add_avg(mmgpu_ctx* ctx, const int16_t* src0, int s0_stride, const int16_t* src1, int s1_stride,
+                             int16_t* dst, int dst_stride, int w, int h, int clp_min, int clp_max)
+{
+  if (!ctx || !src0 || !src1 || !dst || w <= 0 || h <= 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  int rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)w * h * 3 + 64);
+  if (rc) return rc;
+  int16_t *d0 = ctx->dTmp, *d1 = d0 + (size_t)w * h, *dd = d1 + (size_t)w * h;
+  CU(cudaMemcpy2DAsync(d0, 2 * w, src0, 2 * s0_stride, 2 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpy2DAsync(d1, 2 * w, src1, 2 * s1_stride, 2 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+  const int hr = ctx->fir.cpShift;
+  const int shift = hr + 1, offset = (1 << (shift - 1)) + 2 * 8192;
+  dim3 tb(32, 4), gr((w + 31) / 32, (h + 3) / 4);
+  k_add_avg<<<gr, tb, 0, ctx->stream>>>(d0, w, d1, w, dd, w, w, h, shift, offset, clp_min, clp_max);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2DAsync(dst, 2 * dst_stride, dd, 2 * w, 2 * w, h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+// ---- org -----------------------------------------------------------------------------------------
+extern "C" int mmgpu_set_org(mmgpu_ctx* ctx, const int16_t* org, int stride, int w, int h)
+{
+  if (!ctx || !org || w <= 0 || h <= 0 || stride < w) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  const int pitch = (w + 63) / 64 * 64;
+  int rc = ensureCap(ctx, &ctx->dOrgOwned, &ctx->orgCap, (size_t)pitch * h);
+  if (rc) return rc;
+  CU(cudaMemcpy2DAsync(ctx->dOrgOwned, 2 * pitch, org, 2 * (size_t)stride, 2 * (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->dOrg = ctx->dOrgOwned;
+  ctx->orgStride = pitch;
+  ctx->orgW = w;
+  ctx->orgH = h;
+  return MMGPU_OK;
+}
+extern "C" int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stride, int w, int h)
+{
+  if (!ctx || !org || w <= 0 || h <= 0 || stride < w) return MMGPU_ERR_ARG;
+  if (((uintptr_t)org & 7) || (stride & 3)) return fail(ctx, MMGPU_ERR_ARG, "device org must be 8-byte aligned, stride a multiple of 4");
+  ctx->dOrg = org;
+  ctx->orgStride = stride;
+  ctx->orgW = w;
+  ctx->orgH = h;
+  return MMGPU_OK;
+}
+
+// ---- plans ---------------------------------------------------------------------------------------
+static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_block* blocks, int n_cands, bool needOrg)
+{
+  std::vector<MmItem> items;
+  std::vector<int32_t> candBlock((size_t)n_cands, -1);
+  uint64_t samples = 0;
+  for (int bi = 0; bi < n_blocks; ++bi)
+  {
+    const mmgpu_block& b = blocks[bi];
+    int rc = checkBlockShape(ctx, 0, 0, b.x, b.y, b.w, b.h);
+    if (rc) return rc;
+    if (b.model < MMGPU_CLASSIC || b.model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "bad model in block");
+    if (b.rot_slot < 0 || b.rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad rot_slot in block");
+    if (b.ref_slot < 0 || b.ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[b.ref_slot].plane00[0])
+      return fail(ctx, MMGPU_ERR_STATE, "block references an unset reference slot");
+    if (b.cand_count < 0 || b.cand_first < 0 || (long)b.cand_first + b.cand_count > n_cands)
+      return fail(ctx, MMGPU_ERR_ARG, "candidate range outside the mv array");
+    if (needOrg && ((b.org_x & 3) || b.org_x < 0 || b.org_y < 0 || b.org_x + b.w > ctx->orgW || b.org_y + b.h > ctx->orgH))
+      return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane (or org_x not a multiple of 4)");
+    const int n = (b.w >> 2) * (b.h >> 2);
+    for (int c = 0; c < b.cand_count; ++c)
+    {
+      if (candBlock[b.cand_first + c] != -1) return fail(ctx, MMGPU_ERR_ARG, "candidate ranges of blocks overlap");
+      candBlock[b.cand_first + c] = bi;
+    }
+    if (n >= 32)
+    {
+      for (int c = 0; c < b.cand_count; ++c)
+        for (int s = 0; s < n; s += 32) items.push_back(MmItem{bi, b.cand_first + c, s, 0});
+    }
+    else
+    {
+      const int per = 32 / n;
+      for (int c = 0; c < b.cand_count; c += per) items.push_back(MmItem{bi, b.cand_first + c, 0, 0});
+    }
+    samples += (uint64_t)b.w * b.h * b.cand_count;
+  }
+  for (int i = 0; i < n_cands; ++i)
+    if (candBlock[i] < 0) return fail(ctx, MMGPU_ERR_ARG, "candidate not owned by any block");
+  int rc;
+  if ((rc = ensureCap(ctx, &p->dBlocks, &p->capBlocks, (size_t)n_blocks))) return rc;
+  if ((rc = ensureCap(ctx, &p->dItems, &p->capItems, items.size()))) return rc;
+  if ((rc = ensureCap(ctx, &p->dCandBlock, &p->capCands, (size_t)n_cands))) return rc;
+  if ((rc = ensureCap(ctx, &p->dCands, &p->capCandParams, (size_t)n_cands))) return rc;
+  CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(p->dItems, items.data(), sizeof(MmItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(p->dCandBlock, candBlock.data(), sizeof(int32_t) * n_cands, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // items/candBlock are stack vectors
+  p->ctx = ctx;
+  p->nBlocks = n_blocks;
+  p->nCands = n_cands;
+  p->nItems = (int)items.size();
+  p->samples = samples;
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_plan_create(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* blocks, int n_cands, mmgpu_plan** out)
+{
+  if (!ctx || !blocks || !out || n_blocks <= 0 || n_cands <= 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  mmgpu_plan* p = new mmgpu_plan();
+  memset(p, 0, sizeof(*p));
+  int rc = buildPlan(ctx, p, n_blocks, blocks, n_cands, false);
+  if (rc) { freePlan(p); delete p; return rc; }
+  *out = p;
+  return MMGPU_OK;
+}
+extern "C" void mmgpu_plan_destroy(mmgpu_plan* p)
+{
+  if (!p) return;
+  if (p->ctx) cudaSetDevice(p->ctx->cfg.device);
+  freePlan(p);
+  delete p;
+}
+extern "C" uint64_t mmgpu_plan_samples(const mmgpu_plan* p) { return p ? p->samples : 0; }
+
+static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int mode, int dist_kind,
+                    int sub_shift, int clp_min, int clp_max, unsigned long long* d_dist, int16_t* d_dst, int dst_stride)
+{
+  if (mv_prec_shift < 0 || mv_prec_shift > 4) return fail(ctx, MMGPU_ERR_ARG, "mv_prec_shift must be 0..4");
+  MmParams P = baseParams(ctx);
+  P.blocks = plan->dBlocks;
+  P.items = plan->dItems;
+  P.nItems = plan->nItems;
+  P.mvs = d_mvs;
+  P.mvShift = mv_prec_shift;
+  P.cands = plan->dCands;
+  P.clpMin = clp_min;
+  P.clpMax = clp_max;
+  P.distKind = dist_kind;
+  P.subShift = sub_shift;
+  P.dist = d_dist;
+  P.dst = d_dst;
+  P.dstStride = dst_stride;
+  k_cand_setup<<<(plan->nCands + 127) / 128, 128, 0, ctx->stream>>>(ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs,
+                                                                   mv_prec_shift, ctx->dRot, plan->nCands, plan->dCands);
+  ctx->launches++;
+  const int grid = (plan->nItems + 3) / 4;
+  if (mode == MM_MODE_DIST)
+  {
+    P.oobMode = MMGPU_OOB_ME;
+    CU(cudaMemsetAsync(d_dist, 0, sizeof(unsigned long long) * plan->nCands, ctx->stream));
+    k_me<MM_MODE_DIST><<<grid, 128, 0, ctx->stream>>>(P);
+  }
+  else
+  {
+    P.oobMode = MMGPU_OOB_PRED;
+    k_me<MM_MODE_PRED><<<grid, 128, 0, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_me_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift,
+                                     int dist_kind, int sub_shift, int clp_min, int clp_max, uint64_t* d_dist)
+{
+  if (!ctx || !plan || !d_mvs || !d_dist) return MMGPU_ERR_ARG;
+  if (!ctx->dOrg) return fail(ctx, MMGPU_ERR_STATE, "mmgpu_set_org* has not been called");
+  if (dist_kind != MMGPU_DIST_SAD && dist_kind != MMGPU_DIST_HAD) return fail(ctx, MMGPU_ERR_ARG, "bad dist_kind");
+  if (sub_shift < 0 || sub_shift > 2 || (dist_kind == MMGPU_DIST_HAD && sub_shift != 0)) return fail(ctx, MMGPU_ERR_ARG, "bad sub_shift");
+  cudaSetDevice(ctx->cfg.device);
+  return launchMe(ctx, plan, d_mvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max,
+                  reinterpret_cast<unsigned long long*>(d_dist), nullptr, 0);
+}
+
+extern "C" int mmgpu_mc_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift,
+                                     int clp_min, int clp_max, int16_t* d_dst, int dst_stride)
+{
+  if (!ctx || !plan || !d_mvs || !d_dst) return MMGPU_ERR_ARG;
+  if (((uintptr_t)d_dst & 7) || (dst_stride & 3)) return fail(ctx, MMGPU_ERR_ARG, "dst must be 8-byte aligned, stride a multiple of 4");
+  cudaSetDevice(ctx->cfg.device);
+  return launchMe(ctx, plan, d_mvs, mv_prec_shift, MM_MODE_PRED, 0, 0, clp_min, clp_max, nullptr, d_dst, dst_stride);
+}
+
+extern "C" int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* blocks, int n_cands, const mmgpu_mv* mvs,
+                              int mv_prec_shift, int dist_kind, int sub_shift, int clp_min, int clp_max, uint64_t* dist)
+{
+  if (!ctx || !blocks || !mvs || !dist || n_blocks <= 0 || n_cands <= 0) return MMGPU_ERR_ARG;
+  if (!ctx->dOrg) return fail(ctx, MMGPU_ERR_STATE, "mmgpu_set_org* has not been called");
+  cudaSetDevice(ctx->cfg.device);
+  int rc = buildPlan(ctx, &ctx->scratchPlan, n_blocks, blocks, n_cands, true);
+  if (rc) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dMvs, &ctx->capMvs, (size_t)n_cands))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dDist, &ctx->capDist, (size_t)n_cands))) return rc;
+  CU(cudaMemcpyAsync(ctx->dMvs, mvs, sizeof(mmgpu_mv) * n_cands, cudaMemcpyHostToDevice, ctx->stream));
+  rc = mmgpu_me_batch_device(ctx, &ctx->scratchPlan, ctx->dMvs, mv_prec_shift, dist_kind, sub_shift, clp_min, clp_max,
+                             reinterpret_cast<uint64_t*>(ctx->dDist));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(dist, ctx->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
