@@ -1,0 +1,290 @@
+"""Parity tests proper: the sm_100a path, called through the C ABI (ctypes), against the CPU oracle on
+the same seeded inputs.  Bit-exact everywhere (integer positions, samples, distortions).
+Reference lines each case follows are quoted in oracle/mm_oracle.c next to the restated function."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vvc_extension_mm_b200 as mm
+from vvc_extension_mm_b200 import workload as wl
+
+pytestmark = pytest.mark.gpu
+
+W, H = 2048, 1024
+SIZES = [(8, 4), (4, 8), (8, 8), (16, 8), (8, 16), (16, 16), (32, 8), (4, 32), (32, 32), (64, 16), (16, 64), (64, 64),
+         (128, 64), (64, 128), (128, 128), (16, 4), (128, 4), (4, 128)]
+EPIPOLE = [0.3, -0.5, 0.81]
+
+
+@pytest.fixture(scope="module")
+def env(oracle_2k, gpu_2k):
+    o, g = oracle_2k, gpu_2k
+    R = ol.Oracle.rodrigues(EPIPOLE)
+    Rg = mm.rodrigues(EPIPOLE)
+    assert np.array_equal(R.view(np.uint32), Rg.view(np.uint32)), "host-side setEpipole differs from oracle"
+    o.set_rotation(ol.GED_CAMPOSE, R)
+    g.set_rotation(0, Rg)
+    ref = wl.pad_frame(wl.synth_frame(W, H, seed=11), 288, 1)
+    cur = wl.synth_frame(W, H, seed=12, shift=(3.0, 1.0))
+    g.set_ref(0, 0, [p.origin for p in ref], [p.stride for p in ref])
+    # the oracle uses its own PaddedPlane type; wrap the same memory
+    class P:  # noqa
+        pass
+    planes = []
+    for p in ref:
+        q = P(); q.origin = p.origin; q.stride = p.stride; planes.append(q)
+    return o, g, planes, ref, cur
+
+
+def rand_block(rng, w, h):
+    x = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+    y = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+    return x, y
+
+
+def test_mpa_cache_matches(env):
+    """MotionPlaneAdaptiveMotionModel::fillCache on the device == oracle: checked through reproject of
+    every 128x128 block of the picture with mv = 0 (reads the whole cache)."""
+    o, g, *_ = env
+    for model in (ol.MPA_FB, ol.MPA_LR, ol.MPA_TB):
+        for y in range(0, H, 128):
+            for x in range(0, W, 256):
+                ox, oy = o.reproject((x, y), (128, 128), (0, 0), model)
+                gx, gy = g.reproject((x, y), (128, 128), (0, 0), model)
+                assert np.array_equal(ox, gx) and np.array_equal(oy, gy), (model, x, y)
+
+
+@pytest.mark.parametrize("model", list(range(1, 11)))
+def test_reproject_luma_chroma(env, model):
+    o, g, *_ = env
+    rng = np.random.default_rng(100 + model)
+    n = 0
+    for it in range(120):
+        w, h = SIZES[it % len(SIZES)]
+        x, y = rand_block(rng, w, h)
+        if it % 9 == 0:
+            y = 0 if it % 2 else H - h          # poles
+        if it % 10 == 0:
+            x = 0 if it % 4 else W - w          # ERP seam
+        mv = (int(rng.integers(-800, 800)), int(rng.integers(-400, 400)))
+        if it % 11 == 0: mv = (0, 0)
+        if it % 13 == 0: mv = (mv[0], 0)
+        if it % 17 == 0: mv = (0, mv[1])
+        ox, oy = o.reproject((x, y), (w, h), mv, model)
+        gx, gy = g.reproject((x, y), (w, h), mv, model)
+        assert np.array_equal(ox, gx) and np.array_equal(oy, gy), ("luma", model, x, y, w, h, mv)
+        if w >= 8 or h >= 8:
+            cw, ch = max(w // 2, 2), max(h // 2, 2)
+            ox, oy = o.reproject((x // 2, y // 2), (cw, ch), mv, model, comp=1, chroma_fmt=1)
+            gx, gy = g.reproject((x // 2, y // 2), (cw, ch), mv, model, comp=1, chroma_fmt=1)
+            assert np.array_equal(ox, gx) and np.array_equal(oy, gy), ("chroma", model, x, y, w, h, mv)
+        n += len(ox)
+    assert n > 0
+
+
+def test_reproject_zero_epipole_nan_path(env):
+    """Quirk Q4: default (0,0,0) epipole -> NaN rotation -> 'no motion' via isNaN().select."""
+    o, g, *_ = env
+    Rn = ol.Oracle.rodrigues([0, 0, 0])
+    o.set_rotation(ol.GED_CAMPOSE, Rn)
+    try:
+        ox, oy = o.reproject((512, 256), (32, 32), (37, -21), ol.GED_CAMPOSE)
+        gx, gy = g.reproject((512, 256), (32, 32), (37, -21), mm.GED_CAMPOSE, rot_slot=5)  # slot 5 still default
+        assert np.array_equal(ox, gx) and np.array_equal(oy, gy)
+        exp_x = (np.arange(8) * 4 + 512) * 16
+        assert np.array_equal(gx.reshape(8, 8, order="F")[0], exp_x)
+    finally:
+        o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(EPIPOLE))
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4, 5, 6, 8, 10])
+@pytest.mark.parametrize("bi", [False, True])
+def test_mc_block_all_components(env, model, bi):
+    """xPredInterBlkMM / xPredInterBlk: Y, Cb, Cr; uni (clipped) and bi (14-bit intermediate)."""
+    o, g, planes, ref, cur = env
+    rng = np.random.default_rng(200 + model + (50 if bi else 0))
+    for it in range(24):
+        w, h = SIZES[it % len(SIZES)]
+        x, y = rand_block(rng, w, h)
+        mv = (int(rng.integers(-500, 500)), int(rng.integers(-300, 300)))
+        if it % 6 == 0: mv = ((mv[0] // 16) * 16, (mv[1] // 16) * 16)   # integer MV -> copy / single-pass cases
+        if it % 7 == 0: mv = ((mv[0] // 16) * 16, mv[1])
+        if it % 8 == 0: mv = (mv[0], (mv[1] // 16) * 16)
+        if model == 0:
+            x = min(max(x, 64), W - w - 64); y = min(max(y, 64), H - h - 64)
+            a = o.mc_block_classic(planes[0], 0, 1, (x, y), (w, h), mv, bi)
+        else:
+            a = o.mc_block(planes[0], 0, 1, (x, y), (w, h), mv, model, bi)
+        b = g.mc(0, 0, 1, (x, y), (w, h), mv, model, bi=bi)
+        assert np.array_equal(a, b), ("Y", model, bi, x, y, w, h, mv)
+        if w >= 8 and h >= 8:
+            for comp in (1, 2):
+                cp, cs = (x // 2, y // 2), (w // 2, h // 2)
+                if model == 0:
+                    a = o.mc_block_classic(planes[comp], comp, 1, cp, cs, mv, bi)
+                else:
+                    a = o.mc_block(planes[comp], comp, 1, cp, cs, mv, model, bi)
+                b = g.mc(0, comp, 1, cp, cs, mv, model, bi=bi)
+                assert np.array_equal(a, b), ("C", comp, model, bi, x, y, w, h, mv)
+
+
+def test_mc_oob_zero_fill_both_rules(env):
+    """Quirk Q2: MC uses +-maxCU slack, ME uses none; OOB sub-blocks are zero-filled."""
+    o, g, planes, ref, cur = env
+    seen_zero = False
+    for oob in (ol.OOB_PRED, ol.OOB_ME):
+        for (x, y, mv) in [(0, 0, (-40 * 16, -30 * 16)), (W - 64, H - 64, (90 * 16, 70 * 16)), (0, 512, (-200 * 16, 0)),
+                           (W - 32, 0, (150 * 16 + 5, -140 * 16 - 3))]:
+            for model in (ol.T3D, ol.MPA_LR, ol.ROT):
+                a = o.mc_block(planes[0], 0, 1, (x, y), (32, 32), mv, model, False, oob=oob)
+                b = g.mc(0, 0, 1, (x, y), (32, 32), mv, model, oob=oob)
+                assert np.array_equal(a, b), (oob, x, y, mv, model)
+                seen_zero |= bool((a == 0).all(axis=None) or (a[:4, :4] == 0).all())
+    assert seen_zero
+
+
+def _blocks_for(sizes, rng, model_cycle, cands, ref_slot=0):
+    blocks = np.zeros(len(sizes), dtype=mm.api.BLOCK_DTYPE)
+    mvs = np.zeros(len(sizes) * cands, dtype=mm.api.MV_DTYPE)
+    for i, (w, h) in enumerate(sizes):
+        x, y = rand_block(rng, w, h)
+        blocks[i] = (x, y, w, h, model_cycle[i % len(model_cycle)], ref_slot, 0, i * cands, cands, x, y, 0)
+    return blocks, mvs
+
+
+@pytest.mark.parametrize("dist,sub_shift", [(ol.DIST_SAD, 0), (ol.DIST_SAD, 1), (ol.DIST_HAD, 0)])
+@pytest.mark.parametrize("prec", [4, 2])
+def test_me_batch_matches_oracle(env, dist, sub_shift, prec):
+    """xMVReprojectionInterpolation + distFunc for batches of candidates, every block size and model."""
+    o, g, planes, ref, cur = env
+    rng = np.random.default_rng(300 + dist * 10 + sub_shift + prec)
+    g.set_org(cur[0])
+    sizes = SIZES * 2
+    models = [1, 2, 3, 4, 5, 6, 10, 7, 9, 0]
+    cands = 9
+    blocks, mvs = _blocks_for(sizes, rng, models, cands)
+    scale = 1 if prec == 4 else 4
+    mvs["hor"] = rng.integers(-48 * scale, 48 * scale, size=len(mvs))
+    mvs["ver"] = rng.integers(-32 * scale, 32 * scale, size=len(mvs))
+    mvs["hor"][::9] = 0; mvs["ver"][::9] = 0
+    for b in blocks:  # classic candidates must stay inside the padded plane
+        if b["model"] == 0:
+            b["x"] = b["org_x"] = min(max(b["x"], 64), W - b["w"] - 64)
+            b["y"] = b["org_y"] = min(max(b["y"], 64), H - b["h"] - 64)
+    got = g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=dist, sub_shift=sub_shift)
+    for b in blocks:
+        sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+        org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+        m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+        exp = o.me_block(planes[0], org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                         mv_prec_shift=prec, dist=dist, sub_shift=sub_shift, had_mode=ol.HAD_SIMD)
+        assert np.array_equal(exp, got[sl]), (dict(zip(b.dtype.names, b.tolist())), exp, got[sl])
+
+
+def test_me_batch_scalar_had_mode(oracle_2k):
+    """--SIMD=SCALAR hosts use (int)(sad / sqrt(16*8) * 2); selectable per context."""
+    o = oracle_2k
+    g = mm.MmGpu(W, H, max_refs=1, had_mode=mm.HAD_SCALAR)
+    try:
+        ref = wl.pad_frame(wl.synth_frame(W, H, seed=21), 288, 1)
+        cur = wl.synth_frame(W, H, seed=22)
+        g.set_ref(0, 0, [p.origin for p in ref], [p.stride for p in ref])
+        g.set_org(cur[0])
+        rng = np.random.default_rng(5)
+        sizes = [(16, 8), (8, 16), (32, 8), (8, 4), (4, 8), (64, 16), (16, 4)]
+        blocks, mvs = _blocks_for(sizes, rng, [ol.T3D, ol.MPA_FB], 4)
+        mvs["hor"] = rng.integers(-30, 30, size=len(mvs)); mvs["ver"] = rng.integers(-30, 30, size=len(mvs))
+        got = g.me_batch(blocks, mvs, dist=mm.DIST_HAD)
+        class P: pass
+        pl = P(); pl.origin = ref[0].origin; pl.stride = ref[0].stride
+        for b in blocks:
+            sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+            org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+            m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+            exp = o.me_block(pl, org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                             dist=ol.DIST_HAD, had_mode=ol.HAD_SCALAR)
+            assert np.array_equal(exp, got[sl])
+    finally:
+        g.close()
+
+
+def test_unpadded_upload_extends_border_like_reference(env):
+    """Picture::extendPicBorder on the device: MC through slot 1 (device-padded) == slot 0 (host-padded)."""
+    o, g, planes, ref, cur = env
+    g.set_ref_unpadded(1, 0, [p.inner.copy() for p in ref])
+    rng = np.random.default_rng(9)
+    for (x, y) in [(0, 0), (W - 64, 0), (0, H - 64), (W - 64, H - 64), (1024, 512)]:
+        mv = (int(rng.integers(-1500, 1500)), int(rng.integers(-1500, 1500)))
+        for comp, pos, size in ((0, (x, y), (64, 64)), (1, (x // 2, y // 2), (32, 32)), (2, (x // 2, y // 2), (32, 32))):
+            a = g.mc(0, comp, 1, pos, size, mv, mm.T3D)
+            b = g.mc(1, comp, 1, pos, size, mv, mm.T3D)
+            assert np.array_equal(a, b)
+
+
+def test_add_avg(env):
+    o, g, *_ = env
+    rng = np.random.default_rng(3)
+    for (w, h) in [(8, 4), (16, 16), (128, 64)]:
+        a = rng.integers(-8192, 8191, size=(h, w)).astype(np.int16)
+        b = rng.integers(-8192, 8191, size=(h, w)).astype(np.int16)
+        exp = np.zeros((h, w), dtype=np.int16)
+        ol.lib().orc_add_avg(a.ctypes.data, w, b.ctypes.data, w, exp.ctypes.data, w, w, h, 10, 0, 1023)
+        assert np.array_equal(exp, g.add_avg(a, b))
+
+
+def test_bi_pred_pipeline(env):
+    """xPredInterBi shape: two MM MCs at bi=true + xWeightedAverage == oracle."""
+    o, g, planes, ref, cur = env
+    for model, mv0, mv1 in [(ol.MPA_TB, (35, -18), (-77, 40)), (ol.ROT, (100, 3), (-9, -250))]:
+        a0 = o.mc_block(planes[0], 0, 1, (640, 384), (64, 32), mv0, model, True)
+        a1 = o.mc_block(planes[0], 0, 1, (640, 384), (64, 32), mv1, model, True)
+        exp = np.zeros((32, 64), dtype=np.int16)
+        ol.lib().orc_add_avg(a0.ctypes.data, 64, a1.ctypes.data, 64, exp.ctypes.data, 64, 64, 32, 10, 0, 1023)
+        b0 = g.mc(0, 0, 1, (640, 384), (64, 32), mv0, model, bi=True)
+        b1 = g.mc(0, 0, 1, (640, 384), (64, 32), mv1, model, bi=True)
+        assert np.array_equal(exp, g.add_avg(b0, b1))
+
+
+def test_full_frame_properties(env):
+    """BASELINE-size batch (whole 2048x1024 frame): size-independent properties.
+    (1) distortion of MC(frame, mv=0, identity-at-zero models) against the reference frame itself is 0;
+    (2) SAD(subShift=0) of the fast batch path == SAD recomputed from predictions of the MC batch path;
+    (3) candidate order does not matter (checksum of distortions invariant under permutation)."""
+    import torch
+    o, g, planes, ref, cur = env
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=5, cands_per_block=4, mv_range=32, models=(mm.T3D, mm.ROT, mm.TAN))
+    # (1) org := reference picture, all-zero MVs -> identity models give exact copies -> distortion 0
+    g.set_org(np.ascontiguousarray(ref[0].inner))
+    zero = np.zeros(len(mvs), dtype=mm.api.MV_DTYPE)
+    for dist in (mm.DIST_SAD, mm.DIST_HAD):
+        d = g.me_batch(blocks, zero, mv_prec_shift=prec, dist=dist)
+        # ME rule (InterSearch.cpp:6332): sub-blocks with xPos >= W-4 or yPos >= H-4 are zero-filled (Q2)
+        inner = (blocks["x"] + blocks["w"] < W) & (blocks["y"] + blocks["h"] < H)
+        per_block = d.reshape(len(blocks), -1)
+        assert int(per_block[inner].sum()) == 0
+        assert int(per_block[~inner].sum()) > 0
+    # (2)+(3)
+    g.set_org(cur[0])
+    d1 = g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD)
+    one = blocks.copy(); one["cand_count"] = 1; one["cand_first"] = np.arange(len(one))
+    mv1 = mvs[blocks["cand_first"]]
+    plan = g.plan(one, len(one))
+    dmv = torch.from_numpy(mv1.view(np.int32).reshape(-1, 2).copy()).cuda()
+    dst = torch.zeros((H, W), dtype=torch.int16, device="cuda")
+    g.mc_batch_device(plan, dmv.data_ptr(), dst.data_ptr(), W, mv_prec_shift=prec)
+    g.sync()
+    pred = dst.cpu().numpy()
+    # the MC batch uses the +-maxCU rule, the ME batch the strict rule: compare only where both agree (inside)
+    sad = np.abs(cur[0].astype(np.int64) - pred.astype(np.int64))
+    chk = 0
+    for b in blocks[:400]:
+        s = int(sad[b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]].sum())
+        if 160 <= b["x"] <= W - 300 and 160 <= b["y"] <= H - 300:
+            assert s == int(d1[b["cand_first"]]), b
+            chk += 1
+    assert chk > 20
+    perm = np.random.default_rng(1).permutation(len(blocks))
+    pb = blocks[perm]
+    d2 = g.me_batch(pb, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD)
+    assert np.array_equal(d1, d2)
+    plan.close()

@@ -1,0 +1,122 @@
+"""CPU tests of the PRODUCT's host-compilable code and of the C-ABI library (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NATIVE = os.path.join(ROOT, "tests", "native")
+BUILD = os.path.join(NATIVE, "_build")
+CXXFLAGS = ["-O2", "-std=c++17", "-msse4.1", "-ffp-contract=off", "-fno-builtin"]
+
+
+def _build(src, out, extra):
+    os.makedirs(BUILD, exist_ok=True)
+    deps = [os.path.join(NATIVE, src)] + [os.path.join(ROOT, "vvc-extension-mm_b200", "csrc", f) for f in ("mm_libm.cuh", "mm_map.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++"] + CXXFLAGS + extra + ["-x", "c++", os.path.join(NATIVE, src), "-o", out, "-lm"])
+    return out
+
+
+def test_libm_port_pinned_against_box_libm():
+    """mm_libm.cuh (glibc 2.39 sinf/cosf/tanf/atanf/atan2f/acosf/asinf/roundf restated) == the real libm.
+    Strided here (~8M inputs per function); the exhaustive 2^32 run is tests/golden/libm_pin_exhaustive_r01.log."""
+    exe = _build("libm_pin.cpp", os.path.join(BUILD, "libm_pin"), ["-pthread"])
+    out = subprocess.run([exe, "509", "8"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "total mismatches 0" in out.stdout
+
+
+def test_product_mapping_host_build_equals_oracle():
+    """mm_map.cuh compiled for the host == oracle, all models, luma + chroma, poles/seam/zero-MV cases."""
+    so = _build("map_host.cpp", os.path.join(BUILD, "libmaphost.so"), ["-fPIC", "-shared"])
+    Hn = C.CDLL(so)
+    Hn.mmhost_create.restype = C.c_void_p
+    Hn.mmhost_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+    Hn.mmhost_destroy.argtypes = [C.c_void_p]
+    Hn.mmhost_reproject.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p] * 3
+    import vvc_extension_mm_b200 as mm
+    for (W, Hh) in ((2048, 1024), (4096, 2048), (1280, 640)):
+        o = ol.Oracle(W, Hh)
+        fma = 1  # this box's glibc picks __sinf_fma (checked by test_libm_port_pinned_against_box_libm)
+        h = Hn.mmhost_create(W, Hh, 1.0, 1, fma)
+        rng = np.random.default_rng(W)
+        Rs = {7: mm.rodrigues([1, 0, 0]), 8: mm.rodrigues([0, 1, 0]), 9: mm.rodrigues([0, 0, 1]),
+              10: mm.rodrigues([0.3, -0.5, 0.81])}
+        assert np.array_equal(Rs[10].view(np.uint32), ol.Oracle.rodrigues([0.3, -0.5, 0.81]).view(np.uint32))
+        o.set_rotation(10, Rs[10])
+        sizes = [(8, 4), (4, 8), (8, 8), (16, 8), (8, 16), (16, 16), (32, 8), (64, 64), (128, 128), (4, 16), (64, 4)]
+        bad = tot = 0
+        for it in range(700):
+            w, hh = sizes[rng.integers(len(sizes))]
+            x = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+            y = int(rng.integers(0, (Hh - hh) // 4 + 1)) * 4
+            if it % 7 == 0:
+                y = 0 if it % 2 else Hh - hh
+            if it % 9 == 0:
+                x = 0 if it % 2 else W - w
+            mv = (int(rng.integers(-900, 900)), int(rng.integers(-500, 500)))
+            if it % 11 == 0: mv = (0, 0)
+            if it % 13 == 0: mv = (mv[0], 0)
+            if it % 17 == 0: mv = (0, mv[1])
+            m = int(rng.integers(1, 11))
+            for comp, fmt in ((0, 0), (1, 1)):
+                px, py, pw, ph, cs = (x, y, w, hh, 0) if comp == 0 else (x // 2, y // 2, w // 2, hh // 2, 1)
+                ox, oy = o.reproject((px, py), (pw, ph), mv, m, comp, fmt)
+                gx = np.zeros_like(ox); gy = np.zeros_like(oy)
+                R = Rs.get(m, np.zeros(9, np.float32)).astype(np.float32)
+                Hn.mmhost_reproject(h, comp, cs, cs, px, py, pw, ph, mv[0], mv[1], m, R.ctypes.data, gx.ctypes.data, gy.ctypes.data)
+                bad += int((ox != gx).sum() + (oy != gy).sum())
+                tot += 2 * len(ox)
+        Hn.mmhost_destroy(h)
+        o.close()
+        assert bad == 0 and tot > 100000
+
+
+def test_abi_library_exports_every_declared_symbol():
+    import vvc_extension_mm_b200 as mm
+    mm.build_library()
+    hdr = open(os.path.join(ROOT, "include", "mmgpu.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|void|const char\*|void\*|uint64_t|float)\s+(mmgpu_[a-z_0-9]+)\(", hdr, re.M)))
+    assert len(declared) >= 20
+    lib = C.CDLL(mm.library_path())
+    for name in declared:
+        assert hasattr(lib, name), "library does not export " + name
+    assert sorted(mm.exported_symbols()) == declared
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product must fail loudly when there is no usable sm_100 device."""
+    import torch
+    import vvc_extension_mm_b200 as mm
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mm.MmGpuError):
+        mm.MmGpu(2048, 1024)
+
+
+def test_host_helpers_match_oracle():
+    import vvc_extension_mm_b200 as mm
+    for e in ([1, 0, 0], [0, 0, 1], [0, 0, -1], [0.2, 0.4, -0.7], [0, 0, 0], [-3.5, 2.0, 1.0]):
+        a, b = mm.rodrigues(e), ol.Oracle.rodrigues(e)
+        nan = np.isnan(a)
+        assert np.array_equal(nan, np.isnan(b))          # NaN sign/payload is irrelevant (isNaN().select)
+        assert np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+    for v in (0, 1, -1, 1 << 24, -(1 << 24) + 5, 12345678):
+        assert mm.fixed_to_float(v, 24) == float(ol.lib().orc_fixed_to_float(v, 24))
+
+
+def test_workload_partition_covers_frame():
+    from vvc_extension_mm_b200 import workload as wl
+    b, mv, prec = wl.frame_batch(2048, 1024, seed=3, cands_per_block=2)
+    cover = np.zeros((1024, 2048), dtype=np.int32)
+    for x, y, w, h in zip(b["x"], b["y"], b["w"], b["h"]):
+        cover[y:y + h, x:x + w] += 1
+    assert (cover == 1).all()
+    rows = [wl.shard_ctu_rows(8, r, 4) for r in range(4)]
+    assert sorted(sum(rows, [])) == list(range(8))

@@ -1,0 +1,280 @@
+"""ctypes mirror of include/mmgpu.h.
+
+Names follow the reference: blocks (pu.blocks[compID]), Mv in 1/16 pel, MotionModelID values,
+reference slots holding Picture::getRecoBuf planes with margins.
+"""
+import ctypes as C
+import os
+import numpy as np
+from .build import library_path
+
+CLASSIC, MPA_FB, MPA_LR, MPA_TB, TAN, T3D, ROT, GED_X, GED_Y, GED_Z, GED_CAMPOSE = range(11)
+MODEL_NAMES = {0: "CLASSIC", 1: "MPA_FB", 2: "MPA_LR", 3: "MPA_TB", 4: "TAN", 5: "3DT", 6: "ROT", 7: "GED_X",
+               8: "GED_Y", 9: "GED_Z", 10: "GED_CAMPOSE"}
+OOB_PRED, OOB_ME = 0, 1
+DIST_SAD, DIST_HAD = 0, 1
+HAD_SCALAR, HAD_SIMD = 0, 1
+
+EXPORTS = [
+    "mmgpu_create", "mmgpu_destroy", "mmgpu_last_error", "mmgpu_sync", "mmgpu_stream", "mmgpu_launch_count",
+    "mmgpu_kernel_timing_enable", "mmgpu_kernel_timing_read",
+    "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
+    "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
+    "mmgpu_me_batch", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
+    "mmgpu_mc_batch_device",
+]
+
+
+class MmGpuError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("pic_w", C.c_int32), ("pic_h", C.c_int32), ("chroma_fmt", C.c_int32), ("bit_depth", C.c_int32),
+                ("max_cu", C.c_int32), ("margin", C.c_int32), ("offset4x4", C.c_float), ("ged_flavor", C.c_int32),
+                ("max_refs", C.c_int32), ("device", C.c_int32), ("libm_fma", C.c_int32), ("had_mode", C.c_int32)]
+
+
+class Mv(C.Structure):
+    _fields_ = [("hor", C.c_int32), ("ver", C.c_int32)]
+
+
+class Block(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("model", C.c_int32),
+                ("ref_slot", C.c_int32), ("rot_slot", C.c_int32), ("cand_first", C.c_int32), ("cand_count", C.c_int32),
+                ("org_x", C.c_int32), ("org_y", C.c_int32), ("reserved", C.c_int32)]
+
+
+BLOCK_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("model", "<i4"), ("ref_slot", "<i4"),
+                        ("rot_slot", "<i4"), ("cand_first", "<i4"), ("cand_count", "<i4"), ("org_x", "<i4"),
+                        ("org_y", "<i4"), ("reserved", "<i4")])
+MV_DTYPE = np.dtype([("hor", "<i4"), ("ver", "<i4")])
+
+_lib = None
+
+
+def load_library():
+    """Load libmmgpu.so; fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise MmGpuError("libmmgpu.so is not built: run __graft_entry__.build() (nvcc, sm_100a)")
+    L = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    L.mmgpu_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.mmgpu_destroy.argtypes = [vp]
+    L.mmgpu_last_error.restype = C.c_char_p
+    L.mmgpu_last_error.argtypes = [vp]
+    L.mmgpu_sync.argtypes = [vp]
+    L.mmgpu_stream.restype = vp
+    L.mmgpu_stream.argtypes = [vp]
+    L.mmgpu_launch_count.restype = u64
+    L.mmgpu_launch_count.argtypes = [vp]
+    L.mmgpu_kernel_timing_enable.argtypes = [vp, i32]
+    L.mmgpu_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    for f in (L.mmgpu_set_ref, L.mmgpu_set_ref_device, L.mmgpu_set_ref_unpadded):
+        f.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.mmgpu_rodrigues.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.mmgpu_fixed_to_float.restype = C.c_float
+    L.mmgpu_fixed_to_float.argtypes = [C.c_int32, C.c_int32]
+    L.mmgpu_set_rotation.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.mmgpu_reproject.argtypes = [vp, i32, i32, i32, i32, i32, i32, Mv, i32, i32, vp, vp]
+    L.mmgpu_mc.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, Mv, i32, i32, i32, i32, i32, i32, vp, i32]
+    L.mmgpu_add_avg.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32]
+    L.mmgpu_set_org.argtypes = [vp, vp, i32, i32, i32]
+    L.mmgpu_set_org_device.argtypes = [vp, vp, i32, i32, i32]
+    L.mmgpu_me_batch.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    L.mmgpu_plan_create.argtypes = [vp, i32, vp, i32, C.POINTER(vp)]
+    L.mmgpu_plan_destroy.argtypes = [vp]
+    L.mmgpu_me_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.mmgpu_plan_samples.restype = u64
+    L.mmgpu_plan_samples.argtypes = [vp]
+    L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """Names include/mmgpu.h declares that the loaded library really exports."""
+    L = load_library()
+    return [n for n in EXPORTS if hasattr(L, n)]
+
+
+def rodrigues(epipole):
+    """GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46): epipole -> row-major 3x3."""
+    L = load_library()
+    e = (C.c_float * 3)(*[float(v) for v in epipole])
+    r = (C.c_float * 9)()
+    L.mmgpu_rodrigues(e, r)
+    return np.array(list(r), dtype=np.float32)
+
+
+def fixed_to_float(fixed, precision=24):
+    return float(load_library().mmgpu_fixed_to_float(int(fixed), int(precision)))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+class MmPlan:
+    def __init__(self, gpu, handle, n_blocks, n_cands):
+        self.gpu, self.h, self.n_blocks, self.n_cands = gpu, handle, n_blocks, n_cands
+
+    @property
+    def samples(self):
+        return int(self.gpu.L.mmgpu_plan_samples(self.h))
+
+    def close(self):
+        if self.h:
+            self.gpu.L.mmgpu_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MmGpu:
+    """One context per InterPrediction / InterSearch instance (MVReprojection::init on the device)."""
+
+    def __init__(self, pic_w, pic_h, chroma_fmt=1, bit_depth=10, max_cu=128, margin=288, offset4x4=1.0, ged_flavor=1,
+                 max_refs=4, device=0, libm_fma=-1, had_mode=-1):
+        self.L = load_library()
+        self.cfg = Config(pic_w, pic_h, chroma_fmt, bit_depth, max_cu, margin, offset4x4, ged_flavor, max_refs, device,
+                          libm_fma, had_mode)
+        h = C.c_void_p()
+        rc = self.L.mmgpu_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0:
+            raise MmGpuError("mmgpu_create failed (%d): %s" % (rc, self.L.mmgpu_last_error(None).decode()))
+        self.h = h
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mmgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise MmGpuError("mmgpu error %d: %s" % (rc, self.L.mmgpu_last_error(self.h).decode()))
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def sync(self):
+        self._chk(self.L.mmgpu_sync(self.h))
+
+    @property
+    def stream(self):
+        return int(self.L.mmgpu_stream(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.mmgpu_launch_count(self.h))
+
+    def kernel_timing(self, on=True):
+        self._chk(self.L.mmgpu_kernel_timing_enable(self.h, int(on)))
+
+    def kernel_timing_read(self):
+        """(total device ms of k_me launches since the last read, number of launches)"""
+        ms, n = C.c_double(), C.c_uint64()
+        self._chk(self.L.mmgpu_kernel_timing_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
+    # -- reference pictures --------------------------------------------------------------------
+    def _planes(self, origins, strides):
+        n = len(origins)
+        p = (C.c_void_p * 3)(*([_ptr(o) for o in origins] + [None] * (3 - n)))
+        s = (C.c_int32 * 3)(*(list(strides) + [0] * (3 - n)))
+        return p, s
+
+    def set_ref(self, slot, poc, origins, strides):
+        """origins[c]: HOST address of sample (0,0) of component c (margins around it are uploaded)."""
+        p, s = self._planes(origins, strides)
+        self._chk(self.L.mmgpu_set_ref(self.h, slot, poc, p, s))
+
+    def set_ref_device(self, slot, poc, origins, strides, keep=None):
+        p, s = self._planes(origins, strides)
+        self._keep[("ref", slot)] = keep
+        self._chk(self.L.mmgpu_set_ref_device(self.h, slot, poc, p, s))
+
+    def set_ref_unpadded(self, slot, poc, planes):
+        """planes: list of 2-D int16 numpy arrays without margins; padding happens on the device."""
+        p, s = self._planes([a.ctypes.data for a in planes], [a.strides[0] // 2 for a in planes])
+        self._chk(self.L.mmgpu_set_ref_unpadded(self.h, slot, poc, p, s))
+
+    def set_rotation(self, rot_slot, R):
+        r = (C.c_float * 9)(*[float(v) for v in R])
+        self._chk(self.L.mmgpu_set_rotation(self.h, rot_slot, r))
+
+    # -- a1 ------------------------------------------------------------------------------------
+    def reproject(self, pos, size, mv, model, comp=0, chroma_fmt=0, rot_slot=0):
+        sx = 1 if (comp and chroma_fmt in (1, 2)) else 0
+        sy = 1 if (comp and chroma_fmt == 1) else 0
+        n = (size[1] // (4 >> sy)) * (size[0] // (4 >> sx))
+        ox = np.zeros(n, dtype=np.int32)
+        oy = np.zeros(n, dtype=np.int32)
+        self._chk(self.L.mmgpu_reproject(self.h, comp, chroma_fmt, pos[0], pos[1], size[0], size[1], Mv(mv[0], mv[1]),
+                                         model, rot_slot, ox.ctypes.data, oy.ctypes.data))
+        return ox, oy
+
+    # -- a5/a6/a8 ------------------------------------------------------------------------------
+    def mc(self, ref_slot, comp, chroma_fmt, pos, size, mv, model, rot_slot=0, bi=False, clp=(0, 1023), oob=OOB_PRED):
+        dst = np.zeros((size[1], size[0]), dtype=np.int16)
+        self._chk(self.L.mmgpu_mc(self.h, ref_slot, comp, chroma_fmt, pos[0], pos[1], size[0], size[1], Mv(mv[0], mv[1]),
+                                  model, rot_slot, int(bi), clp[0], clp[1], oob, dst.ctypes.data, size[0]))
+        return dst
+
+    def add_avg(self, src0, src1, clp=(0, 1023)):
+        h, w = src0.shape
+        dst = np.zeros((h, w), dtype=np.int16)
+        self._chk(self.L.mmgpu_add_avg(self.h, src0.ctypes.data, src0.strides[0] // 2, src1.ctypes.data,
+                                       src1.strides[0] // 2, dst.ctypes.data, w, w, h, clp[0], clp[1]))
+        return dst
+
+    # -- distortion ----------------------------------------------------------------------------
+    def set_org(self, org):
+        """org: 2-D int16 numpy array (pcPatternKey block or the whole current picture)."""
+        self._keep["org"] = org
+        self._chk(self.L.mmgpu_set_org(self.h, org.ctypes.data, org.strides[0] // 2, org.shape[1], org.shape[0]))
+
+    def set_org_device(self, ptr, stride, w, h, keep=None):
+        self._keep["org"] = keep
+        self._chk(self.L.mmgpu_set_org_device(self.h, ptr, stride, w, h))
+
+    def me_batch(self, blocks, mvs, mv_prec_shift=4, dist=DIST_SAD, sub_shift=0, clp=(0, 1023), out=None):
+        """blocks: numpy array of BLOCK_DTYPE; mvs: numpy array of MV_DTYPE -> uint64 distortions."""
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        mvs = np.ascontiguousarray(mvs, dtype=MV_DTYPE)
+        if out is None:
+            out = np.zeros(len(mvs), dtype=np.uint64)
+        self._chk(self.L.mmgpu_me_batch(self.h, len(blocks), blocks.ctypes.data, len(mvs), mvs.ctypes.data, mv_prec_shift,
+                                        dist, sub_shift, clp[0], clp[1], out.ctypes.data))
+        return out
+
+    def plan(self, blocks, n_cands):
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        h = C.c_void_p()
+        self._chk(self.L.mmgpu_plan_create(self.h, len(blocks), blocks.ctypes.data, n_cands, C.byref(h)))
+        return MmPlan(self, h, len(blocks), n_cands)
+
+    def me_batch_device(self, plan, d_mvs, d_dist, mv_prec_shift=4, dist=DIST_SAD, sub_shift=0, clp=(0, 1023)):
+        self._chk(self.L.mmgpu_me_batch_device(self.h, plan.h, _ptr(d_mvs), mv_prec_shift, dist, sub_shift, clp[0],
+                                               clp[1], _ptr(d_dist)))
+
+    def mc_batch_device(self, plan, d_mvs, d_dst, dst_stride, mv_prec_shift=4, clp=(0, 1023)):
+        self._chk(self.L.mmgpu_mc_batch_device(self.h, plan.h, _ptr(d_mvs), mv_prec_shift, clp[0], clp[1], _ptr(d_dst),
+                                               dst_stride))

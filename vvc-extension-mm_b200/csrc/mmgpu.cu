@@ -53,6 +53,12 @@ struct mmgpu_ctx
   size_t capDist;
   int16_t* dTmp;  // small device buffers for mmgpu_mc / reproject / add_avg
   size_t capTmp;
+  // optional CUDA-event timing of k_me
+  bool timing;
+  std::vector<cudaEvent_t> evPool;   // start/stop pairs
+  size_t evUsed;
+  double evAccumMs;
+  uint64_t evAccumN;
 };
 
 static std::string g_createErr;
@@ -171,6 +177,10 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     ctx->cfg.libm_fma = (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
   }
   ctx->launches = 0;
+  ctx->timing = false;
+  ctx->evUsed = 0;
+  ctx->evAccumMs = 0;
+  ctx->evAccumN = 0;
   MmGeom& g = ctx->g;
   g.picW = (float)cfg->pic_w;
   g.picH = (float)cfg->pic_h;
@@ -245,6 +255,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dMvs);
   cudaFree(ctx->dDist);
   cudaFree(ctx->dTmp);
+  for (auto e : ctx->evPool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -255,6 +266,56 @@ extern "C" int mmgpu_sync(mmgpu_ctx* ctx)
   CU(cudaStreamSynchronize(ctx->stream));
   return MMGPU_OK;
 }
+static int drainTiming(mmgpu_ctx* ctx)
+{
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i + 1 < ctx->evUsed; i += 2)
+  {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->evPool[i], ctx->evPool[i + 1]));
+    ctx->evAccumMs += ms;
+    ctx->evAccumN++;
+  }
+  ctx->evUsed = 0;
+  return MMGPU_OK;
+}
+extern "C" int mmgpu_kernel_timing_enable(mmgpu_ctx* ctx, int on)
+{
+  if (!ctx) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  int rc = drainTiming(ctx);
+  if (rc) return rc;
+  ctx->timing = on != 0;
+  ctx->evAccumMs = 0;
+  ctx->evAccumN = 0;
+  return MMGPU_OK;
+}
+extern "C" int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* total_ms, uint64_t* launches)
+{
+  if (!ctx || !total_ms || !launches) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  int rc = drainTiming(ctx);
+  if (rc) return rc;
+  *total_ms = ctx->evAccumMs;
+  *launches = ctx->evAccumN;
+  ctx->evAccumMs = 0;
+  ctx->evAccumN = 0;
+  return MMGPU_OK;
+}
+static int timingEvent(mmgpu_ctx* ctx)
+{
+  if (!ctx->timing) return MMGPU_OK;
+  if (ctx->evUsed >= 4096) { int rc = drainTiming(ctx); if (rc) return rc; }
+  if (ctx->evUsed >= ctx->evPool.size())
+  {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    ctx->evPool.push_back(e);
+  }
+  CU(cudaEventRecord(ctx->evPool[ctx->evUsed++], ctx->stream));
+  return MMGPU_OK;
+}
+
 extern "C" void* mmgpu_stream(mmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t mmgpu_launch_count(const mmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -600,17 +661,21 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
                                                                    mv_prec_shift, ctx->dRot, plan->nCands, plan->dCands);
   ctx->launches++;
   const int grid = (plan->nItems + 3) / 4;
+  int rc;
   if (mode == MM_MODE_DIST)
   {
     P.oobMode = MMGPU_OOB_ME;
     CU(cudaMemsetAsync(d_dist, 0, sizeof(unsigned long long) * plan->nCands, ctx->stream));
+    if ((rc = timingEvent(ctx))) return rc;
     k_me<MM_MODE_DIST><<<grid, 128, 0, ctx->stream>>>(P);
   }
   else
   {
     P.oobMode = MMGPU_OOB_PRED;
+    if ((rc = timingEvent(ctx))) return rc;
     k_me<MM_MODE_PRED><<<grid, 128, 0, ctx->stream>>>(P);
   }
+  if ((rc = timingEvent(ctx))) return rc;
   ctx->launches++;
   CU(cudaGetLastError());
   return MMGPU_OK;
