@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py -- multi-model MC + SATD throughput of the B200 path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU arm (oracle port, all host threads)
+
+A "step" is one pass of the hot path over one frame-wide batch: every block of a 2048x1024 ERP frame
+(mixed VVC partition) x 16 candidate MVs, per block: map (MPA_FB/LR/TB, GED_CAMPOSE epipole (1,0,0), ROT)
+-> 8-tap separable interpolation -> Hadamard SATD against the original.  Synthetic frames, 10 bit, 4:2:0.
+`value`  : luma sample-candidates/s with blocks, MVs, references and originals resident in HBM.
+`e2e`    : the same through the host C ABI (mmgpu_set_org + mmgpu_me_batch) from pinned host buffers,
+           H2D of the original picture / blocks / MVs and D2H of the distortions inside the timed region.
+N > 1    : weak scaling -- each step covers N frames; rank r evaluates CTU rows r, r+N, ... of all N frames;
+           the reference picture of frame f is NCCL-broadcast from rank f inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, CTU = 2048, 1024, 128
+CANDS = 16
+POOL = 32            # synthetic frames resident per GPU (references cycle through them: 270 MB > L2)
+MV_RANGE = 64
+EPIPOLE = (1.0, 0.0, 0.0)
+WORKLOAD = "2048x1024 ERP frame batch (Broadway shape, configs[1]): MPA_FB/LR/TB+GED_CAMPOSE+ROT, mixed 8x4..128x128 " \
+           "partition, 16 integer-pel candidates/block, MC + Hadamard SATD (HadamardME)"
+
+
+def models():
+    import vvc_extension_mm_b200 as mm
+    return (mm.MPA_FB, mm.MPA_LR, mm.MPA_TB, mm.GED_CAMPOSE, mm.ROT)
+
+
+def algorithmic_bytes(blocks):
+    """per block 2WH (original) + per candidate 2WH (reference samples) + 8 (distortion)."""
+    wh = blocks["w"].astype(np.int64) * blocks["h"].astype(np.int64)
+    return int((2 * wh + blocks["cand_count"].astype(np.int64) * (2 * wh + 8)).sum())
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_throughput(n_threads, budget_s, seed=1):
+    """Reference CPU arm / cpu_baseline: the oracle's xMVReprojectionInterpolation + xGetHADs on the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from vvc_extension_mm_b200 import workload as wl
+    from concurrent.futures import ThreadPoolExecutor
+    o = ol.Oracle(W, H)
+    o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(list(EPIPOLE)))
+    ref = wl.pad_frame(wl.synth_frame(W, H, seed), 288, 1)
+    cur = wl.synth_frame(W, H, seed + 1, shift=(3.0, 1.0))
+
+    class P:
+        pass
+    pl = P()
+    pl.origin, pl.stride = ref[0].origin, ref[0].stride
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=seed, cands_per_block=CANDS, mv_range=MV_RANGE, models=models())
+
+    def run_block(b):
+        sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+        org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+        m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+        o.me_block(pl, org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                   mv_prec_shift=prec, dist=ol.DIST_HAD, had_mode=ol.HAD_SIMD)
+        return int(b["w"]) * int(b["h"]) * int(b["cand_count"])
+
+    # bounded sample: whole blocks of the frame, in order, until the time budget is used (ctypes releases the GIL)
+    t0 = time.perf_counter()
+    done = 0
+    nblk = 0
+    chunk = 64 * n_threads
+    with ThreadPoolExecutor(max_workers=n_threads) as ex:
+        i = 0
+        while time.perf_counter() - t0 < budget_s:
+            part = [blocks[(i + k) % len(blocks)] for k in range(chunk)]
+            done += sum(ex.map(run_block, part))
+            nblk += chunk
+            i += chunk
+    dt = time.perf_counter() - t0
+    return done / dt, dt, nblk, done
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference itself cannot be built on
+    this image (Eigen 3.3.7 is fetched from the network at build time), so this times the oracle port with every
+    host thread it can use; rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, dt, nblk, done = cpu_oracle_throughput(cores, per_step, seed=1 + s)
+        if s >= args.warmup:
+            vals.append((v, dt, done))
+    tot_s = sum(d for _, d, _ in vals)
+    tot_n = sum(n for _, _, n in vals)
+    value = tot_n / tot_s
+    line = {
+        "impl": "reference", "metric": "multi-model MC+SATD luma samples/sec at 2048x1024 ERP", "value": value,
+        "unit": "luma sample-candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference path (reference not buildable: Eigen absent)"},
+        "cpu_baseline": {"value": value, "unit": "luma sample-candidates/s", "cores": cores, "kind": "port",
+                         "sample": "%.1f s of whole blocks of the frame batch per step, %d threads" % (per_step, cores)},
+        "e2e": {"value": value, "unit": "luma sample-candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import vvc_extension_mm_b200 as mm
+    from vvc_extension_mm_b200 import workload as wl
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = world
+    dev = torch.device("cuda", local)
+
+    # ---- resident data -------------------------------------------------------------------------------------
+    gpu = mm.MmGpu(W, H, max_refs=POOL + N, device=local)
+    gpu.set_rotation(0, mm.rodrigues(EPIPOLE))
+    pool_ref, pool_org_h = [], []
+    luma_stride = None
+    for f in range(POOL):
+        planes = wl.pad_frame(wl.synth_frame(W, H, seed=100 + f, shift=(0.37 * f, 0.11 * f)), 288, 1)
+        t = [torch.from_numpy(p.buf).to(dev) for p in planes]
+        pool_ref.append((planes, t))
+        pool_org_h.append(torch.from_numpy(wl.synth_plane(W, H, 5000 + f, shift=(0.37 * f + 2.5, 0.11 * f + 1.0))).pin_memory())
+    pool_org_d = [t.to(dev) for t in pool_org_h]
+
+    def origin_ptrs(planes, tens):
+        return [t.data_ptr() + 2 * (p.my * p.stride + p.mx) for p, t in zip(planes, tens)], [p.stride for p in planes]
+
+    for f in range(POOL):
+        o_, s_ = origin_ptrs(*pool_ref[f])
+        gpu.set_ref_device(f, f, o_, s_, keep=pool_ref[f][1])
+    comm = []
+    if N > 1:  # broadcast landing buffers: slot POOL+f holds the reference of frame f of the current step
+        for f in range(N):
+            tens = [torch.empty_like(t) for t in pool_ref[0][1]]
+            comm.append(tens)
+            o_, s_ = origin_ptrs(pool_ref[0][0], tens)
+            gpu.set_ref_device(POOL + f, f, o_, s_, keep=tens)
+
+    # ---- batch: this rank's CTU rows of the N frames of a step ------------------------------------------------
+    rows = wl.shard_ctu_rows(H // CTU, rank, N)
+    blocks_l, mvs_l = [], []
+    for f in range(N):
+        b, m, prec = wl.frame_batch(W, H, seed=1 + f, cands_per_block=CANDS, mv_range=MV_RANGE, models=models(),
+                                    ref_slot=(POOL + f) if N > 1 else 0, ctu_rows=rows)
+        b["cand_first"] += sum(len(x) for x in mvs_l)
+        b["org_y"] += f * H
+        blocks_l.append(b)
+        mvs_l.append(m)
+    blocks = np.concatenate(blocks_l)
+    mvs = np.concatenate(mvs_l)
+    n_cands = len(mvs)
+    samples_rank = int((blocks["w"].astype(np.int64) * blocks["h"] * blocks["cand_count"]).sum())
+    alg_bytes_rank = algorithmic_bytes(blocks)
+    d_mvs = torch.from_numpy(mvs.view(np.int32).reshape(-1, 2).copy()).to(dev)
+    d_dist = torch.zeros(n_cands, dtype=torch.int64, device=dev)
+    d_org = torch.empty((N * H, W), dtype=torch.int16, device=dev)
+    h_org = torch.empty((N * H, W), dtype=torch.int16).pin_memory()
+    h_blocks = torch.from_numpy(blocks.view(np.int32).reshape(-1, 12).copy()).pin_memory()
+    h_mvs = torch.from_numpy(mvs.view(np.int32).reshape(-1, 2).copy()).pin_memory()
+    h_dist = torch.zeros(n_cands, dtype=torch.int64).pin_memory()
+    gpu.set_org_device(d_org.data_ptr(), W, W, N * H, keep=d_org)
+    plans = {}
+    stream = torch.cuda.ExternalStream(gpu.stream, device=dev)
+
+    def step_plan(s):
+        """N == 1: the reference slot changes every step (pool cycling) -> one plan per pool slot."""
+        slot = s % POOL
+        if N > 1:
+            slot = -1
+        if slot not in plans:
+            b = blocks.copy()
+            if N == 1:
+                b["ref_slot"] = slot
+            plans[slot] = (gpu.plan(b, n_cands), b)
+        return plans[slot]
+
+    def load_orgs(s, tgt, src_pool):
+        for f in range(N):
+            tgt[f * H:(f + 1) * H].copy_(src_pool[(s * N + f + 1) % POOL], non_blocking=True)
+
+    def device_step(s):
+        with torch.cuda.stream(stream):
+            if N > 1:
+                for f in range(N):
+                    src = pool_ref[(s * N + f) % POOL][1]
+                    for c in range(3):
+                        if rank == f:
+                            comm[f][c].copy_(src[c], non_blocking=True)
+                        dist.broadcast(comm[f][c], src=f)
+            plan, _ = step_plan(s)
+            gpu.me_batch_device(plan, d_mvs.data_ptr(), d_dist.data_ptr(), mv_prec_shift=prec, dist=mm.DIST_HAD)
+
+    def e2e_step(s):
+        # host-facing call: original picture, blocks, MVs from pinned host memory; distortions back to the host
+        with torch.cuda.stream(stream):
+            if N > 1:
+                for f in range(N):
+                    src = pool_ref[(s * N + f) % POOL][1]
+                    for c in range(3):
+                        if rank == f:
+                            comm[f][c].copy_(src[c], non_blocking=True)
+                        dist.broadcast(comm[f][c], src=f)
+        _, b = step_plan(s)
+        hb = h_blocks.numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
+        hb["ref_slot"] = b["ref_slot"]
+        gpu.set_org(h_org.numpy())
+        gpu.me_batch(hb, h_mvs.numpy().view(mm.api.MV_DTYPE).reshape(-1), mv_prec_shift=prec, dist=mm.DIST_HAD,
+                     out=h_dist.numpy().view(np.uint64))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k, prep):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for s in range(k):
+            prep(s)
+            fn(s)
+        ev1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1000.0
+        return ev0.elapsed_time(ev1), wall
+
+    # org pictures of a step are copied into the contiguous N*H org plane outside the device timing for `value`
+    # (resident in HBM when the step starts) and live in pinned host memory for e2e.
+    with torch.cuda.stream(stream):
+        load_orgs(0, d_org, pool_org_d)
+    for f in range(N):
+        h_org[f * H:(f + 1) * H].copy_(pool_org_h[(f + 1) % POOL])
+
+    for s in range(args.warmup):
+        device_step(s)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    gpu.kernel_timing(True)
+    launches0 = gpu.launch_count
+    dev_ms, _ = timed(device_step, args.steps, lambda s: None)
+    launches = gpu.launch_count - launches0
+    k_ms, k_n = gpu.kernel_timing_read()
+    gpu.kernel_timing(False)
+    clocks = sampler.stop()
+    for s in range(2):
+        e2e_step(s)
+    e2e_dev_ms, e2e_wall_ms = timed(e2e_step, args.steps, lambda s: None)
+    e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
+
+    t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, k_ms = float(tmax[0]), float(tmax[1]), float(tmax[4])
+        samples_all, bytes_all = float(tsum[2]), float(tsum[3])
+    else:
+        samples_all, bytes_all = float(samples_rank), float(alg_bytes_rank)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        value = samples_all * args.steps / (dev_ms / 1000.0)
+        e2e_value = samples_all * args.steps / (e2e_ms / 1000.0)
+        k_avg_ms = k_ms / max(1, k_n)
+        achieved = (alg_bytes_rank / 1e9) / (k_avg_ms / 1000.0) if k_avg_ms > 0 else 0.0
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, dt, nblk, done = cpu_oracle_throughput(1, args.cpu_budget)
+            cpu = {"value": v, "unit": "luma sample-candidates/s", "cores": 1, "kind": "port",
+                   "sample": "%d whole blocks (%.2e sample-candidates) of the same frame batch, %.1f s, oracle port, 1 thread" % (nblk, done, dt)}
+        h2d = int(h_org.numel() * 2 + h_blocks.numel() * 4 + h_mvs.numel() * 4)
+        line = {
+            "metric": "multi-model MC+SATD luma samples/sec at 2048x1024 ERP", "value": value,
+            "unit": "luma sample-candidates/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": N, "blocks_per_rank": int(len(blocks)),
+                       "candidates_per_rank": int(n_cands), "sample_candidates_per_step": samples_all,
+                       "l2": "references cycle through %d resident frames (%.0f MB of luma planes > 126 MB L2)" % (POOL, POOL * 8.4),
+                       "parallelism": "ctu-rows x%d, ncclBroadcast of reference planes per frame" % N if N > 1 else "1 gpu"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_me<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
+                         "algorithmic_bytes_per_launch": alg_bytes_rank,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "luma sample-candidates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(h_dist.numel() * 8), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
