@@ -31,7 +31,8 @@ extern "C" void* mmhost_create(int picW, int picH, float off, int gedModulated, 
       {
         const bool pk = ((long)col * g.rows4 + row) < (n & ~3L);
         float PX, PY; bool v;
-        mm_mpa_to_perspective(g, m + 1, (float)(4 * col) + off, (float)(4 * row) + off, pk, &PX, &PY, &v);
+        MmTrig none; none.valid = false; none.st = none.ct = none.sp = none.cp = 0.f;
+        mm_mpa_to_perspective(g, m + 1, (float)(4 * col) + off, (float)(4 * row) + off, pk, none, &PX, &PY, &v);
         const long i = (long)row * g.cols4 + col;
         c->px[m][i] = PX; c->py[m][i] = PY; c->vip[m][i] = v;
       }
@@ -64,8 +65,19 @@ extern "C" void mmhost_reproject(void* h, int comp, int csx, int csy, int x, int
         const long ci = (long)((y >> 2) + row) * g.cols4 + ((x >> 2) + col);
         cPX = c->px[model - 1][ci]; cPY = c->py[model - 1][ci]; cV = c->vip[model - 1][ci] != 0;
       }
+      // ERP toSphere table values of the grid cell (same evaluation the device tables hoist); every other
+      // call goes through the direct path so both are exercised
+      MmTrig tr; tr.valid = false; tr.st = tr.ct = tr.sp = tr.cp = 0.f;
+      if (((row + col) & 1) == 0)
+      {
+        float th, ph;
+        mm_erp_angles(g, X, Y, &th, &ph);
+        mm_sincos_pk(th, pk, g.fmaBuild != 0, &tr.st, &tr.ct);
+        mm_sincos_pk(ph, pk, g.fmaBuild != 0, &tr.sp, &tr.cp);
+        tr.valid = true;
+      }
       float MX, MY;
-      mm_model_motion(g, model, isLuma, cand, R, X, Y, pk, cPX, cPY, cV, &MX, &MY);
+      mm_model_motion(g, model, isLuma, cand, R, X, Y, pk, cPX, cPY, cV, tr, &MX, &MY);
       int fx, fy;
       mm_to_fixed(g, X, Y, MX, MY, isLuma ? 0 : csx, isLuma ? 0 : csy, &fx, &fy);
       outX[i] = fx; outY[i] = fy;

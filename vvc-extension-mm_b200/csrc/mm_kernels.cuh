@@ -56,6 +56,8 @@ struct MmParams
   const float* rot;          // [slot][9]; slots 0..2 = GEODESIC_X/Y/Z, 3.. = user slots
   const float2* mpa[3];      // row-major [rows4][cols4] motion-plane coordinates of models 1..3
   const uint8_t* mpaVip[3];
+  const float2* thTab[2];    // [scalar|packet][rows4]: (sin, cos) of theta(4*row + off)   (ERP toSphere hoisted)
+  const float2* phTab[2];    // [scalar|packet][cols4]: (sin, cos) of phi(4*col + off)
   const int16_t* org;
   int32_t orgStride;
   int32_t distKind, subShift, hadMode;
@@ -112,29 +114,29 @@ __device__ __forceinline__ MmSub mm_sub_from_index(int w, int h, int s)
   MmSub r;
   r.cols = w >> 2;
   r.rows = h >> 2;
-  int tw, th;
-  if (w > h && (h & 7) == 0 && (w & 15) == 0) { tw = 4; th = 2; r.tileKind = 2; }
-  else if (w < h && (w & 7) == 0 && (h & 15) == 0) { tw = 2; th = 4; r.tileKind = 2; }
-  else if (w > h && (h & 3) == 0 && (w & 7) == 0) { tw = 2; th = 1; r.tileKind = 3; }
-  else if (w < h && (w & 3) == 0 && (h & 7) == 0) { tw = 1; th = 2; r.tileKind = 3; }
-  else if ((h & 7) == 0 && (w & 7) == 0) { tw = 2; th = 2; r.tileKind = 1; }
-  else { tw = 1; th = 1; r.tileKind = 0; }
-  r.T = tw * th;
-  const int t = s / r.T;
-  r.q = s - t * r.T;
-  const int tpr = r.cols / tw;  // tiles per row
-  const int ty = t / tpr, tx = t - ty * tpr;
-  const int qy = r.q / tw, qx = r.q - qy * tw;
-  r.col = tx * tw + qx;
-  r.row = ty * th + qy;
+  int ltw, lth;  // log2 of the tile size in sub-blocks (block sizes are powers of two)
+  if (w > h && (h & 7) == 0 && (w & 15) == 0) { ltw = 2; lth = 1; r.tileKind = 2; }
+  else if (w < h && (w & 7) == 0 && (h & 15) == 0) { ltw = 1; lth = 2; r.tileKind = 2; }
+  else if (w > h && (h & 3) == 0 && (w & 7) == 0) { ltw = 1; lth = 0; r.tileKind = 3; }
+  else if (w < h && (w & 3) == 0 && (h & 7) == 0) { ltw = 0; lth = 1; r.tileKind = 3; }
+  else if ((h & 7) == 0 && (w & 7) == 0) { ltw = 1; lth = 1; r.tileKind = 1; }
+  else { ltw = 0; lth = 0; r.tileKind = 0; }
+  r.T = 1 << (ltw + lth);
+  const int t = s >> (ltw + lth);
+  r.q = s & (r.T - 1);
+  const int ltpr = (31 - __clz(r.cols)) - ltw;  // log2(tiles per row)
+  const int ty = t >> ltpr, tx = t & ((1 << ltpr) - 1);
+  const int qy = r.q >> ltw, qx = r.q & ((1 << ltw) - 1);
+  r.col = (tx << ltw) + qx;
+  r.row = (ty << lth) + qy;
   return r;
 }
 
 // Position of one sub-block in 1/16 (luma) or 1/32 (chroma 4:2:0) pel: mapping + fixed-point conversion.
 __device__ __forceinline__ void mm_subblock_pos(const MmGeom& g, const float2* const* mpa, const uint8_t* const* mpaVip,
-                                                int model, int comp, int csx, int csy, int posX, int posY, int sizeW,
-                                                int sizeH, const MmCand& c, const float* R, int row, int col, int* fx,
-                                                int* fy)
+                                                const float2* const* thTab, const float2* const* phTab, int model,
+                                                int comp, int csx, int csy, int posX, int posY, int sizeW, int sizeH,
+                                                const MmCand& c, const float* R, int row, int col, int* fx, int* fy)
 {
   const int sbw = 4 >> csx, sbh = 4 >> csy;
   const int rows = sizeH / sbh, cols = sizeW / sbw;
@@ -143,29 +145,44 @@ __device__ __forceinline__ void mm_subblock_pos(const MmGeom& g, const float2* c
   const bool pk = i < (n & ~3);
   const bool isLuma = comp == 0;
   float X, Y;
+  int gc = -1, gr = -1;  // picture grid cell (4x4 luma units) of the sub-block, when it sits on the grid
   if (isLuma)
   {
-    X = MM_FADD((float)(4 * ((posX >> 2) + col)), g.off);
-    Y = MM_FADD((float)(4 * ((posY >> 2) + row)), g.off);
+    gc = (posX >> 2) + col;
+    gr = (posY >> 2) + row;
+    X = MM_FADD((float)(4 * gc), g.off);
+    Y = MM_FADD((float)(4 * gr), g.off);
   }
   else
   {
     // LinSpaced(n, start, end) with step exactly 4 (MVReprojection.cpp:113-120): all values exact
     X = MM_FADD(MM_FADD(MM_FMUL((float)posX, (float)(1 << csx)), g.off), (float)(4 * col));
     Y = MM_FADD(MM_FADD(MM_FMUL((float)posY, (float)(1 << csy)), g.off), (float)(4 * row));
+    const int lx = posX << csx, ly = posY << csy;
+    if (((lx | ly) & 3) == 0) { gc = (lx >> 2) + col; gr = (ly >> 2) + row; }
   }
   float cPX = 0.f, cPY = 0.f;
   bool cVip = false;
-  if (isLuma && model >= MM_MPA_FRONT_BACK && model <= MM_MPA_TOP_BOTTOM)
+  const bool mpaModel = model >= MM_MPA_FRONT_BACK && model <= MM_MPA_TOP_BOTTOM;
+  MmTrig tr;
+  tr.valid = false;
+  tr.st = tr.ct = tr.sp = tr.cp = 0.f;
+  if (isLuma && mpaModel)
   {
-    const int ci = ((posY >> 2) + row) * g.cols4 + ((posX >> 2) + col);
+    const int ci = gr * g.cols4 + gc;
     const float2 p = __ldg(&mpa[model - 1][ci]);
     cPX = p.x;
     cPY = p.y;
     cVip = __ldg(&mpaVip[model - 1][ci]) != 0;
   }
+  else if (gc >= 0 && gc < g.cols4 && gr < g.rows4)
+  {
+    const float2 t = __ldg(&thTab[pk ? 1 : 0][gr]), q = __ldg(&phTab[pk ? 1 : 0][gc]);
+    tr.st = t.x; tr.ct = t.y; tr.sp = q.x; tr.cp = q.y;
+    tr.valid = true;
+  }
   float MX, MY;
-  mm_model_motion(g, model, isLuma, c, R, X, Y, pk, cPX, cPY, cVip, &MX, &MY);
+  mm_model_motion(g, model, isLuma, c, R, X, Y, pk, cPX, cPY, cVip, tr, &MX, &MY);
   mm_to_fixed(g, X, Y, MX, MY, isLuma ? 0 : csx, isLuma ? 0 : csy, fx, fy);
 }
 
@@ -182,9 +199,32 @@ __global__ void k_mpa_cache(MmGeom g, int model, float2* out, uint8_t* vip)
   const bool pk = ((long)col * g.rows4 + row) < (n & ~3L);
   float PX, PY;
   bool v;
-  mm_mpa_to_perspective(g, model, X, Y, pk, &PX, &PY, &v);
+  MmTrig none; none.valid = false; none.st = none.ct = none.sp = none.cp = 0.f;
+  mm_mpa_to_perspective(g, model, X, Y, pk, none, &PX, &PY, &v);
   out[idx] = make_float2(PX, PY);
   vip[idx] = v ? 1 : 0;
+}
+
+// ERP toSphere angles of the picture grid, scalar-libm and Eigen-packet variants (Projection.cpp:213-221,
+// Coordinate.cpp:53-60): tab[0] = scalar, tab[1] = packet; th over rows, ph over columns.
+__global__ void k_trig_tables(MmGeom g, float2* th0, float2* th1, float2* ph0, float2* ph1)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fma = g.fmaBuild != 0;
+  if (i < g.rows4)
+  {
+    float th, ph, s, c;
+    mm_erp_angles(g, 0.0f, MM_FADD((float)(4 * i), g.off), &th, &ph);
+    mm_sincos_pk(th, false, fma, &s, &c); th0[i] = make_float2(s, c);
+    mm_sincos_pk(th, true, fma, &s, &c);  th1[i] = make_float2(s, c);
+  }
+  if (i < g.cols4)
+  {
+    float th, ph, s, c;
+    mm_erp_angles(g, MM_FADD((float)(4 * i), g.off), 0.0f, &th, &ph);
+    mm_sincos_pk(ph, false, fma, &s, &c); ph0[i] = make_float2(s, c);
+    mm_sincos_pk(ph, true, fma, &s, &c);  ph1[i] = make_float2(s, c);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -230,7 +270,7 @@ __global__ void k_reproject(MmParams P, int comp, int csx, int csy, int x, int y
   MmCand c;
   mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
   int fx, fy;
-  mm_subblock_pos(P.g, P.mpa, P.mpaVip, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
+  mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
   outX[i] = fx;
   outY[i] = fy;
 }
@@ -319,7 +359,7 @@ __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy
     const float* R = mm_rot_ptr(P.rot, model, rotSlot);
     MmCand c;
     mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
-    mm_subblock_pos(P.g, P.mpa, P.mpaVip, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
     const int xP = fx >> shH, yP = fy >> shV;
     const int picw = P.picW >> csx, pich = P.picH >> csy;
     const int mcw = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csx);
@@ -520,7 +560,7 @@ __global__ void __launch_bounds__(128) k_me(const MmParams P)
   else
   {
     const float* R = mm_rot_ptr(P.rot, b.model, b.rot_slot);
-    mm_subblock_pos(P.g, P.mpa, P.mpaVip, b.model, 0, 0, 0, b.x, b.y, b.w, b.h, c, R, s.row, s.col, &fx, &fy);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, b.model, 0, 0, 0, b.x, b.y, b.w, b.h, c, R, s.row, s.col, &fx, &fy);
     const int mc = (P.oobMode == MMGPU_OOB_ME) ? 0 : P.maxCU;
     const int xP = fx >> 4, yP = fy >> 4;
     oob = (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4);

@@ -207,26 +207,37 @@ MM_HD void mm_pers_to_sphere_arr(const MmGeom& g, float X, float Y, bool vip, bo
   o[1] = s[0];
   o[2] = mm_negf(s[1]);
 }
-MM_HD void mm_mpa_to_perspective(const MmGeom& g, int model, float X, float Y, bool pk, float* PX, float* PY, bool* vip)
+// ERP toSphere of a grid position; `tr` (optional) = {sin(theta), cos(theta), sin(phi), cos(phi)} of that position
+// taken from the per-picture tables (same functions, same values: the tables only hoist the evaluation).
+struct MmTrig  // table values of one grid position; valid == false -> evaluate directly
+{
+  bool valid;
+  float st, ct, sp, cp;
+};
+MM_HD void mm_erp_to_sphere_grid(const MmGeom& g, float X, float Y, bool pk, const MmTrig& tr, float* o)
+{
+  if (tr.valid)
+  {
+    o[0] = MM_FMUL(tr.st, tr.cp);  // (1*sin(theta))*cos(phi): 1*x is exact
+    o[1] = MM_FMUL(tr.st, tr.sp);
+    o[2] = tr.ct;
+  }
+  else
+  {
+    mm_erp_to_sphere_arr(g, X, Y, pk, o);
+  }
+}
+MM_HD void mm_mpa_to_perspective(const MmGeom& g, int model, float X, float Y, bool pk, const MmTrig& tr, float* PX,
+                                 float* PY, bool* vip)
 {
   float s[3];
-  mm_erp_to_sphere_arr(g, X, Y, pk, s);
+  mm_erp_to_sphere_grid(g, X, Y, pk, tr, s);
   float mx, my, mz;
   if (model == MM_MPA_FRONT_BACK) { mx = s[0]; my = s[1]; mz = s[2]; }
   else if (model == MM_MPA_LEFT_RIGHT) { mx = s[1]; my = mm_negf(s[0]); mz = s[2]; }
   else { mx = mm_negf(s[2]); my = s[1]; mz = s[0]; }
   mm_pers_from_sphere_arr(g, mx, my, mz, pk, PX, PY, vip);
 }
-MM_HD void mm_mpa_to_projection(const MmGeom& g, int model, float PX, float PY, bool vip, bool pk, float* X, float* Y)
-{
-  float m[3], sx, sy, sz;
-  mm_pers_to_sphere_arr(g, PX, PY, vip, pk, m);
-  if (model == MM_MPA_FRONT_BACK) { sx = m[0]; sy = m[1]; sz = m[2]; }
-  else if (model == MM_MPA_LEFT_RIGHT) { sx = mm_negf(m[1]); sy = m[0]; sz = m[2]; }
-  else { sx = m[2]; sy = m[1]; sz = mm_negf(m[0]); }
-  mm_erp_from_sphere_arr(g, sx, sy, sz, X, Y);
-}
-
 // ---- per-candidate scalars -----------------------------------------------------------------------
 // blk = position/size of pu.blocks[compID] (component units, quirk Q1); R = rotation of the GED model.
 MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int posY, int sizeW, int sizeH, int mvHor,
@@ -305,90 +316,100 @@ MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int 
 
 // ---- one sub-block -------------------------------------------------------------------------------
 // X,Y: luma-scale coordinates of the sub-block (4*i + off).  For luma MPA the caller passes the cached
-// motion-plane coordinates (cPX,cPY,cVip) of the picture-wide cache.  Returns moved coordinates (float,
-// before NaN handling).
+// motion-plane coordinates (cPX,cPY,cVip) of the picture-wide cache.  `tr` = optional table values of the
+// original position (see mm_erp_to_sphere_grid).  Returns moved coordinates (float, before NaN handling).
+// Every model ends in EquirectangularProjection::fromSphere of the moved point u: one shared tail.
 MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand& c, const float* R, float X, float Y,
-                           bool pk, float cPX, float cPY, bool cVip, float* MX, float* MY)
+                           bool pk, float cPX, float cPY, bool cVip, const MmTrig& tr, float* MX, float* MY)
 {
   const bool fma = g.fmaBuild != 0;
   *MX = X;
   *MY = Y;
+  float u0, u1, u2;
   if (model >= MM_MPA_FRONT_BACK && model <= MM_MPA_TOP_BOTTOM)
   {
     float PX = cPX, PY = cPY;
     bool vip = cVip;
-    if (!isLuma) mm_mpa_to_perspective(g, model, X, Y, pk, &PX, &PY, &vip);
+    if (!isLuma) mm_mpa_to_perspective(g, model, X, Y, pk, tr, &PX, &PY, &vip);
     const float sgn = vip ? -1.0f : 1.0f;
     const float QX = MM_FADD(PX, MM_FMUL(c.mvX, sgn));
     const float QY = MM_FADD(PY, MM_FMUL(c.mvY, sgn));
-    mm_mpa_to_projection(g, model, QX, QY, vip, pk, MX, MY);
+    float m[3];
+    mm_pers_to_sphere_arr(g, QX, QY, vip, pk, m);  // MotionPlaneAdaptiveMotionModel::toProjection (:163-187)
+    if (model == MM_MPA_FRONT_BACK) { u0 = m[0]; u1 = m[1]; u2 = m[2]; }
+    else if (model == MM_MPA_LEFT_RIGHT) { u0 = mm_negf(m[1]); u1 = m[0]; u2 = m[2]; }
+    else { u0 = m[2]; u1 = m[1]; u2 = mm_negf(m[0]); }
   }
-  else if (model >= MM_GEODESIC_X && model <= MM_GEODESIC_CAMPOSE)
+  else
   {
-    if (!isLuma && c.mvZero) return;
-    float s[3], r, th, ph;
-    mm_erp_to_sphere_arr(g, X, Y, pk, s);
-    const float rx = mm_dot3(R[0], s[0], R[1], s[1], R[2], s[2]);
-    const float ry = mm_dot3(R[3], s[0], R[4], s[1], R[5], s[2]);
-    const float rz = mm_dot3(R[6], s[0], R[7], s[1], R[8], s[2]);
-    mm_arr_cart_to_sph(rx, ry, rz, &r, &th, &ph);
-    float thM;
-    if (!g.gedModulated) thM = MM_FADD(th, c.p[1]);
-    else thM = MM_FADD(th, mm_atanf(MM_FDIV(mm_sinf(th, fma), MM_FSUB(c.p[0], mm_cosf(th, fma)))));
-    const float phM = MM_FADD(ph, c.p[2]);
-    float q[3];
-    mm_arr_sph_to_cart(r, thM, phM, pk, fma, q);
-    const float ux = mm_dot3(R[0], q[0], R[3], q[1], R[6], q[2]);
-    const float uy = mm_dot3(R[1], q[0], R[4], q[1], R[7], q[2]);
-    const float uz = mm_dot3(R[2], q[0], R[5], q[1], R[8], q[2]);
-    mm_erp_from_sphere_arr(g, ux, uy, uz, MX, MY);
-  }
-  else if (model == MM_ROTATIONAL)
-  {
-    if (c.mvZero) return;
+    const bool ged = model >= MM_GEODESIC_X && model <= MM_GEODESIC_CAMPOSE;
+    if (c.mvZero && !(ged && isLuma)) return;  // quirk Q3: identity for mv == 0 (not for cached GED)
     float s[3];
-    mm_erp_to_sphere_arr(g, X, Y, pk, s);
-    const float ux = mm_dot3(c.p[0], s[0], c.p[1], s[1], c.p[2], s[2]);
-    const float uy = mm_dot3(c.p[3], s[0], c.p[4], s[1], c.p[5], s[2]);
-    const float uz = mm_dot3(c.p[6], s[0], c.p[7], s[1], c.p[8], s[2]);
-    mm_erp_from_sphere_arr(g, ux, uy, uz, MX, MY);
+    mm_erp_to_sphere_grid(g, X, Y, pk, tr, s);
+    if (ged)
+    {
+      float r, th, ph;
+      const float rx = mm_dot3(R[0], s[0], R[1], s[1], R[2], s[2]);
+      const float ry = mm_dot3(R[3], s[0], R[4], s[1], R[5], s[2]);
+      const float rz = mm_dot3(R[6], s[0], R[7], s[1], R[8], s[2]);
+      mm_arr_cart_to_sph(rx, ry, rz, &r, &th, &ph);
+      float thM;
+      if (!g.gedModulated) thM = MM_FADD(th, c.p[1]);
+      else thM = MM_FADD(th, mm_atanf(MM_FDIV(mm_sinf(th, fma), MM_FSUB(c.p[0], mm_cosf(th, fma)))));
+      const float phM = MM_FADD(ph, c.p[2]);
+      float q[3];
+      mm_arr_sph_to_cart(r, thM, phM, pk, fma, q);
+      u0 = mm_dot3(R[0], q[0], R[3], q[1], R[6], q[2]);
+      u1 = mm_dot3(R[1], q[0], R[4], q[1], R[7], q[2]);
+      u2 = mm_dot3(R[2], q[0], R[5], q[1], R[8], q[2]);
+    }
+    else if (model == MM_ROTATIONAL)
+    {
+      u0 = mm_dot3(c.p[0], s[0], c.p[1], s[1], c.p[2], s[2]);
+      u1 = mm_dot3(c.p[3], s[0], c.p[4], s[1], c.p[5], s[2]);
+      u2 = mm_dot3(c.p[6], s[0], c.p[7], s[1], c.p[8], s[2]);
+    }
+    else if (model == MM_THREE_D_TRANSLATIONAL)
+    {
+      u0 = MM_FADD(s[0], c.p[0]);
+      u1 = MM_FADD(s[1], c.p[1]);
+      u2 = MM_FADD(s[2], c.p[2]);
+    }
+    else if (model == MM_TANGENTIAL)
+    {
+      const float alphaC = c.p[0], sinC = c.p[1], cosC = c.p[2];
+      float r, th, ph;
+      mm_arr_cart_to_sph(s[0], s[1], s[2], &r, &th, &ph);
+      const float eps = MM_FSUB(MM_PI_2_F, th);
+      const float dAl = MM_FSUB(ph, alphaC);
+      float se, ce, sd, cd;
+      mm_sincos_pk(eps, pk, fma, &se, &ce);
+      mm_sincos_pk(dAl, pk, fma, &sd, &cd);
+      const float cosPsi = MM_FADD(MM_FMUL(sinC, se), MM_FMUL(MM_FMUL(cosC, ce), cd));
+      const float yPl = MM_FDIV(MM_FSUB(MM_FMUL(se, cosC), MM_FMUL(MM_FMUL(sinC, ce), cd)), cosPsi);
+      const float xPl = MM_FDIV(MM_FMUL(sd, ce), cosPsi);
+      const float yM = MM_FSUB(yPl, c.p[3]);
+      const float xM = MM_FSUB(xPl, c.p[4]);
+      const float rho = MM_FSQRT(MM_FADD(MM_FMUL(xM, xM), MM_FMUL(yM, yM)));
+      const float eta = mm_atanf(rho);
+      float sEp, cEp;
+      mm_sincos_pk(eta, pk, fma, &sEp, &cEp);
+      const float gamma = MM_FSUB(MM_FMUL(MM_FMUL(rho, cosC), cEp), MM_FMUL(MM_FMUL(yM, sinC), sEp));
+      // non-vectorised expressions (atan / asin): scalar libm sin/cos
+      float sEs = sEp, cEs = cEp;
+      if (pk) { sEs = mm_sinf(eta, fma); cEs = mm_cosf(eta, fma); }
+      const float alphaM = MM_FADD(alphaC, mm_atanf(MM_FDIV(MM_FMUL(xM, sEs), gamma)));
+      const float epsM = mm_asinf(MM_FADD(MM_FMUL(cEs, sinC), MM_FDIV(MM_FMUL(MM_FMUL(yM, sEs), cosC), rho)));
+      float q[3];
+      mm_arr_sph_to_cart(1.0f, MM_FSUB(MM_PI_2_F, epsM), alphaM, pk, fma, q);
+      u0 = q[0]; u1 = q[1]; u2 = q[2];
+    }
+    else
+    {
+      return;
+    }
   }
-  else if (model == MM_THREE_D_TRANSLATIONAL)
-  {
-    if (c.mvZero) return;
-    float s[3];
-    mm_erp_to_sphere_arr(g, X, Y, pk, s);
-    mm_erp_from_sphere_arr(g, MM_FADD(s[0], c.p[0]), MM_FADD(s[1], c.p[1]), MM_FADD(s[2], c.p[2]), MX, MY);
-  }
-  else if (model == MM_TANGENTIAL)
-  {
-    if (c.mvZero) return;
-    const float alphaC = c.p[0], sinC = c.p[1], cosC = c.p[2];
-    float s[3], r, th, ph;
-    mm_erp_to_sphere_arr(g, X, Y, pk, s);
-    mm_arr_cart_to_sph(s[0], s[1], s[2], &r, &th, &ph);
-    const float eps = MM_FSUB(MM_PI_2_F, th);
-    const float dAl = MM_FSUB(ph, alphaC);
-    float se, ce, sd, cd;
-    mm_sincos_pk(eps, pk, fma, &se, &ce);
-    mm_sincos_pk(dAl, pk, fma, &sd, &cd);
-    const float cosPsi = MM_FADD(MM_FMUL(sinC, se), MM_FMUL(MM_FMUL(cosC, ce), cd));
-    const float yPl = MM_FDIV(MM_FSUB(MM_FMUL(se, cosC), MM_FMUL(MM_FMUL(sinC, ce), cd)), cosPsi);
-    const float xPl = MM_FDIV(MM_FMUL(sd, ce), cosPsi);
-    const float yM = MM_FSUB(yPl, c.p[3]);
-    const float xM = MM_FSUB(xPl, c.p[4]);
-    const float rho = MM_FSQRT(MM_FADD(MM_FMUL(xM, xM), MM_FMUL(yM, yM)));
-    const float eta = mm_atanf(rho);
-    float sEp, cEp;
-    mm_sincos_pk(eta, pk, fma, &sEp, &cEp);
-    const float gamma = MM_FSUB(MM_FMUL(MM_FMUL(rho, cosC), cEp), MM_FMUL(MM_FMUL(yM, sinC), sEp));
-    const float sEs = mm_sinf(eta, fma), cEs = mm_cosf(eta, fma);  // non-vectorised expressions (atan/asin)
-    const float alphaM = MM_FADD(alphaC, mm_atanf(MM_FDIV(MM_FMUL(xM, sEs), gamma)));
-    const float epsM = mm_asinf(MM_FADD(MM_FMUL(cEs, sinC), MM_FDIV(MM_FMUL(MM_FMUL(yM, sEs), cosC), rho)));
-    float q[3];
-    mm_arr_sph_to_cart(1.0f, MM_FSUB(MM_PI_2_F, epsM), alphaM, pk, fma, q);
-    mm_erp_from_sphere_arr(g, q[0], q[1], q[2], MX, MY);
-  }
+  mm_erp_from_sphere_arr(g, u0, u1, u2, MX, MY);
 }
 
 // MVReprojection.cpp:152-165: NaN -> no motion, remove offset, chroma rescale, std::round to fixed point.

@@ -40,6 +40,8 @@ struct mmgpu_ctx
   // MPA caches
   float2* dMpa[3];
   uint8_t* dMpaVip[3];
+  float2* dThTab[2];
+  float2* dPhTab[2];
   // original picture
   int16_t* dOrgOwned;
   size_t orgCap;
@@ -90,6 +92,7 @@ static MmParams baseParams(mmgpu_ctx* ctx)
   P.refs = ctx->dRefs;
   P.rot = ctx->dRot;
   for (int i = 0; i < 3; ++i) { P.mpa[i] = ctx->dMpa[i]; P.mpaVip[i] = ctx->dMpaVip[i]; }
+  for (int i = 0; i < 2; ++i) { P.thTab[i] = ctx->dThTab[i]; P.phTab[i] = ctx->dPhTab[i]; }
   P.org = ctx->dOrg;
   P.orgStride = ctx->orgStride;
   P.hadMode = ctx->cfg.had_mode;
@@ -225,6 +228,16 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     k_mpa_cache<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(g, m + 1, ctx->dMpa[m], ctx->dMpaVip[m]);
     ctx->launches++;
   }
+  for (int v = 0; v < 2; ++v)
+  {
+    CU(cudaMalloc(&ctx->dThTab[v], sizeof(float2) * g.rows4));
+    CU(cudaMalloc(&ctx->dPhTab[v], sizeof(float2) * g.cols4));
+  }
+  {
+    const int nt = g.rows4 > g.cols4 ? g.rows4 : g.cols4;
+    k_trig_tables<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(g, ctx->dThTab[0], ctx->dThTab[1], ctx->dPhTab[0], ctx->dPhTab[1]);
+    ctx->launches++;
+  }
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   *out = ctx;
@@ -250,6 +263,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dRefs);
   cudaFree(ctx->dRot);
   for (int m = 0; m < 3; ++m) { cudaFree(ctx->dMpa[m]); cudaFree(ctx->dMpaVip[m]); }
+  for (int v = 0; v < 2; ++v) { cudaFree(ctx->dThTab[v]); cudaFree(ctx->dPhTab[v]); }
   cudaFree(ctx->dOrgOwned);
   freePlan(&ctx->scratchPlan);
   cudaFree(ctx->dMvs);
@@ -566,7 +580,8 @@ extern "C" int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stri
 // ---- plans ---------------------------------------------------------------------------------------
 static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_block* blocks, int n_cands, bool needOrg)
 {
-  std::vector<MmItem> items;
+  // work items are grouped by motion model so that the warps resident on an SM run the same model's code
+  std::vector<MmItem> itemsByModel[MM_NUM_MODELS];
   std::vector<int32_t> candBlock((size_t)n_cands, -1);
   uint64_t samples = 0;
   for (int bi = 0; bi < n_blocks; ++bi)
@@ -588,6 +603,7 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
       if (candBlock[b.cand_first + c] != -1) return fail(ctx, MMGPU_ERR_ARG, "candidate ranges of blocks overlap");
       candBlock[b.cand_first + c] = bi;
     }
+    std::vector<MmItem>& items = itemsByModel[b.model];
     if (n >= 32)
     {
       for (int c = 0; c < b.cand_count; ++c)
@@ -602,6 +618,8 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   }
   for (int i = 0; i < n_cands; ++i)
     if (candBlock[i] < 0) return fail(ctx, MMGPU_ERR_ARG, "candidate not owned by any block");
+  std::vector<MmItem> items;
+  for (int m = 0; m < MM_NUM_MODELS; ++m) items.insert(items.end(), itemsByModel[m].begin(), itemsByModel[m].end());
   int rc;
   if ((rc = ensureCap(ctx, &p->dBlocks, &p->capBlocks, (size_t)n_blocks))) return rc;
   if ((rc = ensureCap(ctx, &p->dItems, &p->capItems, items.size()))) return rc;
