@@ -174,6 +174,7 @@ def main():
     import torch
     import vvc_extension_mm_b200 as mm
     from vvc_extension_mm_b200 import workload as wl
+    from vvc_extension_mm_b200 import shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -257,10 +258,10 @@ def main():
             if N > 1:
                 for f in range(N):
                     src = pool_ref[(s * N + f) % POOL][1]
-                    for c in range(3):
-                        if rank == f:
+                    if rank == f:
+                        for c in range(3):
                             comm[f][c].copy_(src[c], non_blocking=True)
-                        dist.broadcast(comm[f][c], src=f)
+                    shard.broadcast_planes(comm[f], src=f)
             plan, _ = step_plan(s)
             gpu.me_batch_device(plan, d_mvs.data_ptr(), d_dist.data_ptr(), mv_prec_shift=prec, dist=mm.DIST_HAD)
 
@@ -270,10 +271,10 @@ def main():
             if N > 1:
                 for f in range(N):
                     src = pool_ref[(s * N + f) % POOL][1]
-                    for c in range(3):
-                        if rank == f:
+                    if rank == f:
+                        for c in range(3):
                             comm[f][c].copy_(src[c], non_blocking=True)
-                        dist.broadcast(comm[f][c], src=f)
+                    shard.broadcast_planes(comm[f], src=f)
         _, b = step_plan(s)
         hb = h_blocks.numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
         hb["ref_slot"] = b["ref_slot"]
