@@ -186,42 +186,50 @@ def main():
     dev = torch.device("cuda", local)
 
     # ---- resident data -------------------------------------------------------------------------------------
-    gpu = mm.MmGpu(W, H, max_refs=POOL + N, device=local)
+    # A picture = one contiguous byte buffer holding the padded Y, Cb, Cr planes (one NCCL broadcast per picture).
+    n_comm = 2 * N if N > 1 else 0     # double-buffered landing slots: the next step's references arrive while
+    gpu = mm.MmGpu(W, H, max_refs=POOL + n_comm, device=local)   # the current step computes
     gpu.set_rotation(0, mm.rodrigues(EPIPOLE))
+    geo = wl.pad_frame(wl.synth_frame(W, H, seed=100), 288, 1)
+    plane_bytes = [p.buf.nbytes for p in geo]
+    offs = np.concatenate([[0], np.cumsum([(n + 255) // 256 * 256 for n in plane_bytes])]).astype(np.int64)
+    pic_bytes = int(offs[-1])
+
+    def new_picture():
+        return torch.empty(pic_bytes, dtype=torch.uint8, device=dev)
+
+    def register(slot, pic, poc):
+        origins = [pic.data_ptr() + int(offs[c]) + 2 * (p.my * p.stride + p.mx) for c, p in enumerate(geo)]
+        gpu.set_ref_device(slot, poc, origins, [p.stride for p in geo], keep=pic)
+
     pool_ref, pool_org_h = [], []
-    luma_stride = None
     for f in range(POOL):
-        planes = wl.pad_frame(wl.synth_frame(W, H, seed=100 + f, shift=(0.37 * f, 0.11 * f)), 288, 1)
-        t = [torch.from_numpy(p.buf).to(dev) for p in planes]
-        pool_ref.append((planes, t))
+        planes = geo if f == 0 else wl.pad_frame(wl.synth_frame(W, H, seed=100 + f, shift=(0.37 * f, 0.11 * f)), 288, 1)
+        pic = new_picture()
+        for c, p in enumerate(planes):
+            pic[int(offs[c]):int(offs[c]) + plane_bytes[c]].copy_(torch.from_numpy(p.buf.view(np.uint8).reshape(-1)))
+        pool_ref.append(pic)
+        register(f, pic, f)
         pool_org_h.append(torch.from_numpy(wl.synth_plane(W, H, 5000 + f, shift=(0.37 * f + 2.5, 0.11 * f + 1.0))).pin_memory())
     pool_org_d = [t.to(dev) for t in pool_org_h]
-
-    def origin_ptrs(planes, tens):
-        return [t.data_ptr() + 2 * (p.my * p.stride + p.mx) for p, t in zip(planes, tens)], [p.stride for p in planes]
-
-    for f in range(POOL):
-        o_, s_ = origin_ptrs(*pool_ref[f])
-        gpu.set_ref_device(f, f, o_, s_, keep=pool_ref[f][1])
-    comm = []
-    if N > 1:  # broadcast landing buffers: slot POOL+f holds the reference of frame f of the current step
+    # landing buffers: parity p holds the N pictures of a step back to back (filled by ONE all-gather: rank f
+    # contributes the picture it owns, i.e. N simultaneous broadcasts over NVLink/NVSwitch)
+    comm = [torch.empty(N * pic_bytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
+    for p, big in enumerate(comm):
         for f in range(N):
-            tens = [torch.empty_like(t) for t in pool_ref[0][1]]
-            comm.append(tens)
-            o_, s_ = origin_ptrs(pool_ref[0][0], tens)
-            gpu.set_ref_device(POOL + f, f, o_, s_, keep=tens)
+            register(POOL + p * N + f, big[f * pic_bytes:(f + 1) * pic_bytes], f)
 
     # ---- batch: this rank's CTU rows of the N frames of a step ------------------------------------------------
     rows = wl.shard_ctu_rows(H // CTU, rank, N)
     blocks_l, mvs_l = [], []
     for f in range(N):
         b, m, prec = wl.frame_batch(W, H, seed=1 + f, cands_per_block=CANDS, mv_range=MV_RANGE, models=models(),
-                                    ref_slot=(POOL + f) if N > 1 else 0, ctu_rows=rows)
+                                    ref_slot=f, ctu_rows=rows)
         b["cand_first"] += sum(len(x) for x in mvs_l)
         b["org_y"] += f * H
         blocks_l.append(b)
         mvs_l.append(m)
-    blocks = np.concatenate(blocks_l)
+    blocks = np.concatenate(blocks_l)     # ref_slot holds the frame index f here; step_plan() maps it to a slot
     mvs = np.concatenate(mvs_l)
     n_cands = len(mvs)
     samples_rank = int((blocks["w"].astype(np.int64) * blocks["h"] * blocks["cand_count"]).sum())
@@ -236,51 +244,62 @@ def main():
     gpu.set_org_device(d_org.data_ptr(), W, W, N * H, keep=d_org)
     plans = {}
     stream = torch.cuda.ExternalStream(gpu.stream, device=dev)
+    comm_stream = torch.cuda.Stream(device=dev) if N > 1 else None
+    ready = [torch.cuda.Event() for _ in range(2)]   # landing buffers of parity p hold the references of a step
+    freed = [torch.cuda.Event() for _ in range(2)]   # the step that read parity p has finished
+
+    def slots_of(s):
+        """reference slot of frame f of step s"""
+        if N == 1:
+            return np.array([s % POOL])
+        return POOL + (s % 2) * N + np.arange(N)
 
     def step_plan(s):
-        """N == 1: the reference slot changes every step (pool cycling) -> one plan per pool slot."""
-        slot = s % POOL
-        if N > 1:
-            slot = -1
-        if slot not in plans:
+        key = (s % POOL) if N == 1 else (s % 2)
+        if key not in plans:
             b = blocks.copy()
-            if N == 1:
-                b["ref_slot"] = slot
-            plans[slot] = (gpu.plan(b, n_cands), b)
-        return plans[slot]
+            b["ref_slot"] = slots_of(s)[blocks["ref_slot"]]
+            plans[key] = (gpu.plan(b, n_cands), b)
+        return plans[key]
+
+    def prefetch(s):
+        """Rank f owns frame f of step s: it copies its picture into the landing buffer and NCCL-broadcasts it.
+        Runs on the communication stream, one step ahead of the compute stream."""
+        if N == 1:
+            return
+        p = s % 2
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(freed[p])
+            shard.allgather_pictures(comm[p], pool_ref[(s * N + rank) % POOL])
+            ready[p].record(comm_stream)
 
     def load_orgs(s, tgt, src_pool):
         for f in range(N):
             tgt[f * H:(f + 1) * H].copy_(src_pool[(s * N + f + 1) % POOL], non_blocking=True)
 
     def device_step(s):
+        prefetch(s + 1)
         with torch.cuda.stream(stream):
             if N > 1:
-                for f in range(N):
-                    src = pool_ref[(s * N + f) % POOL][1]
-                    if rank == f:
-                        for c in range(3):
-                            comm[f][c].copy_(src[c], non_blocking=True)
-                    shard.broadcast_planes(comm[f], src=f)
+                stream.wait_event(ready[s % 2])
             plan, _ = step_plan(s)
             gpu.me_batch_device(plan, d_mvs.data_ptr(), d_dist.data_ptr(), mv_prec_shift=prec, dist=mm.DIST_HAD)
+            if N > 1:
+                freed[s % 2].record(stream)
 
     def e2e_step(s):
         # host-facing call: original picture, blocks, MVs from pinned host memory; distortions back to the host
-        with torch.cuda.stream(stream):
-            if N > 1:
-                for f in range(N):
-                    src = pool_ref[(s * N + f) % POOL][1]
-                    if rank == f:
-                        for c in range(3):
-                            comm[f][c].copy_(src[c], non_blocking=True)
-                    shard.broadcast_planes(comm[f], src=f)
+        prefetch(s + 1)
+        if N > 1:
+            ready[s % 2].synchronize()
         _, b = step_plan(s)
         hb = h_blocks.numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
         hb["ref_slot"] = b["ref_slot"]
         gpu.set_org(h_org.numpy())
         gpu.me_batch(hb, h_mvs.numpy().view(mm.api.MV_DTYPE).reshape(-1), mv_prec_shift=prec, dist=mm.DIST_HAD,
                      out=h_dist.numpy().view(np.uint64))
+        if N > 1:
+            freed[s % 2].record(stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -290,6 +309,9 @@ def main():
 
     def timed(fn, k, prep):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for p in range(2):
+            freed[p].record(stream)
+        prefetch(0)                      # prologue: references of step 0 (steady state prefetches one step ahead)
         barrier()
         t0 = time.perf_counter()
         ev0.record(stream)
@@ -308,10 +330,13 @@ def main():
     for f in range(N):
         h_org[f * H:(f + 1) * H].copy_(pool_org_h[(f + 1) % POOL])
 
-    for s in range(POOL if N == 1 else 1):
+    for s in range(POOL if N == 1 else 2):
         step_plan(s)          # plans (device-resident block / work lists) are built once, outside any timed region
     sampler = ClockSampler(local)
     sampler.start()
+    for p in range(2):
+        freed[p].record(stream)
+    prefetch(0)
     for s in range(args.warmup):
         device_step(s)
     barrier()
@@ -363,7 +388,9 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step": N, "blocks_per_rank": int(len(blocks)),
                        "candidates_per_rank": int(n_cands), "sample_candidates_per_step": samples_all,
                        "l2": "references cycle through %d resident frames (%.0f MB of luma planes > 126 MB L2)" % (POOL, POOL * 8.4),
-                       "parallelism": "ctu-rows x%d, ncclBroadcast of reference planes per frame" % N if N > 1 else "1 gpu"},
+                       "parallelism": ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each, one owner rank each) reach "
+                                       "every GPU by one ncclAllGather, prefetched one step ahead on a second stream"
+                                       % (N, N, pic_bytes / 1e6)) if N > 1 else "1 gpu"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k_me<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
                          "algorithmic_bytes_per_launch": alg_bytes_rank,

@@ -288,3 +288,41 @@ def test_full_frame_properties(env):
     d2 = g.me_batch(pb, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD)
     assert np.array_equal(d1, d2)
     plan.close()
+
+
+def test_cpp_host_adapter_matches_oracle():
+    """The C++ adapter (reference-shaped argument lists) end to end: MC of a GED_CAMPOSE block and
+    xPatternRefinementProjected's 9-point HAD refinement equal the oracle."""
+    import subprocess
+    from test_native_cpu import _build_adapter
+    exe = _build_adapter()
+    out = subprocess.run([exe, "need-gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = dict((l.split()[0], l.split()[1:]) for l in out.stdout.strip().splitlines())
+    Wd, Hd, M = 512, 256, 288
+    o = ol.Oracle(Wd, Hd)
+    o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues([1, 0, 0]))
+    planes = []
+    for c in range(3):
+        w, h, m = (Wd, Hd, M) if c == 0 else (Wd // 2, Hd // 2, M // 2)
+        xx, yy = np.meshgrid(np.arange(w), np.arange(h))
+        p = ((xx * 7 + yy * 13 + (xx * yy) % 31 + c * 101) & 1023).astype(np.int16)
+        planes.append(wl.Padded(p, m, m, align=1))
+    class P: pass
+    pl = P(); pl.origin = planes[0].origin; pl.stride = planes[0].stride
+    a = o.mc_block(pl, 0, 1, (128, 64), (64, 64), (37, -21), ol.GED_CAMPOSE)
+    s = 0
+    for v in a.reshape(-1).astype(np.uint16).tolist():
+        s = (s * 1000003 + v) & 0xFFFFFFFFFFFFFFFF
+    assert int(lines["mc"][0]) == s
+    org = ((np.arange(32 * 32) * 37) & 1023).astype(np.int16).reshape(32, 32)
+    refine = [(0, 0), (0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (1, -1), (-1, 1), (1, 1)]
+    cand = np.array([(6 + dx, -4 + dy) for dx, dy in refine])
+    d = o.me_block(pl, org, None, (64, 96), (32, 32), ol.MPA_LR, cand, mv_prec_shift=3, dist=ol.DIST_HAD)
+    best, bmv = None, None
+    for (mh, mv), dd in zip(cand, d):
+        u = int(dd) + abs(int(mh)) + abs(int(mv))
+        if best is None or u < best:
+            best, bmv = u, (int(mh), int(mv))
+    assert [int(x) for x in lines["refine"]] == [best, bmv[0], bmv[1]]
+    o.close()

@@ -120,3 +120,27 @@ def test_workload_partition_covers_frame():
     assert (cover == 1).all()
     rows = [wl.shard_ctu_rows(8, r, 4) for r in range(4)]
     assert sorted(sum(rows, [])) == list(range(8))
+
+
+def _build_adapter():
+    import vvc_extension_mm_b200 as mm
+    mm.build_library()
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "adapter_check")
+    src = os.path.join(NATIVE, "adapter_check.cpp")
+    hdr = os.path.join(ROOT, "vvc-extension-mm_b200", "host", "mm_gpu_adapter.h")
+    if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(exe):
+        subprocess.check_call(["g++", "-O2", "-std=c++11", src, "-o", exe, "-L", os.path.dirname(mm.library_path()), "-lmmgpu",
+                               "-Wl,-rpath," + os.path.dirname(mm.library_path())])
+    return exe
+
+
+def test_cpp_host_adapter_builds_and_fails_loudly_without_gpu():
+    """host/mm_gpu_adapter.h (the reference-shaped C++ host side) links against the C ABI; init() throws like a
+    reference CHECK when no sm_100 device exists."""
+    import torch
+    exe = _build_adapter()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("nogpu-throws")

@@ -40,6 +40,11 @@ def _worker(rank, world, port, ret):
     planes = [torch.from_numpy(p.buf) for p in ref]
     shard.broadcast_planes(planes, src=0)
     cur = wl.synth_frame(W, H, seed=2)[0]
+    # fused form: every rank owns one picture, one all-gather delivers all of them to everybody
+    mine = torch.full((1024,), rank + 1, dtype=torch.uint8)
+    landing = torch.zeros(world * 1024, dtype=torch.uint8)
+    shard.allgather_pictures(landing, mine)
+    assert all(int(landing[r * 1024]) == r + 1 and int(landing[r * 1024 + 1023]) == r + 1 for r in range(world))
 
     class P:
         pass

@@ -19,6 +19,13 @@ def broadcast_planes(planes, src, group=None):
         dist.broadcast(t.view(torch.uint8), src=src, group=group)
 
 
+def allgather_pictures(landing, mine, group=None):
+    """Every rank owns one newly reconstructed picture (`mine`, a contiguous byte buffer with the padded planes);
+    after the call `landing` (world * len(mine) bytes) holds all of them in rank order on every GPU: the N
+    per-picture broadcasts of a step fused into one ncclAllGather."""
+    dist.all_gather_into_tensor(landing, mine, group=group)
+
+
 def shard_blocks(blocks, rank, world, ctu=128, pic_h=None):
     """Blocks (numpy BLOCK_DTYPE) whose CTU row belongs to `rank` (round-robin over CTU rows)."""
     rows = (blocks["y"] // ctu) % world
