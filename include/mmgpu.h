@@ -107,6 +107,22 @@ int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, int x, int 
 int mmgpu_add_avg(mmgpu_ctx* ctx, const int16_t* src0, int s0_stride, const int16_t* src1, int s1_stride, int16_t* dst,
                   int dst_stride, int w, int h, int clp_min, int clp_max);
 
+/* ---- a12: InterPrediction::xProcessDMVRProjected + xDMVRCost (InterPrediction.cpp:2442-2635, 2147-2155) -- */
+/* One DMVR sub-PU (min(16,w) x min(16,h) luma, quirk Q6: the sub-PU is the block for the mapping). */
+typedef struct {
+  int32_t x, y, w, h;            /* luma position / size of the sub-PU (8x16, 16x8, 16x16; 8x8 accepted) */
+  int32_t model;                 /* non-classic motion model of the PU */
+  int32_t ref_slot0, ref_slot1;  /* reference pictures of list 0 / list 1 */
+  int32_t rot_slot0, rot_slot1;  /* geodesic rotations of (curPOC, refPOC_L0) / (curPOC, refPOC_L1) */
+  mmgpu_mv mv0, mv1;             /* merge MVs of the PU (MV_PRECISION_INTERNAL) */
+} mmgpu_dmvr_subpu;
+/* costs[i*25 + k] = xDMVRCost(MC(L0, mv0 + o_k), MC(L1, mv1 - o_k)) for the 25 offsets o_k of m_pSearchOffset
+ * (InterPrediction.h:107-111), both MCs at bi = true.  HOST pointers. */
+int mmgpu_dmvr_costs(mmgpu_ctx* ctx, int n_subpus, const mmgpu_dmvr_subpu* subpus, int clp_min, int clp_max, uint64_t* costs);
+/* Host-side decision of the same loop incl. xDMVRSubPixelErrorSurface (InterPrediction.cpp:1958-2048, 2157-2175,
+ * 2502-2583): 25 costs -> pu.mvdL0SubPu (1/16 pel) and minCost; returns notZeroCost (0/1). */
+int mmgpu_dmvr_decide(const uint64_t costs25[25], int w, int h, int32_t delta_mv[2], uint64_t* min_cost);
+
 /* ---- a9-a11 + a6: candidate evaluation, xTZSearchHelp/xPatternRefinementProjected's
  *      xMVReprojectionInterpolation + m_cDistParam.distFunc pair (InterSearch.cpp:363-453, 6222-6249) --- */
 /* original samples (pcPatternKey or the whole current picture), HOST memory */

@@ -781,3 +781,119 @@ void orc_extend_border(int16_t* p, int stride, int w, int h, int mx, int my)
   int16_t* first = p - mx;
   for (int y = 0; y < my; ++y) memcpy(first - (long)(y + 1) * stride, first, sizeof(int16_t) * (w + 2 * mx));
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * DMVR (projected): InterPrediction.cpp:2442-2635, 2147-2155, 1958-2048, 2157-2175
+ * ------------------------------------------------------------------------------------------- */
+static const int kSearchOffset[25][2] = { /* InterPrediction.h:107-111 (hor, ver) */
+  {-2, -2}, {-1, -2}, {0, -2}, {1, -2}, {2, -2}, {-2, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, -1},
+  {-2, 0},  {-1, 0},  {0, 0},  {1, 0},  {2, 0},  {-2, 1},  {-1, 1},  {0, 1},  {1, 1},  {2, 1},
+  {-2, 2},  {-1, 2},  {0, 2},  {1, 2},  {2, 2}};
+
+static uint64_t dmvr_cost(const int16_t* a, int as, const int16_t* b, int bs, int w, int h, int simd)
+{
+  /* xDMVRCost: setDistParam(..., subShiftMode 1) -> DF_SAD + log2(width); return distFunc >> 1 */
+  uint64_t sum = 0;
+  for (int y = 0; y < h; y += 2)
+    for (int x = 0; x < w; ++x)
+    {
+      int d = a[y * as + x] - b[y * bs + x];
+      if (simd) { int16_t d16 = (int16_t)d; int ad = d16 < 0 ? -(int)d16 : (int)d16; sum += (uint64_t)(ad & 0xffff); }
+      else sum += (uint64_t)abs(d);
+    }
+  sum <<= 1;
+  return sum >> 1;
+}
+
+void orc_dmvr_costs(OrcCtx* c, const int16_t* ref0, int rs0, const int16_t* ref1, int rs1, int x, int y, int dx, int dy,
+                    int mv0h, int mv0v, int mv1h, int mv1v, int model, const float* R0, const float* R1, int lo, int hi,
+                    int simd, uint64_t costs25[25])
+{
+  int16_t p0[16 * 16], p1[16 * 16];
+  for (int k = 0; k < 25; ++k)
+  {
+    const int oh = kSearchOffset[k][0] * 16, ov = kSearchOffset[k][1] * 16; /* << MV_FRACTIONAL_BITS_INTERNAL */
+    if (R0) orc_set_rotation(c, model, R0);
+    orc_mc_block(c, ref0, rs0, 0, c->cfg.chroma_fmt, x, y, dx, dy, mv0h + oh, mv0v + ov, model, 1, lo, hi, ORC_OOB_PRED, p0, 16);
+    if (R1) orc_set_rotation(c, model, R1);
+    orc_mc_block(c, ref1, rs1, 0, c->cfg.chroma_fmt, x, y, dx, dy, mv1h - oh, mv1v - ov, model, 1, lo, hi, ORC_OOB_PRED, p1, 16);
+    costs25[k] = dmvr_cost(p0, 16, p1, 16, dx, dy, simd);
+  }
+}
+
+static int32_t div_for_maxq7(int64_t N, int64_t D)
+{
+  int32_t sign = 0, q = 0;
+  if (N < 0) { sign = 1; N = -N; }
+  D = (D << 3);
+  if (N >= D) { N -= D; q++; }
+  q = (q << 1);
+  D = (D >> 1);
+  if (N >= D) { N -= D; q++; }
+  q = (q << 1);
+  if (N >= (D >> 1)) q++;
+  return sign ? -q : q;
+}
+static void sub_pel_error_srfc(const uint64_t* sb, int32_t* dmv)
+{
+  int64_t num, den;
+  num = (int64_t)((sb[1] - sb[3]) << 4);
+  den = (int64_t)((sb[1] + sb[3] - (sb[0] << 1)));
+  if (0 != den)
+  {
+    if ((sb[1] != sb[0]) && (sb[3] != sb[0])) dmv[0] = div_for_maxq7(num, den);
+    else dmv[0] = (sb[1] == sb[0]) ? -8 : 8;
+  }
+  num = (int64_t)((sb[2] - sb[4]) << 4);
+  den = (int64_t)((sb[2] + sb[4] - (sb[0] << 1)));
+  if (0 != den)
+  {
+    if ((sb[2] != sb[0]) && (sb[4] != sb[0])) dmv[1] = div_for_maxq7(num, den);
+    else dmv[1] = (sb[2] == sb[0]) ? -8 : 8;
+  }
+}
+
+int orc_dmvr_decide(const uint64_t costs25[25], int dx, int dy, int32_t delta_mv[2], uint64_t* min_cost)
+{
+  uint64_t sads[25];
+  for (int i = 0; i < 25; ++i) sads[i] = UINT64_MAX;
+  uint64_t* p = &sads[12];
+  int notZero = 1;
+  int16_t total[2] = {0, 0}, delta[2] = {0, 0};
+  uint64_t minCost = costs25[12];
+  minCost -= (minCost >> 2);
+  if (minCost < (uint64_t)(dx * dy)) notZero = 0;
+  else
+  {
+    p[0] = minCost;
+    if (!minCost) notZero = 0;
+    else
+    {
+      for (int n = 0; n < 25; ++n)
+      {
+        const int off = kSearchOffset[n][1] * 5 + kSearchOffset[n][0];
+        if (p[off] == UINT64_MAX) p[off] = costs25[n];
+        if (p[off] < minCost) { minCost = p[off]; delta[0] = (int16_t)kSearchOffset[n][0]; delta[1] = (int16_t)kSearchOffset[n][1]; }
+      }
+      if (!(delta[0] == 0 && delta[1] == 0))
+      {
+        total[0] += delta[0]; total[1] += delta[1];
+        p += delta[1] * 5 + delta[0];
+      }
+    }
+  }
+  total[0] = (int16_t)(total[0] << 4);
+  total[1] = (int16_t)(total[1] << 4);
+  if (notZero && (abs(total[0]) != (2 << 4)) && (abs(total[1]) != (2 << 4)))
+  {
+    int32_t t[2] = {0, 0};
+    uint64_t sb[5] = {p[0], p[-1], p[-5], p[1], p[5]};
+    sub_pel_error_srfc(sb, t);
+    total[0] += (int16_t)t[0];
+    total[1] += (int16_t)t[1];
+  }
+  delta_mv[0] = total[0];
+  delta_mv[1] = total[1];
+  *min_cost = minCost;
+  return notZero;
+}

@@ -107,6 +107,18 @@ void orc_me_block(OrcCtx* c, const int16_t* ref, int ref_stride, const int16_t* 
 void orc_add_avg(const int16_t* src0, int s0_stride, const int16_t* src1, int s1_stride, int16_t* dst, int dst_stride,
                  int w, int h, int bit_depth, int clp_min, int clp_max);
 
+/* InterPrediction::xProcessDMVRProjected integer search of ONE sub-PU (InterPrediction.cpp:2485-2583) with
+ * xDMVRCost (:2147-2155: sized SAD, subShift 1, >>1).  ref0/ref1: luma planes of the two lists, R0/R1: geodesic
+ * rotations of the two (curPOC,refPOC) pairs.  costs25[k] = xDMVRCost at m_pSearchOffset[k] (InterPrediction.h:107-111;
+ * k = 12 is the starting point).  simd_sad != 0 reproduces the 16-bit wrap of xGetSAD_NxN_SIMD's _mm_sub_epi16 on
+ * 14-bit intermediates (x86/RdCostX86.h:378-495). */
+void orc_dmvr_costs(OrcCtx* c, const int16_t* ref0, int rs0, const int16_t* ref1, int rs1, int x, int y, int dx, int dy,
+                    int mv0_hor, int mv0_ver, int mv1_hor, int mv1_ver, int model, const float* R0, const float* R1,
+                    int clp_min, int clp_max, int simd_sad, uint64_t costs25[25]);
+/* Decision logic of the same loop + xDMVRSubPixelErrorSurface/xSubPelErrorSrfc/div_for_maxq7 (:1958-2048, 2157-2175):
+ * from the 25 costs to pu.mvdL0SubPu (1/16 pel) and minCost; returns notZeroCost. */
+int orc_dmvr_decide(const uint64_t costs25[25], int dx, int dy, int32_t delta_mv[2], uint64_t* min_cost);
+
 /* Picture::extendPicBorder (Picture.cpp:988-1048): replicate a w x h plane into its margins in place. */
 void orc_extend_border(int16_t* plane00, int stride, int w, int h, int margin_x, int margin_y);
 

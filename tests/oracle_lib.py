@@ -58,6 +58,9 @@ def lib():
             [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
         L.orc_add_avg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 5
         L.orc_extend_border.argtypes = [C.c_void_p] + [C.c_int] * 5
+        L.orc_dmvr_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 9 + \
+            [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_dmvr_decide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -149,6 +152,24 @@ class Oracle:
                             size[1], model, len(mvs), mh.ctypes.data, mv.ctypes.data, mv_prec_shift, dist, sub_shift,
                             had_mode, clp[0], clp[1], out.ctypes.data)
         return out
+
+
+def dmvr_costs(o, plane0, plane1, pos, size, mv0, mv1, model, R0=None, R1=None, clp=(0, 1023), simd=1):
+    out = np.zeros(25, dtype=np.uint64)
+    r0 = None if R0 is None else np.ascontiguousarray(R0, dtype=np.float32)
+    r1 = None if R1 is None else np.ascontiguousarray(R1, dtype=np.float32)
+    lib().orc_dmvr_costs(o.h, plane0.origin, plane0.stride, plane1.origin, plane1.stride, pos[0], pos[1], size[0], size[1],
+                         mv0[0], mv0[1], mv1[0], mv1[1], model, None if r0 is None else r0.ctypes.data,
+                         None if r1 is None else r1.ctypes.data, clp[0], clp[1], simd, out.ctypes.data)
+    return out
+
+
+def dmvr_decide(costs25, w, h):
+    c = np.ascontiguousarray(costs25, dtype=np.uint64)
+    d = np.zeros(2, dtype=np.int32)
+    m = np.zeros(1, dtype=np.uint64)
+    nz = lib().orc_dmvr_decide(c.ctypes.data, w, h, d.ctypes.data, m.ctypes.data)
+    return int(nz), (int(d[0]), int(d[1])), int(m[0])
 
 
 def sad(org, cur, sub_shift=0):

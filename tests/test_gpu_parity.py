@@ -326,3 +326,35 @@ def test_cpp_host_adapter_matches_oracle():
             best, bmv = u, (int(mh), int(mv))
     assert [int(x) for x in lines["refine"]] == [best, bmv[0], bmv[1]]
     o.close()
+
+
+def test_dmvr_projected_costs_and_decision(env):
+    """a12: the 25 xDMVRCost values of xProcessDMVRProjected per sub-PU (two bi MCs + SAD subShift 1, >>1) and the
+    resulting mvdL0SubPu == oracle; list-specific geodesic rotations and reference pictures."""
+    o, g, planes, ref, cur = env
+    ref1 = wl.pad_frame(wl.synth_frame(W, H, seed=31, shift=(1.5, -0.5)), 288, 1)
+    g.set_ref(2, 8, [p.origin for p in ref1], [p.stride for p in ref1])
+    class P: pass
+    p1 = P(); p1.origin = ref1[0].origin; p1.stride = ref1[0].stride
+    R0 = ol.Oracle.rodrigues(EPIPOLE); R1 = ol.Oracle.rodrigues([-0.2, 0.9, 0.1])
+    g.set_rotation(0, mm.rodrigues(EPIPOLE)); g.set_rotation(1, mm.rodrigues([-0.2, 0.9, 0.1]))
+    rng = np.random.default_rng(77)
+    sub = np.zeros(30, dtype=mm.DMVR_DTYPE)
+    sizes = [(16, 16), (8, 16), (16, 8), (8, 8)]
+    models = [1, 2, 3, 4, 5, 6, 10, 8]
+    for i in range(len(sub)):
+        w, h = sizes[i % 4]
+        x = int(rng.integers(4, (W - w) // 4 - 4)) * 4; y = int(rng.integers(4, (H - h) // 4 - 4)) * 4
+        if i % 7 == 0: y = 0
+        if i % 9 == 0: x = W - w
+        mv0 = (int(rng.integers(-200, 200)), int(rng.integers(-120, 120)))
+        sub[i] = (x, y, w, h, models[i % len(models)], 0, 2, 0, 1, mv0[0], mv0[1], -mv0[0] + int(rng.integers(-8, 8)), -mv0[1])
+    got = g.dmvr_costs(sub)
+    for i, s in enumerate(sub):
+        campose = int(s["model"]) == ol.GED_CAMPOSE     # only the camera-pose model takes per-list epipoles
+        exp = ol.dmvr_costs(o, planes[0], p1, (int(s["x"]), int(s["y"])), (int(s["w"]), int(s["h"])),
+                            (int(s["mv0_hor"]), int(s["mv0_ver"])), (int(s["mv1_hor"]), int(s["mv1_ver"])), int(s["model"]),
+                            R0 if campose else None, R1 if campose else None)
+        assert np.array_equal(exp, got[i]), (i, s, exp, got[i])
+        assert mm.dmvr_decide(got[i], int(s["w"]), int(s["h"])) == ol.dmvr_decide(exp, int(s["w"]), int(s["h"]))
+    o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(EPIPOLE))

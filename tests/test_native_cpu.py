@@ -144,3 +144,32 @@ def test_cpp_host_adapter_builds_and_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("nogpu-throws")
+
+
+def test_dmvr_decide_host_equals_oracle():
+    """mmgpu_dmvr_decide (host side of a12: integer-search bookkeeping + error surface) vs the oracle's restatement
+    of InterPrediction.cpp:1958-2048, 2157-2175, 2502-2583, on random and crafted cost surfaces."""
+    import vvc_extension_mm_b200 as mm
+    rng = np.random.default_rng(7)
+    n = 0
+    for it in range(4000):
+        kind = it % 5
+        if kind == 0:
+            c = rng.integers(0, 3000, size=25)
+        elif kind == 1:                                   # bowl around a random minimum
+            cx, cy = rng.integers(-2, 3, size=2)
+            xs, ys = np.meshgrid(np.arange(-2, 3), np.arange(-2, 3))
+            c = 500 + 90 * (xs - cx) ** 2 + 70 * (ys - cy) ** 2 + rng.integers(0, 40, size=(5, 5))
+            c = c.reshape(-1)
+        elif kind == 2:                                   # early termination: tiny centre cost
+            c = rng.integers(0, 4000, size=25); c[12] = rng.integers(0, 300)
+        elif kind == 3:                                   # ties / flat neighbours -> half-pel branches
+            c = np.full(25, 1000); c[rng.integers(0, 25)] = 900; c[12] = 1300
+        else:
+            c = rng.integers(200, 100000, size=25)
+        for (w, h) in ((16, 16), (8, 16), (16, 8)):
+            a = mm.dmvr_decide(c, w, h)
+            b = ol.dmvr_decide(c, w, h)
+            assert a == b, (c, w, h, a, b)
+            n += 1
+    assert n == 12000

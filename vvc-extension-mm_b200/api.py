@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_me_batch", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide",
 ]
 
 
@@ -49,6 +49,9 @@ BLOCK_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), 
                         ("rot_slot", "<i4"), ("cand_first", "<i4"), ("cand_count", "<i4"), ("org_x", "<i4"),
                         ("org_y", "<i4"), ("reserved", "<i4")])
 MV_DTYPE = np.dtype([("hor", "<i4"), ("ver", "<i4")])
+DMVR_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("model", "<i4"), ("ref_slot0", "<i4"),
+                       ("ref_slot1", "<i4"), ("rot_slot0", "<i4"), ("rot_slot1", "<i4"), ("mv0_hor", "<i4"),
+                       ("mv0_ver", "<i4"), ("mv1_hor", "<i4"), ("mv1_ver", "<i4")])
 
 _lib = None
 
@@ -92,6 +95,8 @@ def load_library():
     L.mmgpu_plan_samples.restype = u64
     L.mmgpu_plan_samples.argtypes = [vp]
     L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
+    L.mmgpu_dmvr_costs.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.mmgpu_dmvr_decide.argtypes = [vp, i32, i32, vp, vp]
     _lib = L
     return L
 
@@ -113,6 +118,16 @@ def rodrigues(epipole):
 
 def fixed_to_float(fixed, precision=24):
     return float(load_library().mmgpu_fixed_to_float(int(fixed), int(precision)))
+
+
+def dmvr_decide(costs25, w, h):
+    """Host decision logic of xProcessDMVRProjected: -> (notZeroCost, (dmv_hor, dmv_ver) in 1/16 pel, minCost)."""
+    L = load_library()
+    c = np.ascontiguousarray(costs25, dtype=np.uint64)
+    d = np.zeros(2, dtype=np.int32)
+    m = np.zeros(1, dtype=np.uint64)
+    nz = L.mmgpu_dmvr_decide(c.ctypes.data, int(w), int(h), d.ctypes.data, m.ctypes.data)
+    return int(nz), (int(d[0]), int(d[1])), int(m[0])
 
 
 def _ptr(a):
@@ -263,6 +278,13 @@ class MmGpu:
             out = np.zeros(len(mvs), dtype=np.uint64)
         self._chk(self.L.mmgpu_me_batch(self.h, len(blocks), blocks.ctypes.data, len(mvs), mvs.ctypes.data, mv_prec_shift,
                                         dist, sub_shift, clp[0], clp[1], out.ctypes.data))
+        return out
+
+    def dmvr_costs(self, subpus, clp=(0, 1023)):
+        """subpus: numpy array of DMVR_DTYPE -> (n, 25) uint64 xDMVRCost values at m_pSearchOffset."""
+        subpus = np.ascontiguousarray(subpus, dtype=DMVR_DTYPE)
+        out = np.zeros((len(subpus), 25), dtype=np.uint64)
+        self._chk(self.L.mmgpu_dmvr_costs(self.h, len(subpus), subpus.ctypes.data, clp[0], clp[1], out.ctypes.data))
         return out
 
     def plan(self, blocks, n_cands):

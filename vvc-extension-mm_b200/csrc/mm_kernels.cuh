@@ -663,6 +663,77 @@ __global__ void __launch_bounds__(128) k_me(const MmParams P)
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_dmvr: xProcessDMVRProjected's cost evaluations (InterPrediction.cpp:2510-2567).  One group of 2n lanes per
+// (sub-PU, search offset): n lanes interpolate the L0 prediction of the sub-PU's n sub-blocks at mv0 + offset,
+// n lanes the L1 prediction at mv1 - offset (bi = true: 14-bit intermediates, +-maxCU OOB rule, the sub-PU is
+// "the block": quirk Q6); xDMVRCost = SAD over even rows (subShift 1), << 1, >> 1.
+// -------------------------------------------------------------------------------------------------
+struct MmDmvrItem
+{
+  int32_t subpu;   // index into the sub-PU array
+  int32_t off;     // first m_pSearchOffset index handled by this warp
+  int32_t pad0, pad1;
+};
+
+__global__ void __launch_bounds__(128) k_dmvr(const MmParams P, const mmgpu_dmvr_subpu* __restrict__ subpus,
+                                              const MmDmvrItem* __restrict__ items, int nItems, int simdSad,
+                                              unsigned long long* __restrict__ costs)
+{
+  __shared__ MmTaps s_taps[16];
+  mm_build_taps(s_taps);
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nItems) return;
+  const MmDmvrItem it = items[warp];
+  const mmgpu_dmvr_subpu sp = subpus[it.subpu];
+  const int cols = sp.w >> 2, rows = sp.h >> 2;
+  const int n = cols * rows;                    // 4, 8 or 16 sub-blocks
+  const int g = lane / (2 * n), within = lane - g * 2 * n;
+  const int list = within / n, sb = within - list * n;
+  const int off = it.off + g;
+  const bool valid = off < 25;
+  const int offc = valid ? off : it.off;
+  const int oh = (offc % 5 - 2) * 16, ov = (offc / 5 - 2) * 16;   // m_pSearchOffset << MV_FRACTIONAL_BITS_INTERNAL
+  const int mh = list ? (sp.mv1.hor - oh) : (sp.mv0.hor + oh);
+  const int mv = list ? (sp.mv1.ver - ov) : (sp.mv0.ver + ov);
+  const int row = sb / cols, col = sb - row * cols;
+  const MmRef ref = P.refs[list ? sp.ref_slot1 : sp.ref_slot0];
+  const float* R = mm_rot_ptr(P.rot, sp.model, list ? sp.rot_slot1 : sp.rot_slot0);
+  MmCand c;
+  mm_cand_setup(P.g, sp.model, true, sp.x, sp.y, sp.w, sp.h, mh, mv, R, &c);
+  int fx, fy;
+  mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, sp.model, 0, 0, 0, sp.x, sp.y, sp.w, sp.h, c, R, row, col, &fx, &fy);
+  const int xP = fx >> 4, yP = fy >> 4;
+  const bool oob = (xP < -P.maxCU || yP < -P.maxCU || xP >= P.picW + P.maxCU - 4 || yP >= P.picH + P.maxCU - 4);
+  int pred[16];
+  if (oob)
+  {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pred[i] = 0;
+  }
+  else
+  {
+    mm_fir_luma4x4<true>(P.fir, s_taps, ref.plane00[0], ref.stride[0], xP, yP, fx & 15, fy & 15, P.clpMin, P.clpMax, pred);
+  }
+  // rows 0 and 2 of the sub-block (even rows of the sub-PU): L0 lanes receive the L1 samples of lane ^ n
+  unsigned int sad = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+  {
+    const int mine = pred[(i >> 2) * 8 + (i & 3)];
+    const int other = __shfl_xor_sync(0xffffffffu, mine, n);
+    int d = mine - other;
+    if (simdSad) { d = (int)(int16_t)d; d = abs(d) & 0xffff; }   // _mm_sub_epi16 + _mm_abs_epi16, zero-extended
+    else d = abs(d);
+    sad += (unsigned int)d;
+  }
+  if (list) sad = 0;
+  for (int o = n >> 1; o > 0; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+  if (valid && within == 0) costs[(long)it.subpu * 25 + off] = ((unsigned long long)sad << 1) >> 1;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Picture::extendPicBorder on the device (Picture.cpp:1008-1046): one thread per margin sample
 // -------------------------------------------------------------------------------------------------
 __global__ void k_extend_border(int16_t* plane00, int stride, int w, int h, int mx, int my)

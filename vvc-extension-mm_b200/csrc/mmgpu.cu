@@ -55,6 +55,10 @@ struct mmgpu_ctx
   size_t capDist;
   int16_t* dTmp;  // small device buffers for mmgpu_mc / reproject / add_avg
   size_t capTmp;
+  mmgpu_dmvr_subpu* dSubpus;
+  size_t capSubpus;
+  MmDmvrItem* dDmvrItems;
+  size_t capDmvrItems;
   // optional CUDA-event timing of k_me
   bool timing;
   std::vector<cudaEvent_t> evPool;   // start/stop pairs
@@ -269,6 +273,8 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dMvs);
   cudaFree(ctx->dDist);
   cudaFree(ctx->dTmp);
+  cudaFree(ctx->dSubpus);
+  cudaFree(ctx->dDmvrItems);
   for (auto e : ctx->evPool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -737,4 +743,111 @@ extern "C" int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* b
   CU(cudaMemcpyAsync(dist, ctx->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return MMGPU_OK;
+}
+
+// ---- a12: DMVR (projected) ------------------------------------------------------------------------------
+extern "C" int mmgpu_dmvr_costs(mmgpu_ctx* ctx, int n_subpus, const mmgpu_dmvr_subpu* subpus, int clp_min, int clp_max,
+                                uint64_t* costs)
+{
+  if (!ctx || !subpus || !costs || n_subpus <= 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  std::vector<MmDmvrItem> items;
+  for (int i = 0; i < n_subpus; ++i)
+  {
+    const mmgpu_dmvr_subpu& s = subpus[i];
+    int rc = checkBlockShape(ctx, 0, 0, s.x, s.y, s.w, s.h);
+    if (rc) return rc;
+    if (s.w > 16 || s.h > 16 || s.w < 8 || s.h < 8) return fail(ctx, MMGPU_ERR_ARG, "DMVR sub-PU must be 8..16 wide and high");
+    if (s.model <= MMGPU_CLASSIC || s.model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "DMVR projected needs a non-classic model");
+    if (s.ref_slot0 < 0 || s.ref_slot0 >= ctx->cfg.max_refs || !ctx->hRefs[s.ref_slot0].plane00[0] || s.ref_slot1 < 0 ||
+        s.ref_slot1 >= ctx->cfg.max_refs || !ctx->hRefs[s.ref_slot1].plane00[0])
+      return fail(ctx, MMGPU_ERR_STATE, "DMVR sub-PU references an unset reference slot");
+    if (s.rot_slot0 < 0 || s.rot_slot0 >= MM_MAX_ROT || s.rot_slot1 < 0 || s.rot_slot1 >= MM_MAX_ROT)
+      return fail(ctx, MMGPU_ERR_ARG, "bad rot_slot");
+    const int n = (s.w >> 2) * (s.h >> 2);
+    const int per = 32 / (2 * n);
+    for (int o = 0; o < 25; o += per) items.push_back(MmDmvrItem{i, o, 0, 0});
+  }
+  int rc;
+  if ((rc = ensureCap(ctx, &ctx->dSubpus, &ctx->capSubpus, (size_t)n_subpus))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dDmvrItems, &ctx->capDmvrItems, items.size()))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dDist, &ctx->capDist, (size_t)n_subpus * 25))) return rc;
+  CU(cudaMemcpyAsync(ctx->dSubpus, subpus, sizeof(mmgpu_dmvr_subpu) * n_subpus, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->dDmvrItems, items.data(), sizeof(MmDmvrItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+  MmParams P = baseParams(ctx);
+  P.clpMin = clp_min;
+  P.clpMax = clp_max;
+  P.oobMode = MMGPU_OOB_PRED;
+  const int nItems = (int)items.size();
+  k_dmvr<<<(nItems + 3) / 4, 128, 0, ctx->stream>>>(P, ctx->dSubpus, ctx->dDmvrItems, nItems, ctx->cfg.had_mode == MMGPU_HAD_SIMD,
+                                                  ctx->dDist);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(costs, ctx->dDist, sizeof(uint64_t) * (size_t)n_subpus * 25, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+static int32_t divForMaxq7(int64_t N, int64_t D)   // InterPrediction.cpp:1958-1994
+{
+  int32_t sign = 0, q = 0;
+  if (N < 0) { sign = 1; N = -N; }
+  D = (D << 3);
+  if (N >= D) { N -= D; q++; }
+  q = (q << 1);
+  D = (D >> 1);
+  if (N >= D) { N -= D; q++; }
+  q = (q << 1);
+  if (N >= (D >> 1)) q++;
+  return sign ? -q : q;
+}
+
+extern "C" int mmgpu_dmvr_decide(const uint64_t costs25[25], int w, int h, int32_t delta_mv[2], uint64_t* min_cost)
+{
+  // xProcessDMVRProjected's integer search bookkeeping (iterationCount == 1) + xDMVRSubPixelErrorSurface
+  static const int offs[25][2] = {{-2, -2}, {-1, -2}, {0, -2}, {1, -2}, {2, -2}, {-2, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, -1},
+                                  {-2, 0},  {-1, 0},  {0, 0},  {1, 0},  {2, 0},  {-2, 1},  {-1, 1},  {0, 1},  {1, 1},  {2, 1},
+                                  {-2, 2},  {-1, 2},  {0, 2},  {1, 2},  {2, 2}};
+  uint64_t sads[25];
+  for (int i = 0; i < 25; ++i) sads[i] = UINT64_MAX;
+  uint64_t* p = &sads[12];
+  int notZero = 1;
+  int16_t total[2] = {0, 0}, delta[2] = {0, 0};
+  uint64_t minCost = costs25[12];
+  minCost -= (minCost >> 2);
+  if (minCost < (uint64_t)(w * h)) notZero = 0;
+  else
+  {
+    p[0] = minCost;
+    for (int n = 0; n < 25; ++n)
+    {
+      const int o = offs[n][1] * 5 + offs[n][0];
+      if (p[o] == UINT64_MAX) p[o] = costs25[n];
+      if (p[o] < minCost) { minCost = p[o]; delta[0] = (int16_t)offs[n][0]; delta[1] = (int16_t)offs[n][1]; }
+    }
+    if (!(delta[0] == 0 && delta[1] == 0))
+    {
+      total[0] = (int16_t)(total[0] + delta[0]);
+      total[1] = (int16_t)(total[1] + delta[1]);
+      p += delta[1] * 5 + delta[0];
+    }
+  }
+  total[0] = (int16_t)(total[0] << 4);
+  total[1] = (int16_t)(total[1] << 4);
+  if (notZero && (abs(total[0]) != (2 << 4)) && (abs(total[1]) != (2 << 4)))
+  {
+    const uint64_t sb[5] = {p[0], p[-1], p[-5], p[1], p[5]};
+    int32_t t[2] = {0, 0};
+    int64_t num = (int64_t)((sb[1] - sb[3]) << 4), den = (int64_t)((sb[1] + sb[3] - (sb[0] << 1)));
+    if (den != 0) t[0] = ((sb[1] != sb[0]) && (sb[3] != sb[0])) ? divForMaxq7(num, den) : ((sb[1] == sb[0]) ? -8 : 8);
+    num = (int64_t)((sb[2] - sb[4]) << 4);
+    den = (int64_t)((sb[2] + sb[4] - (sb[0] << 1)));
+    if (den != 0) t[1] = ((sb[2] != sb[0]) && (sb[4] != sb[0])) ? divForMaxq7(num, den) : ((sb[2] == sb[0]) ? -8 : 8);
+    total[0] = (int16_t)(total[0] + t[0]);
+    total[1] = (int16_t)(total[1] + t[1]);
+  }
+  delta_mv[0] = total[0];
+  delta_mv[1] = total[1];
+  if (min_cost) *min_cost = minCost;
+  return notZero;
 }
