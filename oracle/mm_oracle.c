@@ -897,3 +897,9 @@ int orc_dmvr_decide(const uint64_t costs25[25], int dx, int dy, int32_t delta_mv
   *min_cost = minCost;
   return notZero;
 }
+
+/* xDMVRCost alone (InterPrediction.cpp:2147-2155), exported so tests can pin it against oracle/_ref. */
+uint64_t orc_dmvr_cost(const int16_t* a, int as, const int16_t* b, int bs, int w, int h, int simd_sad)
+{
+  return dmvr_cost(a, as, b, bs, w, h, simd_sad);
+}

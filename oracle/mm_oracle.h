@@ -119,6 +119,8 @@ void orc_dmvr_costs(OrcCtx* c, const int16_t* ref0, int rs0, const int16_t* ref1
  * from the 25 costs to pu.mvdL0SubPu (1/16 pel) and minCost; returns notZeroCost. */
 int orc_dmvr_decide(const uint64_t costs25[25], int dx, int dy, int32_t delta_mv[2], uint64_t* min_cost);
 
+uint64_t orc_dmvr_cost(const int16_t* a, int as, const int16_t* b, int bs, int w, int h, int simd_sad);
+
 /* Picture::extendPicBorder (Picture.cpp:988-1048): replicate a w x h plane into its margins in place. */
 void orc_extend_border(int16_t* plane00, int stride, int w, int h, int margin_x, int margin_y);
 

@@ -60,6 +60,8 @@ def lib():
         L.orc_extend_border.argtypes = [C.c_void_p] + [C.c_int] * 5
         L.orc_dmvr_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 9 + \
             [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_dmvr_cost.restype = C.c_uint64
+        L.orc_dmvr_cost.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_dmvr_decide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
