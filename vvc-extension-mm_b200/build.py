@@ -17,7 +17,8 @@ NVCC_FLAGS = [
 
 
 def library_path():
-    return OUT
+    """MMGPU_LIB overrides the library (kernel-variant experiments); default: the in-tree build."""
+    return os.environ.get("MMGPU_LIB", OUT)
 
 
 def needs_build():
@@ -31,7 +32,7 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MMGPU_NVCC_EXTRA", "").split() + ["-o", OUT, SRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

@@ -530,7 +530,10 @@ enum { MM_MODE_DIST = 0, MM_MODE_PRED = 1 };
 // k_me: one warp per work item.
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(128) k_me(const MmParams P)
+#ifndef MM_ME_MINBLOCKS
+#define MM_ME_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, MM_ME_MINBLOCKS) k_me(const MmParams P)
 {
   __shared__ MmTaps s_taps[16];
   mm_build_taps(s_taps);

@@ -24,8 +24,15 @@
 
 #if defined(__CUDACC__)
 #define MM_HD __host__ __device__ __forceinline__
+// the big libm routines: inlined by default; -DMM_NOINLINE_LIBM keeps one copy each (smaller kernel code)
+#ifdef MM_NOINLINE_LIBM
+#define MM_HDL __host__ __device__ __noinline__
+#else
+#define MM_HDL __host__ __device__ __forceinline__
+#endif
 #else
 #define MM_HD static inline
+#define MM_HDL static inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -212,7 +219,7 @@ MM_HD double mm_sc_reduce_large(uint32_t xi, int* np)
 
 MM_HD uint32_t mm_abstop12(float x) { return (MM_F2U(x) >> 20) & 0x7ffu; }
 
-MM_HD float mm_sinf(float y, bool fma_build)
+MM_HDL float mm_sinf(float y, bool fma_build)
 {
   double x = (double)y;
   const uint32_t top = mm_abstop12(y);
@@ -242,7 +249,7 @@ MM_HD float mm_sinf(float y, bool fma_build)
   return MM_FDIV(MM_FSUB(y, y), MM_FSUB(y, y));  // __math_invalidf: NaN
 }
 
-MM_HD float mm_cosf(float y, bool fma_build)
+MM_HDL float mm_cosf(float y, bool fma_build)
 {
   double x = (double)y;
   const uint32_t top = mm_abstop12(y);
@@ -275,7 +282,7 @@ MM_HD float mm_cosf(float y, bool fma_build)
 // ------------------------------------------------------------------------------------------
 // glibc 2.39 flt-32/s_atanf.c
 // ------------------------------------------------------------------------------------------
-MM_HD float mm_atanf(float x)
+MM_HDL float mm_atanf(float x)
 {
   const float atanhi0 = MM_U2F(0x3eed6338u), atanhi1 = MM_U2F(0x3f490fdau), atanhi2 = MM_U2F(0x3f7b985eu),
               atanhi3 = MM_U2F(0x3fc90fdau);
@@ -352,7 +359,7 @@ MM_HD float mm_atanf(float x)
 // ------------------------------------------------------------------------------------------
 // glibc 2.39 flt-32/e_atan2f.c (the w_atan2f wrapper only touches errno)
 // ------------------------------------------------------------------------------------------
-MM_HD float mm_atan2f(float y, float x)
+MM_HDL float mm_atan2f(float y, float x)
 {
   const float tiny = MM_U2F(0x0da24260u);
   const float pi_o_4 = MM_U2F(0x3f490fdbu), pi_o_2 = MM_U2F(0x3fc90fdbu), pi = MM_U2F(0x40490fdbu),
@@ -433,7 +440,7 @@ MM_HD float mm_acos_pq(float z)
   return MM_FDIV(p, q);
 }
 
-MM_HD float mm_acosf(float x)
+MM_HDL float mm_acosf(float x)
 {
   const float pio2_hi = MM_U2F(0x3fc90fdau), pio2_lo = MM_U2F(0x33a22168u), pi = MM_U2F(0x40490fdau);
   const int32_t hx = (int32_t)MM_F2U(x);
@@ -488,7 +495,7 @@ MM_HD float mm_asin_poly(float t)
   return MM_FMUL(t, w);
 }
 
-MM_HD float mm_asinf(float x)
+MM_HDL float mm_asinf(float x)
 {
   const float pio2_hi = MM_U2F(0x3fc90fdbu), pio2_lo = MM_U2F(0xb33bbd2eu), pio4_hi = MM_U2F(0x3f490fdbu);
   const int32_t hx = (int32_t)MM_F2U(x);
@@ -592,7 +599,7 @@ MM_HD float mm_kernel_tanf(float x, float y, int iy)
   return MM_FADD(t, MM_FMUL(a, MM_FADD(s, MM_FMUL(t, v))));
 }
 
-MM_HD float mm_tanf(float x)
+MM_HDL float mm_tanf(float x)
 {
   const int32_t ix = (int32_t)(MM_F2U(x) & 0x7fffffffu);
   if (ix <= 0x3f490fda) return mm_kernel_tanf(x, 0.0f, 1);
