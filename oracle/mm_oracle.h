@@ -7,16 +7,19 @@
  * It is a plain-C restatement of the reference's algorithm (FAU-LMS/vvc-extension-mm,
  * VTM-17.2 + MM); every function cites the reference file:line it follows.
  *
- * PARITY STATUS
+ * PARITY STATUS (details: DESIGN.md section 2)
  *   integer steps (FIR, clip, OOB zero fill, SAD, HAD, DMVR cost, weighted average):
- *       pinned by source -- scalar C++ in the reference fully determines the result.
- *   float mapping: the reference cannot be compiled on this box (Eigen 3.3.7 is fetched from
- *       the network at build time, source/3rdparty/External-Eigen3.cmake:4-6) and ships no
- *       tests or golden vectors, so the Eigen-specific parts (SSE psin/pcos packets, packet vs
- *       scalar traversal, 3-term dot association, round) are "PARITY UNPINNED": restated from
- *       Eigen 3.3.7's published sources as recalled.  The libm part calls the REAL glibc libm
- *       of the box (sinf, cosf, tanf, atanf, atan2f, acosf, asinf, roundf, sin, cos), so it is
- *       the reference's own arithmetic by construction.
+ *       PINNED against the reference's own InterpolationFilter.cpp / RdCost.cpp + SSE4.1/AVX2 units compiled
+ *       from /root/reference into oracle/_ref/libvtmref.so (tests/test_oracle_vs_reference_objects.py).
+ *   float mapping, operation order / model algebra / caching / quirks:
+ *       PINNED against the reference's own MVReprojection.cpp, MotionModels/*.cpp, Projection.cpp, Coordinate.cpp
+ *       compiled unchanged into oracle/_ref/libvtmmap.so (tests/test_oracle_vs_reference_mapping.py).
+ *   libm: the oracle calls the REAL glibc of the box (sinf cosf tanf atanf atan2f acosf asinf roundf sin cos).
+ *   Eigen 3.3.7 itself is not on the box (fetched from the network by the reference's cmake,
+ *       source/3rdparty/External-Eigen3.cmake:4-6) and the reference ships no tests or golden vectors:
+ *       libvtmmap.so is built against a functional stand-in (oracle/eigen_func_shim).  What that stand-in and
+ *       this file assert about Eigen -- SSE psin/pcos packets, packet-body/scalar-tail traversal, 3-term dot
+ *       association, scalar min/max, round -- is "PARITY UNPINNED": restated from Eigen 3.3.7 as recalled.
  */
 #ifndef MM_ORACLE_H
 #define MM_ORACLE_H

@@ -42,6 +42,12 @@ static float (*volatile l_asinf)(float) = asinf;
 static float (*volatile l_tanf)(float) = tanf;
 static float (*volatile l_roundf)(float) = roundf;
 static float (*volatile l_atan2f)(float, float) = atan2f;
+// gcc -O3 (the reference's release build) merges sin(x)/cos(x) pairs into sincosf: its two results must equal sinf/cosf
+static void (*volatile l_sincosf)(float, float*, float*) = sincosf;
+static float w_sincos_s(float x) { float s, c; l_sincosf(x, &s, &c); return s; }
+static float w_sincos_c(float x) { float s, c; l_sincosf(x, &s, &c); return c; }
+static float (*volatile l_sincos_s)(float) = w_sincos_s;
+static float (*volatile l_sincos_c)(float) = w_sincos_c;
 
 static uint64_t run1(const char* name, fn1 mine, float (*volatile* ref)(float), uint64_t stride, int nthreads)
 {
@@ -153,6 +159,8 @@ int main(int argc, char** argv)
   uint64_t bad = 0;
   bad += run1("sinf", w_sinf, &l_sinf, stride, nthreads);
   bad += run1("cosf", w_cosf, &l_cosf, stride, nthreads);
+  bad += run1("sincosf.s", w_sinf, &l_sincos_s, stride, nthreads);
+  bad += run1("sincosf.c", w_cosf, &l_sincos_c, stride, nthreads);
   bad += run1("atanf", w_atanf, &l_atanf, stride, nthreads);
   bad += run1("acosf", w_acosf, &l_acosf, stride, nthreads);
   bad += run1("asinf", w_asinf, &l_asinf, stride, nthreads);

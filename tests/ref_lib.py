@@ -64,3 +64,62 @@ def sub_shift(w, h, mode):
 
 def dmvr_cost(a, b, bd=10):
     return int(lib().ref_dmvr_cost(a.ctypes.data, a.strides[0] // 2, b.ctypes.data, b.strides[0] // 2, a.shape[1], a.shape[0], bd))
+
+
+# ---- oracle/_ref/libvtmmap.so: the reference's own float-mapping source (compiled against oracle/eigen_func_shim) ----
+_MAP_SO = os.path.join(ROOT, "oracle", "_ref", "libvtmmap.so")
+_map = None
+
+
+def map_available():
+    if not os.path.exists(_MAP_SO) and os.path.isdir("/root/reference/source/Lib/CommonLib"):
+        subprocess.call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_MAP_SO)
+
+
+def maplib():
+    global _map
+    if _map is None:
+        L = C.CDLL(_MAP_SO)
+        L.refmap_create.restype = C.c_void_p
+        L.refmap_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int]
+        L.refmap_set_epipole.argtypes = [C.c_float] * 3
+        L.refmap_rodrigues.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.refmap_reproject.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_void_p]
+        L.refmap_mpa_cache.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _map = L
+    return _map
+
+
+class RefMap:
+    """MVReprojection of the reference itself (MVReprojection.cpp + MotionModels/*.cpp + Projection.cpp + Coordinate.cpp)."""
+
+    def __init__(self, w, h, offset4x4=1.0, ged_flavor=1):
+        self.L, self.w, self.h = maplib(), w, h
+        self.h_ = self.L.refmap_create(w, h, offset4x4, ged_flavor)
+
+    def set_epipole(self, e):
+        self.L.refmap_set_epipole(float(e[0]), float(e[1]), float(e[2]))
+
+    def rodrigues(self, e):
+        R = np.zeros(9, dtype=np.float32)
+        self.L.refmap_rodrigues(self.h_, float(e[0]), float(e[1]), float(e[2]), R.ctypes.data)
+        return R
+
+    def reproject(self, pos, size, mv, model, comp=0, chroma_fmt=0, cur_poc=0, ref_poc=1):
+        sx = 1 if (comp and chroma_fmt in (1, 2)) else 0
+        sy = 1 if (comp and chroma_fmt == 1) else 0
+        n = (size[1] // (4 >> sy)) * (size[0] // (4 >> sx))
+        ox = np.zeros(n, dtype=np.int32)
+        oy = np.zeros(n, dtype=np.int32)
+        self.L.refmap_reproject(self.h_, pos[0], pos[1], size[0], size[1], mv[0], mv[1], model, comp, chroma_fmt, cur_poc, ref_poc,
+                                ox.ctypes.data, oy.ctypes.data)
+        return ox, oy
+
+    def mpa_cache(self, model):
+        n = (self.w // 4) * (self.h // 4)
+        px = np.zeros(n, dtype=np.float32)
+        py = np.zeros(n, dtype=np.float32)
+        v = np.zeros(n, dtype=np.uint8)
+        self.L.refmap_mpa_cache(self.h_, model, px.ctypes.data, py.ctypes.data, v.ctypes.data)
+        return px, py, v

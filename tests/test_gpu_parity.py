@@ -358,3 +358,33 @@ def test_dmvr_projected_costs_and_decision(env):
         assert np.array_equal(exp, got[i]), (i, s, exp, got[i])
         assert mm.dmvr_decide(got[i], int(s["w"]), int(s["h"])) == ol.dmvr_decide(exp, int(s["w"]), int(s["h"]))
     o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(EPIPOLE))
+
+
+def test_gpu_positions_equal_reference_source_directly(env):
+    """The sm_100a mapping against the reference's OWN MVReprojection/MotionModels source (oracle/_ref/libvtmmap.so,
+    compiled against the Eigen stand-in) without the oracle in between."""
+    import ref_lib as rl
+    if not rl.map_available():
+        pytest.skip("oracle/_ref/libvtmmap.so not present")
+    o, g, *_ = env
+    ref = rl.RefMap(W, H, 1.0, 1)
+    ref.set_epipole(EPIPOLE)
+    g.set_rotation(0, mm.rodrigues(EPIPOLE))
+    rng = np.random.default_rng(4242)
+    n = 0
+    for it in range(600):
+        w, h = SIZES[it % len(SIZES)]
+        x, y = rand_block(rng, w, h)
+        if it % 8 == 0: y = 0 if it % 16 else H - h
+        mv = (int(rng.integers(-1000, 1000)), int(rng.integers(-500, 500)))
+        if it % 10 == 0: mv = (0, 0)
+        m = 1 + it % 10
+        ax, ay = ref.reproject((x, y), (w, h), mv, m)
+        bx, by = g.reproject((x, y), (w, h), mv, m)
+        assert np.array_equal(ax, bx) and np.array_equal(ay, by), (m, x, y, w, h, mv)
+        if w >= 8 and h >= 8:
+            ax, ay = ref.reproject((x // 2, y // 2), (w // 2, h // 2), mv, m, comp=1, chroma_fmt=1)
+            bx, by = g.reproject((x // 2, y // 2), (w // 2, h // 2), mv, m, comp=1, chroma_fmt=1)
+            assert np.array_equal(ax, bx) and np.array_equal(ay, by), ("chroma", m, x, y, w, h, mv)
+        n += len(ax)
+    assert n > 10000
