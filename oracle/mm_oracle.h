@@ -12,7 +12,7 @@
  *       PINNED against the reference's own InterpolationFilter.cpp / RdCost.cpp + SSE4.1/AVX2 units compiled
  *       from /root/reference into oracle/_ref/libvtmref.so (tests/test_oracle_vs_reference_objects.py).
  *   float mapping, operation order / model algebra / caching / quirks:
- *       PINNED against the reference's own MVReprojection.cpp, MotionModels/*.cpp, Projection.cpp, Coordinate.cpp
+ *       PINNED against the reference's own MVReprojection.cpp, MotionModels/<model>.cpp, Projection.cpp, Coordinate.cpp
  *       compiled unchanged into oracle/_ref/libvtmmap.so (tests/test_oracle_vs_reference_mapping.py).
  *   libm: the oracle calls the REAL glibc of the box (sinf cosf tanf atanf atan2f acosf asinf roundf sin cos).
  *   Eigen 3.3.7 itself is not on the box (fetched from the network by the reference's cmake,

@@ -228,6 +228,36 @@ __global__ void k_trig_tables(MmGeom g, float2* th0, float2* th1, float2* ph0, f
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_build_items: the work list of a batch, one warp per block.  itemBase[b] = first work item of block b
+// (host-computed, grouped by motion model); also fills the candidate -> block map used by k_cand_setup.
+// -------------------------------------------------------------------------------------------------
+__global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ itemBase, int nBlocks,
+                              MmItem* __restrict__ items, int32_t* __restrict__ candBlock)
+{
+  const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (bi >= nBlocks) return;
+  const mmgpu_block b = blocks[bi];
+  const int n = (b.w >> 2) * (b.h >> 2);
+  const int base = itemBase[bi];
+  for (int j = lane; j < b.cand_count; j += 32) candBlock[b.cand_first + j] = bi;
+  if (n >= 32)
+  {
+    const int chunks = n >> 5, total = b.cand_count * chunks;
+    for (int t = lane; t < total; t += 32)
+    {
+      const int c = t / chunks, ch = t - c * chunks;
+      items[base + t] = MmItem{bi, b.cand_first + c, ch << 5, 0};
+    }
+  }
+  else
+  {
+    const int per = 32 / n, total = (b.cand_count + per - 1) / per;
+    for (int t = lane; t < total; t += 32) items[base + t] = MmItem{bi, b.cand_first + t * per, 0, 0};
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // k_cand_setup: one thread per candidate MV
 // -------------------------------------------------------------------------------------------------
 __global__ void k_cand_setup(MmGeom g, const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ candBlock,

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "mm_kernels.cuh"
@@ -20,7 +21,8 @@ struct mmgpu_plan
   MmItem* dItems;
   int32_t* dCandBlock;
   MmCand* dCands;
-  size_t capBlocks, capItems, capCands, capCandParams;
+  int32_t* dItemBase;
+  size_t capBlocks, capItems, capCands, capCandParams, capItemBase;
 };
 
 struct mmgpu_ctx
@@ -59,6 +61,11 @@ struct mmgpu_ctx
   size_t capSubpus;
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
+  // pinned host staging for small per-call tables (reused; guarded by an event)
+  void* hStage;
+  size_t capStage;
+  cudaEvent_t stageFree;
+  bool stageBusy;
   // optional CUDA-event timing of k_me
   bool timing;
   std::vector<cudaEvent_t> evPool;   // start/stop pairs
@@ -185,6 +192,9 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   }
   ctx->launches = 0;
   ctx->timing = false;
+  ctx->hStage = nullptr;
+  ctx->capStage = 0;
+  ctx->stageBusy = false;
   ctx->evUsed = 0;
   ctx->evAccumMs = 0;
   ctx->evAccumN = 0;
@@ -210,6 +220,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   f.cpShift = hr;
 
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->stageFree, cudaEventDisableTiming));
   ctx->hRefs.assign(cfg->max_refs, MmRef());
   ctx->ownedPlanes.assign((size_t)cfg->max_refs * 3, nullptr);
   CU(cudaMalloc(&ctx->dRefs, sizeof(MmRef) * cfg->max_refs));
@@ -254,6 +265,9 @@ static void freePlan(mmgpu_plan* p)
   cudaFree(p->dItems);
   cudaFree(p->dCandBlock);
   cudaFree(p->dCands);
+  cudaFree(p->dItemBase);
+  p->dItemBase = nullptr;
+  p->capItemBase = 0;
   p->dBlocks = nullptr; p->dItems = nullptr; p->dCandBlock = nullptr; p->dCands = nullptr;
   p->capBlocks = p->capItems = p->capCands = p->capCandParams = 0;
 }
@@ -273,6 +287,8 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dMvs);
   cudaFree(ctx->dDist);
   cudaFree(ctx->dTmp);
+  if (ctx->hStage) cudaFreeHost(ctx->hStage);
+  cudaEventDestroy(ctx->stageFree);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
   for (auto e : ctx->evPool) cudaEventDestroy(e);
@@ -456,6 +472,19 @@ extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9]
 }
 
 // ---- scratch -------------------------------------------------------------------------------------
+static int ensurePinned(mmgpu_ctx* ctx, size_t bytes)
+{
+  if (ctx->stageBusy) { CU(cudaEventSynchronize(ctx->stageFree)); ctx->stageBusy = false; }
+  if (ctx->capStage >= bytes) return MMGPU_OK;
+  if (ctx->hStage) cudaFreeHost(ctx->hStage);
+  ctx->hStage = nullptr;
+  ctx->capStage = 0;
+  const size_t n = bytes + bytes / 2 + 4096;
+  CU(cudaMallocHost(&ctx->hStage, n));
+  ctx->capStage = n;
+  return MMGPU_OK;
+}
+
 template <typename T>
 static int ensureCap(mmgpu_ctx* ctx, T** p, size_t* cap, size_t need)
 {
@@ -584,17 +613,22 @@ extern "C" int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stri
 }
 
 // ---- plans ---------------------------------------------------------------------------------------
+// Host part of a plan: validate the blocks, count the warps of work of each and lay them out grouped by motion model
+// (so the warps resident on an SM run the same model's code).  The work list itself and the candidate->block map are
+// written by k_build_items on the device; nothing here is O(candidates).
 static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_block* blocks, int n_cands, bool needOrg)
 {
-  // work items are grouped by motion model so that the warps resident on an SM run the same model's code
-  std::vector<MmItem> itemsByModel[MM_NUM_MODELS];
-  std::vector<int32_t> candBlock((size_t)n_cands, -1);
+  int rc;
+  if ((rc = ensurePinned(ctx, (size_t)n_blocks * sizeof(int32_t) * 2))) return rc;
+  int32_t* itemBase = reinterpret_cast<int32_t*>(ctx->hStage);
+  int32_t* order = itemBase + n_blocks;
+  long modelItems[MM_NUM_MODELS] = {0};
   uint64_t samples = 0;
+  long candSum = 0;
   for (int bi = 0; bi < n_blocks; ++bi)
   {
     const mmgpu_block& b = blocks[bi];
-    int rc = checkBlockShape(ctx, 0, 0, b.x, b.y, b.w, b.h);
-    if (rc) return rc;
+    if ((rc = checkBlockShape(ctx, 0, 0, b.x, b.y, b.w, b.h))) return rc;
     if (b.model < MMGPU_CLASSIC || b.model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "bad model in block");
     if (b.rot_slot < 0 || b.rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad rot_slot in block");
     if (b.ref_slot < 0 || b.ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[b.ref_slot].plane00[0])
@@ -604,41 +638,47 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
     if (needOrg && ((b.org_x & 3) || b.org_x < 0 || b.org_y < 0 || b.org_x + b.w > ctx->orgW || b.org_y + b.h > ctx->orgH))
       return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane (or org_x not a multiple of 4)");
     const int n = (b.w >> 2) * (b.h >> 2);
-    for (int c = 0; c < b.cand_count; ++c)
-    {
-      if (candBlock[b.cand_first + c] != -1) return fail(ctx, MMGPU_ERR_ARG, "candidate ranges of blocks overlap");
-      candBlock[b.cand_first + c] = bi;
-    }
-    std::vector<MmItem>& items = itemsByModel[b.model];
-    if (n >= 32)
-    {
-      for (int c = 0; c < b.cand_count; ++c)
-        for (int s = 0; s < n; s += 32) items.push_back(MmItem{bi, b.cand_first + c, s, 0});
-    }
-    else
-    {
-      const int per = 32 / n;
-      for (int c = 0; c < b.cand_count; c += per) items.push_back(MmItem{bi, b.cand_first + c, 0, 0});
-    }
+    const int nItems = (n >= 32) ? b.cand_count * (n >> 5) : (b.cand_count + (32 / n) - 1) / (32 / n);
+    itemBase[bi] = nItems;
+    order[bi] = bi;
+    modelItems[b.model] += nItems;
+    candSum += b.cand_count;
     samples += (uint64_t)b.w * b.h * b.cand_count;
   }
-  for (int i = 0; i < n_cands; ++i)
-    if (candBlock[i] < 0) return fail(ctx, MMGPU_ERR_ARG, "candidate not owned by any block");
-  std::vector<MmItem> items;
-  for (int m = 0; m < MM_NUM_MODELS; ++m) items.insert(items.end(), itemsByModel[m].begin(), itemsByModel[m].end());
-  int rc;
+  // candidate ranges must tile [0, n_cands): equal total + no overlap between neighbours in cand_first order
+  if (candSum != n_cands) return fail(ctx, MMGPU_ERR_ARG, "candidate ranges of the blocks do not cover the mv array exactly once");
+  std::sort(order, order + n_blocks, [blocks](int32_t a, int32_t b) { return blocks[a].cand_first < blocks[b].cand_first; });
+  long expect = 0;
+  for (int i = 0; i < n_blocks; ++i)
+  {
+    if (blocks[order[i]].cand_first != expect) return fail(ctx, MMGPU_ERR_ARG, "candidate ranges of blocks overlap or leave gaps");
+    expect += blocks[order[i]].cand_count;
+  }
+  long modelBase[MM_NUM_MODELS], total = 0;
+  for (int m = 0; m < MM_NUM_MODELS; ++m) { modelBase[m] = total; total += modelItems[m]; }
+  if (total > 0x7fffffffL) return fail(ctx, MMGPU_ERR_ARG, "batch too large");
+  for (int bi = 0; bi < n_blocks; ++bi)
+  {
+    const int cnt = itemBase[bi];
+    itemBase[bi] = (int32_t)modelBase[blocks[bi].model];
+    modelBase[blocks[bi].model] += cnt;
+  }
   if ((rc = ensureCap(ctx, &p->dBlocks, &p->capBlocks, (size_t)n_blocks))) return rc;
-  if ((rc = ensureCap(ctx, &p->dItems, &p->capItems, items.size()))) return rc;
+  if ((rc = ensureCap(ctx, &p->dItemBase, &p->capItemBase, (size_t)n_blocks))) return rc;
+  if ((rc = ensureCap(ctx, &p->dItems, &p->capItems, (size_t)total))) return rc;
   if ((rc = ensureCap(ctx, &p->dCandBlock, &p->capCands, (size_t)n_cands))) return rc;
   if ((rc = ensureCap(ctx, &p->dCands, &p->capCandParams, (size_t)n_cands))) return rc;
   CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(p->dItems, items.data(), sizeof(MmItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(p->dCandBlock, candBlock.data(), sizeof(int32_t) * n_cands, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));  // items/candBlock are stack vectors
+  CU(cudaMemcpyAsync(p->dItemBase, itemBase, sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
+  k_build_items<<<(n_blocks + 3) / 4, 128, 0, ctx->stream>>>(p->dBlocks, p->dItemBase, n_blocks, p->dItems, p->dCandBlock);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->stageFree, ctx->stream));  // the pinned staging buffer may be rewritten after this point
+  ctx->stageBusy = true;
   p->ctx = ctx;
   p->nBlocks = n_blocks;
   p->nCands = n_cands;
-  p->nItems = (int)items.size();
+  p->nItems = (int)total;
   p->samples = samples;
   return MMGPU_OK;
 }
@@ -651,6 +691,7 @@ extern "C" int mmgpu_plan_create(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block
   memset(p, 0, sizeof(*p));
   int rc = buildPlan(ctx, p, n_blocks, blocks, n_cands, false);
   if (rc) { freePlan(p); delete p; return rc; }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { freePlan(p); delete p; return fail(ctx, MMGPU_ERR_CUDA, "plan upload failed"); }
   *out = p;
   return MMGPU_OK;
 }
