@@ -30,7 +30,7 @@ struct MmItem  // one warp of work
   int32_t block;  // index into blocks
   int32_t cand;   // first candidate (global index) handled by this warp
   int32_t sb;     // first sub-block (tile-major index) handled by this warp
-  int32_t pad;
+  int32_t ncand;  // number of consecutive candidates this warp evaluates
 };
 
 struct MmFir  // InterpolationFilter::filter<> shifts/offsets for the context's bit depth
@@ -132,11 +132,18 @@ __device__ __forceinline__ MmSub mm_sub_from_index(int w, int h, int s)
   return r;
 }
 
-// Position of one sub-block in 1/16 (luma) or 1/32 (chroma 4:2:0) pel: mapping + fixed-point conversion.
-__device__ __forceinline__ void mm_subblock_pos(const MmGeom& g, const float2* const* mpa, const uint8_t* const* mpaVip,
-                                                const float2* const* thTab, const float2* const* phTab, int model,
-                                                int comp, int csx, int csy, int posX, int posY, int sizeW, int sizeH,
-                                                const MmCand& c, const float* R, int row, int col, int* fx, int* fy)
+// Candidate-independent state of one sub-block: its coordinates, packet flag and the model's prepared values.
+struct MmSbState
+{
+  float X, Y;
+  bool pk;
+  MmInv inv;
+};
+
+__device__ __forceinline__ void mm_subblock_prepare(const MmGeom& g, const float2* const* mpa, const uint8_t* const* mpaVip,
+                                                    const float2* const* thTab, const float2* const* phTab, int model,
+                                                    int comp, int csx, int csy, int posX, int posY, int sizeW, int sizeH,
+                                                    const MmCand& blk, const float* R, int row, int col, MmSbState* st)
 {
   const int sbw = 4 >> csx, sbh = 4 >> csy;
   const int rows = sizeH / sbh, cols = sizeW / sbw;
@@ -181,9 +188,30 @@ __device__ __forceinline__ void mm_subblock_pos(const MmGeom& g, const float2* c
     tr.st = t.x; tr.ct = t.y; tr.sp = q.x; tr.cp = q.y;
     tr.valid = true;
   }
+  st->X = X;
+  st->Y = Y;
+  st->pk = pk;
+  mm_model_prepare(g, model, isLuma, blk, R, X, Y, pk, cPX, cPY, cVip, tr, &st->inv);
+}
+
+__device__ __forceinline__ void mm_subblock_apply(const MmGeom& g, int model, int comp, int csx, int csy, const MmCand& c,
+                                                  const float* R, const MmSbState& st, int* fx, int* fy)
+{
+  const bool isLuma = comp == 0;
   float MX, MY;
-  mm_model_motion(g, model, isLuma, c, R, X, Y, pk, cPX, cPY, cVip, tr, &MX, &MY);
-  mm_to_fixed(g, X, Y, MX, MY, isLuma ? 0 : csx, isLuma ? 0 : csy, fx, fy);
+  mm_model_apply(g, model, isLuma, c, R, st.X, st.Y, st.pk, st.inv, &MX, &MY);
+  mm_to_fixed(g, st.X, st.Y, MX, MY, isLuma ? 0 : csx, isLuma ? 0 : csy, fx, fy);
+}
+
+// Position of one sub-block in 1/16 (luma) or 1/32 (chroma 4:2:0) pel: mapping + fixed-point conversion.
+__device__ __forceinline__ void mm_subblock_pos(const MmGeom& g, const float2* const* mpa, const uint8_t* const* mpaVip,
+                                                const float2* const* thTab, const float2* const* phTab, int model,
+                                                int comp, int csx, int csy, int posX, int posY, int sizeW, int sizeH,
+                                                const MmCand& c, const float* R, int row, int col, int* fx, int* fy)
+{
+  MmSbState st;
+  mm_subblock_prepare(g, mpa, mpaVip, thTab, phTab, model, comp, csx, csy, posX, posY, sizeW, sizeH, c, R, row, col, &st);
+  mm_subblock_apply(g, model, comp, csx, csy, c, R, st, fx, fy);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -232,7 +260,7 @@ __global__ void k_trig_tables(MmGeom g, float2* th0, float2* th1, float2* ph0, f
 // (host-computed, grouped by motion model); also fills the candidate -> block map used by k_cand_setup.
 // -------------------------------------------------------------------------------------------------
 __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ itemBase, int nBlocks,
-                              MmItem* __restrict__ items, int32_t* __restrict__ candBlock)
+                              int candChunk, MmItem* __restrict__ items, int32_t* __restrict__ candBlock)
 {
   const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,19 +269,23 @@ __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int3
   const int n = (b.w >> 2) * (b.h >> 2);
   const int base = itemBase[bi];
   for (int j = lane; j < b.cand_count; j += 32) candBlock[b.cand_first + j] = bi;
+  // a work item = up to candChunk candidates (n >= 32) or candChunk steps of 32/n candidates (n < 32) of one
+  // 32-sub-block chunk: the warp prepares the candidate-independent state once and loops over the candidates
   if (n >= 32)
   {
-    const int chunks = n >> 5, total = b.cand_count * chunks;
+    const int chunks = n >> 5, groups = (b.cand_count + candChunk - 1) / candChunk, total = groups * chunks;
     for (int t = lane; t < total; t += 32)
     {
-      const int c = t / chunks, ch = t - c * chunks;
-      items[base + t] = MmItem{bi, b.cand_first + c, ch << 5, 0};
+      const int gidx = t / chunks, ch = t - gidx * chunks;
+      const int c0 = gidx * candChunk;
+      items[base + t] = MmItem{bi, b.cand_first + c0, ch << 5, min(candChunk, b.cand_count - c0)};
     }
   }
   else
   {
-    const int per = 32 / n, total = (b.cand_count + per - 1) / per;
-    for (int t = lane; t < total; t += 32) items[base + t] = MmItem{bi, b.cand_first + t * per, 0, 0};
+    const int per = (32 / n) * candChunk, total = (b.cand_count + per - 1) / per;
+    for (int t = lane; t < total; t += 32)
+      items[base + t] = MmItem{bi, b.cand_first + t * per, 0, min(per, b.cand_count - t * per)};
   }
 }
 

@@ -284,7 +284,7 @@ MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int 
   }
   else if (model == MM_TANGENTIAL)
   {
-    if (c->mvZero) return;
+    // block constants (block centre only): filled for zero MVs too, the candidate loop reads them from any candidate
     float cc[3], sc[3];
     mm_erp_to_sphere_sc(g, bcx, bcy, cc);
     mm_sc_cart_to_sph(cc, sc);
@@ -315,12 +315,68 @@ MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int 
 }
 
 // ---- one sub-block -------------------------------------------------------------------------------
-// X,Y: luma-scale coordinates of the sub-block (4*i + off).  For luma MPA the caller passes the cached
-// motion-plane coordinates (cPX,cPY,cVip) of the picture-wide cache.  `tr` = optional table values of the
-// original position (see mm_erp_to_sphere_grid).  Returns moved coordinates (float, before NaN handling).
-// Every model ends in EquirectangularProjection::fromSphere of the moved point u: one shared tail.
-MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand& c, const float* R, float X, float Y,
-                           bool pk, float cPX, float cPY, bool cVip, const MmTrig& tr, float* MX, float* MY)
+// The mapping of a sub-block is split into the part that does not depend on the candidate MV (mm_model_prepare:
+// the reference recomputes it per call, encoder-side memoisation aside -- quirk Q8 says that has no numeric effect)
+// and the per-candidate part (mm_model_apply).  k_me prepares once per warp and applies per candidate.
+struct MmInv
+{
+  float a, b, c, d, e;  // MPA: PX,PY | GED: r,theta,phi,sinf(theta),cosf(theta) | ROT/3DT: s0,s1,s2 | TAN: yPl,xPl
+  bool flag;            // MPA: virtual image plane
+};
+
+// X,Y: luma-scale coordinates of the sub-block (4*i + off).  For luma MPA the caller passes the cached motion-plane
+// coordinates (cPX,cPY,cVip) of the picture-wide cache.  `tr` = optional table values of the original position.
+// `blk` = any candidate of the block (TAN block constants p[0..2] are MV independent).
+MM_HD void mm_model_prepare(const MmGeom& g, int model, bool isLuma, const MmCand& blk, const float* R, float X, float Y,
+                            bool pk, float cPX, float cPY, bool cVip, const MmTrig& tr, MmInv* inv)
+{
+  const bool fma = g.fmaBuild != 0;
+  inv->a = inv->b = inv->c = inv->d = inv->e = 0.0f;
+  inv->flag = false;
+  if (model >= MM_MPA_FRONT_BACK && model <= MM_MPA_TOP_BOTTOM)
+  {
+    float PX = cPX, PY = cPY;
+    bool vip = cVip;
+    if (!isLuma) mm_mpa_to_perspective(g, model, X, Y, pk, tr, &PX, &PY, &vip);
+    inv->a = PX; inv->b = PY; inv->flag = vip;
+    return;
+  }
+  float s[3];
+  mm_erp_to_sphere_grid(g, X, Y, pk, tr, s);
+  if (model >= MM_GEODESIC_X && model <= MM_GEODESIC_CAMPOSE)
+  {
+    float r, th, ph;
+    const float rx = mm_dot3(R[0], s[0], R[1], s[1], R[2], s[2]);
+    const float ry = mm_dot3(R[3], s[0], R[4], s[1], R[5], s[2]);
+    const float rz = mm_dot3(R[6], s[0], R[7], s[1], R[8], s[2]);
+    mm_arr_cart_to_sph(rx, ry, rz, &r, &th, &ph);
+    inv->a = r; inv->b = th; inv->c = ph;
+    if (g.gedModulated) { inv->d = mm_sinf(th, fma); inv->e = mm_cosf(th, fma); }
+  }
+  else if (model == MM_TANGENTIAL)
+  {
+    const float alphaC = blk.p[0], sinC = blk.p[1], cosC = blk.p[2];
+    float r, th, ph;
+    mm_arr_cart_to_sph(s[0], s[1], s[2], &r, &th, &ph);
+    const float eps = MM_FSUB(MM_PI_2_F, th);
+    const float dAl = MM_FSUB(ph, alphaC);
+    float se, ce, sd, cd;
+    mm_sincos_pk(eps, pk, fma, &se, &ce);
+    mm_sincos_pk(dAl, pk, fma, &sd, &cd);
+    const float cosPsi = MM_FADD(MM_FMUL(sinC, se), MM_FMUL(MM_FMUL(cosC, ce), cd));
+    inv->a = MM_FDIV(MM_FSUB(MM_FMUL(se, cosC), MM_FMUL(MM_FMUL(sinC, ce), cd)), cosPsi);  // cart2DYPlane
+    inv->b = MM_FDIV(MM_FMUL(sd, ce), cosPsi);                                              // cart2DXPlane
+  }
+  else
+  {
+    inv->a = s[0]; inv->b = s[1]; inv->c = s[2];
+  }
+}
+
+// Returns moved coordinates (float, before NaN handling).  Every model ends in EquirectangularProjection::fromSphere
+// of the moved point u: one shared tail.
+MM_HD void mm_model_apply(const MmGeom& g, int model, bool isLuma, const MmCand& c, const float* R, float X, float Y,
+                          bool pk, const MmInv& inv, float* MX, float* MY)
 {
   const bool fma = g.fmaBuild != 0;
   *MX = X;
@@ -328,12 +384,10 @@ MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand
   float u0, u1, u2;
   if (model >= MM_MPA_FRONT_BACK && model <= MM_MPA_TOP_BOTTOM)
   {
-    float PX = cPX, PY = cPY;
-    bool vip = cVip;
-    if (!isLuma) mm_mpa_to_perspective(g, model, X, Y, pk, tr, &PX, &PY, &vip);
+    const bool vip = inv.flag;
     const float sgn = vip ? -1.0f : 1.0f;
-    const float QX = MM_FADD(PX, MM_FMUL(c.mvX, sgn));
-    const float QY = MM_FADD(PY, MM_FMUL(c.mvY, sgn));
+    const float QX = MM_FADD(inv.a, MM_FMUL(c.mvX, sgn));
+    const float QY = MM_FADD(inv.b, MM_FMUL(c.mvY, sgn));
     float m[3];
     mm_pers_to_sphere_arr(g, QX, QY, vip, pk, m);  // MotionPlaneAdaptiveMotionModel::toProjection (:163-187)
     if (model == MM_MPA_FRONT_BACK) { u0 = m[0]; u1 = m[1]; u2 = m[2]; }
@@ -344,18 +398,12 @@ MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand
   {
     const bool ged = model >= MM_GEODESIC_X && model <= MM_GEODESIC_CAMPOSE;
     if (c.mvZero && !(ged && isLuma)) return;  // quirk Q3: identity for mv == 0 (not for cached GED)
-    float s[3];
-    mm_erp_to_sphere_grid(g, X, Y, pk, tr, s);
     if (ged)
     {
-      float r, th, ph;
-      const float rx = mm_dot3(R[0], s[0], R[1], s[1], R[2], s[2]);
-      const float ry = mm_dot3(R[3], s[0], R[4], s[1], R[5], s[2]);
-      const float rz = mm_dot3(R[6], s[0], R[7], s[1], R[8], s[2]);
-      mm_arr_cart_to_sph(rx, ry, rz, &r, &th, &ph);
+      const float r = inv.a, th = inv.b, ph = inv.c;
       float thM;
       if (!g.gedModulated) thM = MM_FADD(th, c.p[1]);
-      else thM = MM_FADD(th, mm_atanf(MM_FDIV(mm_sinf(th, fma), MM_FSUB(c.p[0], mm_cosf(th, fma)))));
+      else thM = MM_FADD(th, mm_atanf(MM_FDIV(inv.d, MM_FSUB(c.p[0], inv.e))));
       const float phM = MM_FADD(ph, c.p[2]);
       float q[3];
       mm_arr_sph_to_cart(r, thM, phM, pk, fma, q);
@@ -365,31 +413,21 @@ MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand
     }
     else if (model == MM_ROTATIONAL)
     {
-      u0 = mm_dot3(c.p[0], s[0], c.p[1], s[1], c.p[2], s[2]);
-      u1 = mm_dot3(c.p[3], s[0], c.p[4], s[1], c.p[5], s[2]);
-      u2 = mm_dot3(c.p[6], s[0], c.p[7], s[1], c.p[8], s[2]);
+      u0 = mm_dot3(c.p[0], inv.a, c.p[1], inv.b, c.p[2], inv.c);
+      u1 = mm_dot3(c.p[3], inv.a, c.p[4], inv.b, c.p[5], inv.c);
+      u2 = mm_dot3(c.p[6], inv.a, c.p[7], inv.b, c.p[8], inv.c);
     }
     else if (model == MM_THREE_D_TRANSLATIONAL)
     {
-      u0 = MM_FADD(s[0], c.p[0]);
-      u1 = MM_FADD(s[1], c.p[1]);
-      u2 = MM_FADD(s[2], c.p[2]);
+      u0 = MM_FADD(inv.a, c.p[0]);
+      u1 = MM_FADD(inv.b, c.p[1]);
+      u2 = MM_FADD(inv.c, c.p[2]);
     }
     else if (model == MM_TANGENTIAL)
     {
       const float alphaC = c.p[0], sinC = c.p[1], cosC = c.p[2];
-      float r, th, ph;
-      mm_arr_cart_to_sph(s[0], s[1], s[2], &r, &th, &ph);
-      const float eps = MM_FSUB(MM_PI_2_F, th);
-      const float dAl = MM_FSUB(ph, alphaC);
-      float se, ce, sd, cd;
-      mm_sincos_pk(eps, pk, fma, &se, &ce);
-      mm_sincos_pk(dAl, pk, fma, &sd, &cd);
-      const float cosPsi = MM_FADD(MM_FMUL(sinC, se), MM_FMUL(MM_FMUL(cosC, ce), cd));
-      const float yPl = MM_FDIV(MM_FSUB(MM_FMUL(se, cosC), MM_FMUL(MM_FMUL(sinC, ce), cd)), cosPsi);
-      const float xPl = MM_FDIV(MM_FMUL(sd, ce), cosPsi);
-      const float yM = MM_FSUB(yPl, c.p[3]);
-      const float xM = MM_FSUB(xPl, c.p[4]);
+      const float yM = MM_FSUB(inv.a, c.p[3]);
+      const float xM = MM_FSUB(inv.b, c.p[4]);
       const float rho = MM_FSQRT(MM_FADD(MM_FMUL(xM, xM), MM_FMUL(yM, yM)));
       const float eta = mm_atanf(rho);
       float sEp, cEp;
@@ -410,6 +448,14 @@ MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand
     }
   }
   mm_erp_from_sphere_arr(g, u0, u1, u2, MX, MY);
+}
+
+MM_HD void mm_model_motion(const MmGeom& g, int model, bool isLuma, const MmCand& c, const float* R, float X, float Y,
+                           bool pk, float cPX, float cPY, bool cVip, const MmTrig& tr, float* MX, float* MY)
+{
+  MmInv inv;
+  mm_model_prepare(g, model, isLuma, c, R, X, Y, pk, cPX, cPY, cVip, tr, &inv);
+  mm_model_apply(g, model, isLuma, c, R, X, Y, pk, inv, MX, MY);
 }
 
 // MVReprojection.cpp:152-165: NaN -> no motion, remove offset, chroma rescale, std::round to fixed point.

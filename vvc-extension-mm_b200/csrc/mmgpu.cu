@@ -62,6 +62,7 @@ struct mmgpu_ctx
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
   // pinned host staging for small per-call tables (reused; guarded by an event)
+  int candChunk;  // candidates evaluated by one warp per work item (amortises the candidate-independent part)
   void* hStage;
   size_t capStage;
   cudaEvent_t stageFree;
@@ -194,6 +195,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   ctx->timing = false;
   ctx->hStage = nullptr;
   ctx->capStage = 0;
+  ctx->candChunk = 1;  // k_me evaluates one candidate per work item (a candidate loop was measured slower: DESIGN.md 4)
   ctx->stageBusy = false;
   ctx->evUsed = 0;
   ctx->evAccumMs = 0;
@@ -638,7 +640,9 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
     if (needOrg && ((b.org_x & 3) || b.org_x < 0 || b.org_y < 0 || b.org_x + b.w > ctx->orgW || b.org_y + b.h > ctx->orgH))
       return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane (or org_x not a multiple of 4)");
     const int n = (b.w >> 2) * (b.h >> 2);
-    const int nItems = (n >= 32) ? b.cand_count * (n >> 5) : (b.cand_count + (32 / n) - 1) / (32 / n);
+    const int chunk = ctx->candChunk;
+    const int nItems = (n >= 32) ? ((b.cand_count + chunk - 1) / chunk) * (n >> 5)
+                                 : (b.cand_count + (32 / n) * chunk - 1) / ((32 / n) * chunk);
     itemBase[bi] = nItems;
     order[bi] = bi;
     modelItems[b.model] += nItems;
@@ -670,7 +674,8 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   if ((rc = ensureCap(ctx, &p->dCands, &p->capCandParams, (size_t)n_cands))) return rc;
   CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(p->dItemBase, itemBase, sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-  k_build_items<<<(n_blocks + 3) / 4, 128, 0, ctx->stream>>>(p->dBlocks, p->dItemBase, n_blocks, p->dItems, p->dCandBlock);
+  k_build_items<<<(n_blocks + 3) / 4, 128, 0, ctx->stream>>>(p->dBlocks, p->dItemBase, n_blocks, ctx->candChunk, p->dItems,
+                                                            p->dCandBlock);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->stageFree, ctx->stream));  // the pinned staging buffer may be rewritten after this point
