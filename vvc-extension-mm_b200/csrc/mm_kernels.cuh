@@ -591,10 +591,12 @@ enum { MM_MODE_DIST = 0, MM_MODE_PRED = 1 };
 // -------------------------------------------------------------------------------------------------
 // k_me: one warp per work item.
 // -------------------------------------------------------------------------------------------------
-template <int MODE>
 #ifndef MM_ME_MINBLOCKS
 #define MM_ME_MINBLOCKS 8
 #endif
+// MODEL >= 0: kernel specialised for one motion model (work items are grouped by model, the host launches one
+// kernel per model present in the batch: smaller code per kernel, no model dispatch); MODEL < 0: generic.
+template <int MODE, int MODEL>
 __global__ void __launch_bounds__(128, MM_ME_MINBLOCKS) k_me(const MmParams P)
 {
   __shared__ MmTaps s_taps[16];
@@ -617,15 +619,16 @@ __global__ void __launch_bounds__(128, MM_ME_MINBLOCKS) k_me(const MmParams P)
 
   int fx, fy;
   bool oob = false;
-  if (b.model == MM_CLASSIC)
+  const int model = (MODEL >= 0) ? MODEL : b.model;
+  if (model == MM_CLASSIC)
   {
     fx = ((b.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
     fy = ((b.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
   }
   else
   {
-    const float* R = mm_rot_ptr(P.rot, b.model, b.rot_slot);
-    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, b.model, 0, 0, 0, b.x, b.y, b.w, b.h, c, R, s.row, s.col, &fx, &fy);
+    const float* R = mm_rot_ptr(P.rot, model, b.rot_slot);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, b.x, b.y, b.w, b.h, c, R, s.row, s.col, &fx, &fy);
     const int mc = (P.oobMode == MMGPU_OOB_ME) ? 0 : P.maxCU;
     const int xP = fx >> 4, yP = fy >> 4;
     oob = (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4);
