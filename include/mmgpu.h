@@ -103,6 +103,22 @@ int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, int y, int 
 int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
              int rot_slot, int bi, int clp_min, int clp_max, int oob_mode, int16_t* dst, int dst_stride);
 
+/* Whole-picture reconstruction shape (DecCu::xReconInter -> InterPrediction::motionCompensation -> xPredInterUni /
+ * xPredInterBi, InterPrediction.cpp:455-681): many PUs x components in one call. */
+typedef struct {
+  int32_t comp;                  /* ComponentID 0/1/2 */
+  int32_t x, y, w, h;            /* pu.blocks[comp] position / size (component units) */
+  int32_t model;                 /* mmgpu_model, CLASSIC included */
+  int32_t bi;                    /* 0: uni (list 0 fields), 1: bi-prediction: both lists at 14 bit + PelBuf::addAvg */
+  int32_t ref_slot0, rot_slot0;
+  mmgpu_mv mv0;                  /* MV_PRECISION_INTERNAL */
+  int32_t ref_slot1, rot_slot1;
+  mmgpu_mv mv1;
+} mmgpu_mc_job;
+/* dst[c]: HOST planes of the (un-padded) picture being reconstructed; every job writes its block at (x,y). */
+int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max, int16_t* const dst[3],
+                  const int32_t dst_stride[3]);
+
 /* ---- a13: InterPrediction::xWeightedAverage -> PelBuf::addAvg (Buffer.cpp:551-587) ------------------ */
 int mmgpu_add_avg(mmgpu_ctx* ctx, const int16_t* src0, int s0_stride, const int16_t* src1, int s1_stride, int16_t* dst,
                   int dst_stride, int w, int h, int clp_min, int clp_max);

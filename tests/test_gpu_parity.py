@@ -388,3 +388,88 @@ def test_gpu_positions_equal_reference_source_directly(env):
             assert np.array_equal(ax, bx) and np.array_equal(ay, by), ("chroma", m, x, y, w, h, mv)
         n += len(ax)
     assert n > 10000
+
+
+def test_decoder_shape_full_picture_md5(env):
+    """BASELINE config 4 shape: reconstruct a whole 2048x1024 4:2:0 picture from per-PU (model, MVs, uni/bi) decisions --
+    DecCu::xReconInter -> motionCompensation -> xPredInterUni/xPredInterBi -> xPredInterBlkMM/xPredInterBlk + addAvg --
+    on the GPU in one mmgpu_mc_jobs call and on the oracle; the decoded-picture MD5s (PicYuvMD5 style: per plane) match."""
+    import hashlib
+    o, g, planes, ref, cur = env
+    ref1 = wl.pad_frame(wl.synth_frame(W, H, seed=41, shift=(-1.25, 0.75)), 288, 1)
+    g.set_ref(3, 16, [p.origin for p in ref1], [p.stride for p in ref1])
+    class P: pass
+    planes1 = []
+    for p in ref1:
+        q = P(); q.origin = p.origin; q.stride = p.stride; planes1.append(q)
+    Ra = ol.Oracle.rodrigues(EPIPOLE); Rb = ol.Oracle.rodrigues([0.1, 0.2, -0.97])
+    g.set_rotation(0, mm.rodrigues(EPIPOLE)); g.set_rotation(2, mm.rodrigues([0.1, 0.2, -0.97]))
+    rng = np.random.default_rng(2026)
+    part = wl.frame_partition(W, H, seed=77)
+    jobs = []
+    exp = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
+    for (x, y, w, h) in part:
+        model = int(rng.integers(0, 11))
+        bi = bool(rng.random() < 0.3) and (w * h > 32)          # 8x4 / 4x8 PUs are uni-predicted in VVC
+        mv0 = (int(rng.integers(-700, 700)), int(rng.integers(-400, 400)))
+        mv1 = (int(rng.integers(-700, 700)), int(rng.integers(-400, 400)))
+        if rng.random() < 0.1: mv0 = ((mv0[0] >> 4) << 4, (mv0[1] >> 4) << 4)
+        for comp in range(3):
+            cx, cy, cw, ch = (x, y, w, h) if comp == 0 else (x // 2, y // 2, w // 2, h // 2)
+            jobs.append((comp, cx, cy, cw, ch, model, int(bi), 0, 0, mv0[0], mv0[1], 3, 2, mv1[0], mv1[1]))
+            def mc(pl, mv, R, want_bi):
+                if model == 0:
+                    return o.mc_block_classic(pl[comp], comp, 1, (cx, cy), (cw, ch), mv, want_bi)
+                if model == ol.GED_CAMPOSE:
+                    o.set_rotation(ol.GED_CAMPOSE, R)
+                return o.mc_block(pl[comp], comp, 1, (cx, cy), (cw, ch), mv, model, want_bi)
+            a = mc(planes, mv0, Ra, bi)
+            if bi:
+                b = mc(planes1, mv1, Rb, True)
+                out = np.zeros_like(a)
+                ol.lib().orc_add_avg(a.ctypes.data, cw, b.ctypes.data, cw, out.ctypes.data, cw, cw, ch, 10, 0, 1023)
+                a = out
+            exp[comp][cy:cy + ch, cx:cx + cw] = a
+    o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(EPIPOLE))
+    got = [np.full((H, W), -1, np.int16), np.full((H // 2, W // 2), -1, np.int16), np.full((H // 2, W // 2), -1, np.int16)]
+    g.mc_jobs(np.array(jobs, dtype=mm.JOB_DTYPE), got)
+    for c in range(3):
+        assert hashlib.md5(got[c].tobytes()).hexdigest() == hashlib.md5(exp[c].tobytes()).hexdigest(), \
+            ("plane", c, int((got[c] != exp[c]).sum()))
+    assert len(jobs) > 5000
+
+
+def test_config3_all_five_models_4096x2048():
+    """BASELINE config 3 shape: 4096x2048 10-bit ERP, low-delay-P search range (+-64), all five model families
+    (MPA x3, GED, ROT, TAN, 3DT) in one frame batch: SAD (integer search) and HAD (quarter-pel refinement) == oracle on a
+    sample of blocks, and the whole-batch checksum is block-order invariant."""
+    Wd, Hd = 4096, 2048
+    o = ol.Oracle(Wd, Hd)
+    g = mm.MmGpu(Wd, Hd, max_refs=1)
+    try:
+        o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues([1, 0, 0]))
+        g.set_rotation(0, mm.rodrigues([1, 0, 0]))
+        ref = wl.pad_frame(wl.synth_frame(Wd, Hd, seed=51), 288, 1)
+        cur = wl.synth_frame(Wd, Hd, seed=52, shift=(4.0, -2.0))
+        g.set_ref(0, 0, [p.origin for p in ref], [p.stride for p in ref])
+        g.set_org(cur[0])
+        class P: pass
+        pl = P(); pl.origin = ref[0].origin; pl.stride = ref[0].stride
+        models = (mm.MPA_FB, mm.MPA_LR, mm.MPA_TB, mm.GED_CAMPOSE, mm.ROT, mm.TAN, mm.T3D)
+        for frac, dist in ((False, mm.DIST_SAD), (True, mm.DIST_HAD)):
+            blocks, mvs, prec = wl.frame_batch(Wd, Hd, seed=9, cands_per_block=4, mv_range=64, models=models, frac=frac)
+            got = g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=dist)
+            rng = np.random.default_rng(1)
+            for bi in rng.choice(len(blocks), size=160, replace=False):
+                b = blocks[bi]
+                sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+                org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+                m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+                exp = o.me_block(pl, org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                                 mv_prec_shift=prec, dist=dist, had_mode=ol.HAD_SIMD)
+                assert np.array_equal(exp, got[sl]), (dict(zip(b.dtype.names, b.tolist())), exp, got[sl])
+            perm = np.random.default_rng(2).permutation(len(blocks))
+            assert np.array_equal(got, g.me_batch(blocks[perm], mvs, mv_prec_shift=prec, dist=dist))
+    finally:
+        g.close()
+        o.close()

@@ -11,5 +11,5 @@ from .api import (  # noqa: F401
     MmGpu, MmGpuError, MmPlan, Block, MODEL_NAMES,
     CLASSIC, MPA_FB, MPA_LR, MPA_TB, TAN, T3D, ROT, GED_X, GED_Y, GED_Z, GED_CAMPOSE,
     OOB_PRED, OOB_ME, DIST_SAD, DIST_HAD, HAD_SCALAR, HAD_SIMD,
-    rodrigues, fixed_to_float, exported_symbols, load_library, dmvr_decide, DMVR_DTYPE,
+    rodrigues, fixed_to_float, exported_symbols, load_library, dmvr_decide, DMVR_DTYPE, JOB_DTYPE,
 )

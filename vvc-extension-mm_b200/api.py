@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_me_batch", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs",
 ]
 
 
@@ -49,6 +49,9 @@ BLOCK_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), 
                         ("rot_slot", "<i4"), ("cand_first", "<i4"), ("cand_count", "<i4"), ("org_x", "<i4"),
                         ("org_y", "<i4"), ("reserved", "<i4")])
 MV_DTYPE = np.dtype([("hor", "<i4"), ("ver", "<i4")])
+JOB_DTYPE = np.dtype([("comp", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("model", "<i4"), ("bi", "<i4"),
+                      ("ref_slot0", "<i4"), ("rot_slot0", "<i4"), ("mv0_hor", "<i4"), ("mv0_ver", "<i4"),
+                      ("ref_slot1", "<i4"), ("rot_slot1", "<i4"), ("mv1_hor", "<i4"), ("mv1_ver", "<i4")])
 DMVR_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("model", "<i4"), ("ref_slot0", "<i4"),
                        ("ref_slot1", "<i4"), ("rot_slot0", "<i4"), ("rot_slot1", "<i4"), ("mv0_hor", "<i4"),
                        ("mv0_ver", "<i4"), ("mv1_hor", "<i4"), ("mv1_ver", "<i4")])
@@ -96,6 +99,7 @@ def load_library():
     L.mmgpu_plan_samples.argtypes = [vp]
     L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
     L.mmgpu_dmvr_costs.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.mmgpu_mc_jobs.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_dmvr_decide.argtypes = [vp, i32, i32, vp, vp]
     _lib = L
     return L
@@ -279,6 +283,14 @@ class MmGpu:
         self._chk(self.L.mmgpu_me_batch(self.h, len(blocks), blocks.ctypes.data, len(mvs), mvs.ctypes.data, mv_prec_shift,
                                         dist, sub_shift, clp[0], clp[1], out.ctypes.data))
         return out
+
+    def mc_jobs(self, jobs, planes, clp=(0, 1023)):
+        """Whole-picture reconstruction shape: jobs (JOB_DTYPE) write their predictions into `planes`
+        (list of 2-D int16 numpy arrays Y[,Cb,Cr], modified in place)."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        p, s = self._planes([a.ctypes.data for a in planes], [a.strides[0] // 2 for a in planes])
+        self._chk(self.L.mmgpu_mc_jobs(self.h, len(jobs), jobs.ctypes.data, clp[0], clp[1], p, s))
+        return planes
 
     def dmvr_costs(self, subpus, clp=(0, 1023)):
         """subpus: numpy array of DMVR_DTYPE -> (n, 25) uint64 xDMVRCost values at m_pSearchOffset."""

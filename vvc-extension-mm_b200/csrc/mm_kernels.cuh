@@ -4,6 +4,7 @@
 //   k_cand_setup       per-(block,mv) scalars of the motion models (mm_map.cuh: mm_cand_setup)
 //   k_reproject        MVReprojection::reprojectMotionVectorSubblocks (MVReprojection.cpp:80-166)
 //   k_mc_generic       xPredInterBlkMM / xPredInterBlk, any component, uni/bi (InterPrediction.cpp:683-856, 928-1096)
+//   k_mc_jobs          whole-picture reconstruction shape: jobs of any component, uni or bi with fused addAvg
 //   k_me<MODE>         fused map -> 8-tap separable FIR -> SAD/HAD for all candidates of all blocks
 //                      (InterSearch.cpp:6277-6385 + RdCost.cpp:482-.., 2943-3067), or prediction write-out
 //   k_extend_border    Picture::extendPicBorder (Picture.cpp:988-1048)
@@ -439,6 +440,74 @@ __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy
   else
     mm_fir_generic<4>(P.fir, ref.plane00[comp], ref.stride[comp], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, d,
                       dstStride);
+}
+
+// One sub-block of one component into `out` (row stride 4): mapping (or classic MV) + OOB rule + FIR.
+__device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w,
+                                               int h, mmgpu_mv mv, int model, int rotSlot, bool bi, int row, int col,
+                                               int16_t* out)
+{
+  const int sbw = 4 >> csx, sbh = 4 >> csy;
+  const MmRef ref = P.refs[refSlot];
+  const int shH = 4 + csx, shV = 4 + csy;
+  int fx, fy;
+  if (model == MM_CLASSIC)
+  {
+    fx = ((x + col * sbw) << shH) + mv.hor;
+    fy = ((y + row * sbh) << shV) + mv.ver;
+  }
+  else
+  {
+    const float* R = mm_rot_ptr(P.rot, model, rotSlot);
+    MmCand c;
+    mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
+    const int xP = fx >> shH, yP = fy >> shV;
+    const int picw = P.picW >> csx, pich = P.picH >> csy;
+    const int mcw = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csx);
+    const int mch = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csy);
+    if (xP < -mcw || yP < -mch || xP >= picw + mcw - sbw || yP >= pich + mch - sbh)
+    {
+      for (int i = 0; i < 16; ++i) out[i] = 0;
+      return;
+    }
+  }
+  const int xP = fx >> shH, yP = fy >> shV, xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  if (comp == 0)
+    mm_fir_generic<8>(P.fir, ref.plane00[0], ref.stride[0], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
+  else
+    mm_fir_generic<4>(P.fir, ref.plane00[comp], ref.stride[comp], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
+}
+
+// Whole-picture reconstruction shape (DecCu::xReconInter -> motionCompensation -> xPredInterUni / xPredInterBi,
+// InterPrediction.cpp:455-681): one CTA per job (one component of one PU); uni-prediction writes the clipped
+// prediction, bi-prediction interpolates both lists at 14 bit and applies PelBuf::addAvg (Buffer.cpp:551-587) in
+// registers before the store.  dst planes are un-padded device pictures.
+__global__ void k_mc_jobs(MmParams P, const mmgpu_mc_job* __restrict__ jobs, int16_t* dstY, int16_t* dstCb, int16_t* dstCr,
+                          int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset)
+{
+  const mmgpu_mc_job j = jobs[blockIdx.x];
+  const int csx = j.comp ? csxC : 0, csy = j.comp ? csyC : 0;
+  const int sbw = 4 >> csx, sbh = 4 >> csy;
+  const int rows = j.h / sbh, cols = j.w / sbw;
+  int16_t* plane = j.comp == 0 ? dstY : (j.comp == 1 ? dstCb : dstCr);
+  const int stride = j.comp == 0 ? strideY : strideC;
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+  {
+    const int col = i / rows, row = i - col * rows;
+    int16_t a[16], b[16];
+    mm_mc_subblock(P, j.ref_slot0, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv0, j.model, j.rot_slot0, j.bi != 0, row, col, a);
+    if (j.bi)
+    {
+      mm_mc_subblock(P, j.ref_slot1, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv1, j.model, j.rot_slot1, true, row, col, b);
+      for (int r = 0; r < sbh; ++r)
+        for (int q = 0; q < sbw; ++q)
+          a[r * 4 + q] = (int16_t)mm_clip(((int)a[r * 4 + q] + (int)b[r * 4 + q] + avgOffset) >> avgShift, P.clpMin, P.clpMax);
+    }
+    int16_t* d = plane + (long)(j.y + row * sbh) * stride + (j.x + col * sbw);
+    for (int r = 0; r < sbh; ++r)
+      for (int q = 0; q < sbw; ++q) d[(long)r * stride + q] = a[r * 4 + q];
+  }
 }
 
 // -------------------------------------------------------------------------------------------------

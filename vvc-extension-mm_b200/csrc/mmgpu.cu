@@ -60,6 +60,10 @@ struct mmgpu_ctx
   size_t capTmp;
   mmgpu_dmvr_subpu* dSubpus;
   size_t capSubpus;
+  mmgpu_mc_job* dJobs;
+  size_t capJobs;
+  int16_t* dPic[3];   // reconstruction picture planes for mmgpu_mc_jobs
+  size_t capPic[3];
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
   // pinned host staging for small per-call tables (reused; guarded by an event)
@@ -294,6 +298,8 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaEventDestroy(ctx->stageFree);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
+  cudaFree(ctx->dJobs);
+  for (int c = 0; c < 3; ++c) cudaFree(ctx->dPic[c]);
   for (auto e : ctx->evPool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -904,4 +910,61 @@ extern "C" int mmgpu_dmvr_decide(const uint64_t costs25[25], int w, int h, int32
   delta_mv[1] = total[1];
   if (min_cost) *min_cost = minCost;
   return notZero;
+}
+
+// ---- whole-picture reconstruction shape -------------------------------------------------------------------
+extern "C" int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max,
+                             int16_t* const dst[3], const int32_t dst_stride[3])
+{
+  if (!ctx || !jobs || !dst || !dst_stride || n_jobs <= 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  const int fmt = ctx->cfg.chroma_fmt;
+  bool used[3] = {false, false, false};
+  for (int i = 0; i < n_jobs; ++i)
+  {
+    const mmgpu_mc_job& j = jobs[i];
+    if (j.comp < 0 || j.comp >= numComps(ctx)) return fail(ctx, MMGPU_ERR_ARG, "bad component in job");
+    int rc = checkBlockShape(ctx, j.comp, fmt, j.x, j.y, j.w, j.h);
+    if (rc) return rc;
+    if (j.model < MMGPU_CLASSIC || j.model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "bad model in job");
+    const int nl = j.bi ? 2 : 1;
+    for (int l = 0; l < nl; ++l)
+    {
+      const int rs = l ? j.ref_slot1 : j.ref_slot0, ro = l ? j.rot_slot1 : j.rot_slot0;
+      if (rs < 0 || rs >= ctx->cfg.max_refs || !ctx->hRefs[rs].plane00[j.comp]) return fail(ctx, MMGPU_ERR_STATE, "job references an unset reference slot");
+      if (ro < 0 || ro >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad rot_slot in job");
+    }
+    used[j.comp] = true;
+  }
+  int rc;
+  int pitch[3] = {0, 0, 0}, cw[3], ch[3];
+  for (int c = 0; c < numComps(ctx); ++c)
+  {
+    int mx, my;
+    compDims(ctx, c, &cw[c], &ch[c], &mx, &my);
+    pitch[c] = (cw[c] + 63) / 64 * 64;
+    if (!used[c]) continue;
+    if (!dst[c]) return fail(ctx, MMGPU_ERR_ARG, "null destination plane");
+    if ((rc = ensureCap(ctx, &ctx->dPic[c], &ctx->capPic[c], (size_t)pitch[c] * ch[c]))) return rc;
+    // the caller's picture already holds the samples of blocks this call does not cover
+    CU(cudaMemcpy2DAsync(ctx->dPic[c], 2 * (size_t)pitch[c], dst[c], 2 * (size_t)dst_stride[c], 2 * (size_t)cw[c], ch[c],
+                         cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((rc = ensureCap(ctx, &ctx->dJobs, &ctx->capJobs, (size_t)n_jobs))) return rc;
+  CU(cudaMemcpyAsync(ctx->dJobs, jobs, sizeof(mmgpu_mc_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+  MmParams P = baseParams(ctx);
+  P.clpMin = clp_min;
+  P.clpMax = clp_max;
+  P.oobMode = MMGPU_OOB_PRED;
+  const int shift = ctx->fir.cpShift + 1, offset = (1 << (shift - 1)) + 2 * 8192;
+  k_mc_jobs<<<n_jobs, 64, 0, ctx->stream>>>(P, ctx->dJobs, ctx->dPic[0], ctx->dPic[1], ctx->dPic[2], pitch[0], pitch[1],
+                                           scaleX(1, fmt), scaleY(1, fmt), shift, offset);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  for (int c = 0; c < numComps(ctx); ++c)
+    if (used[c])
+      CU(cudaMemcpy2DAsync(dst[c], 2 * (size_t)dst_stride[c], ctx->dPic[c], 2 * (size_t)pitch[c], 2 * (size_t)cw[c], ch[c],
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
 }
