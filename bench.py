@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 
 W, H, CTU = 2048, 1024, 128
 CANDS = 16
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fir<DIST> launch of this workload, from the committed
+# `ncu --set full` capture (profiles/ncu_k_fir_r01c_summary.csv); None until that capture exists for the current kernel.
+NCU_TRAFFIC_BYTES = None
 POOL = 32            # synthetic frames resident per GPU (references cycle through them: 270 MB > L2)
 MV_RANGE = 64
 EPIPOLE = (1.0, 0.0, 0.0)
@@ -344,7 +347,7 @@ def main():
     launches0 = gpu.launch_count
     dev_ms, _ = timed(device_step, args.steps, lambda s: None)
     launches = gpu.launch_count - launches0
-    k_ms, k_n = gpu.kernel_timing_read()
+    kmap_ms, k_ms, k_n = gpu.kernel_timing_read()
     gpu.kernel_timing(False)
     for s in range(2):
         e2e_step(s)
@@ -352,13 +355,13 @@ def main():
     clocks = sampler.stop()
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
 
-    t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms, kmap_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, k_ms = float(tmax[0]), float(tmax[1]), float(tmax[4])
+        dev_ms, e2e_ms, k_ms, kmap_ms = float(tmax[0]), float(tmax[1]), float(tmax[4]), float(tmax[5])
         samples_all, bytes_all = float(tsum[2]), float(tsum[3])
     else:
         samples_all, bytes_all = float(samples_rank), float(alg_bytes_rank)
@@ -374,6 +377,9 @@ def main():
         e2e_value = samples_all * args.steps / (e2e_ms / 1000.0)
         k_avg_ms = k_ms / max(1, k_n)
         achieved = (alg_bytes_rank / 1e9) / (k_avg_ms / 1000.0) if k_avg_ms > 0 else 0.0
+        kmap_avg_ms = kmap_ms / max(1, k_n)
+        path_ms = k_avg_ms + kmap_avg_ms
+        path_achieved = (alg_bytes_rank / 1e9) / (path_ms / 1000.0) if path_ms > 0 else 0.0
         cpu = None
         if not args.no_cpu_baseline:
             v, dt, nblk, done = cpu_oracle_throughput(1, args.cpu_budget)
@@ -392,7 +398,9 @@ def main():
                                        "every GPU by one ncclAllGather, prefetched one step ahead on a second stream"
                                        % (N, N, pic_bytes / 1e6)) if N > 1 else "1 gpu"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_me<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
+                         "traffic": NCU_TRAFFIC_BYTES, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
+                         "path": {"kernels": "k_map + k_fir<DIST>", "k_map_ms": kmap_avg_ms, "ms": path_ms,
+                                  "achieved": path_achieved, "frac": path_achieved / peak},
                          "algorithmic_bytes_per_launch": alg_bytes_rank,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
             "cpu_baseline": cpu,

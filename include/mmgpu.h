@@ -72,10 +72,11 @@ int mmgpu_sync(mmgpu_ctx* ctx);
 void* mmgpu_stream(mmgpu_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 uint64_t mmgpu_launch_count(const mmgpu_ctx* ctx);
-/* CUDA-event timing of the dominant kernel (k_me) on the context's stream: enable, run, then read the
- * accumulated device time and launch count (synchronises the stream; resets the accumulators). */
+/* CUDA-event timing of the two batch kernels on the context's stream (k_map: positions, k_fir: interpolation +
+ * distortion): enable, run, then read the accumulated device times and the number of batches (synchronises the
+ * stream; resets the accumulators). */
 int mmgpu_kernel_timing_enable(mmgpu_ctx* ctx, int on);
-int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* total_ms, uint64_t* launches);
+int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* map_ms, double* fir_ms, uint64_t* batches);
 
 /* ---- reference pictures: Picture::getRecoBuf(compID, wrapRef) after extendPicBorder (Picture.cpp:988-1092) */
 /* plane00[c] points at sample (0,0) of component c in HOST memory; the margins around it are copied too. */

@@ -79,7 +79,7 @@ def load_library():
     L.mmgpu_launch_count.restype = u64
     L.mmgpu_launch_count.argtypes = [vp]
     L.mmgpu_kernel_timing_enable.argtypes = [vp, i32]
-    L.mmgpu_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.mmgpu_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64)]
     for f in (L.mmgpu_set_ref, L.mmgpu_set_ref_device, L.mmgpu_set_ref_unpadded):
         f.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_rodrigues.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -208,10 +208,10 @@ class MmGpu:
         self._chk(self.L.mmgpu_kernel_timing_enable(self.h, int(on)))
 
     def kernel_timing_read(self):
-        """(total device ms of k_me launches since the last read, number of launches)"""
-        ms, n = C.c_double(), C.c_uint64()
-        self._chk(self.L.mmgpu_kernel_timing_read(self.h, C.byref(ms), C.byref(n)))
-        return ms.value, int(n.value)
+        """(device ms of k_map launches, device ms of k_fir launches, number of batches) since the last read"""
+        m, f, n = C.c_double(), C.c_double(), C.c_uint64()
+        self._chk(self.L.mmgpu_kernel_timing_read(self.h, C.byref(m), C.byref(f), C.byref(n)))
+        return m.value, f.value, int(n.value)
 
     # -- reference pictures --------------------------------------------------------------------
     def _planes(self, origins, strides):

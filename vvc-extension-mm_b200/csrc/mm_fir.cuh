@@ -1,0 +1,208 @@
+// mm_fir.cuh -- device functions of the integer part: VTM separable interpolation and the distortion pieces.
+#pragma once
+#include "mm_common.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// Generic FIR of one sub-block (any component / tap count / uni or bi): the literal two-pass
+// structure of xPredInterBlkMM (InterPrediction.cpp:786-828) with filter<>'s arithmetic.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mm_clip(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+template <int NTAPS>
+__device__ void mm_fir_generic(const MmFir& f, const int16_t* __restrict__ ref, int stride, int xPos, int yPos, int xFrac,
+                               int yFrac, int sbw, int sbh, bool rnd, int lo, int hi, int16_t* dst, int dstStride)
+{
+  const int8_t* ch = (NTAPS == 8) ? c_lumaFilter[xFrac] : c_chromaFilter[xFrac];
+  const int8_t* cv = (NTAPS == 8) ? c_lumaFilter[yFrac] : c_chromaFilter[yFrac];
+  const int16_t* p = ref + (long)yPos * stride + xPos;
+  const int half = NTAPS / 2 - 1;
+  if (yFrac == 0 || xFrac == 0)
+  {
+    for (int r = 0; r < sbh; ++r)
+      for (int x = 0; x < sbw; ++x)
+      {
+        int val;
+        if (xFrac == 0 && yFrac == 0)
+        {
+          // filterCopy<true,isLast> (:392-470)
+          const int s = p[r * stride + x];
+          val = rnd ? s : (int)(int16_t)((int16_t)(s << f.cpShift) - (int16_t)8192);
+        }
+        else
+        {
+          int sum = 0;
+          if (yFrac == 0)
+            for (int k = 0; k < NTAPS; ++k) sum += p[r * stride + x + k - half] * ch[k];
+          else
+            for (int k = 0; k < NTAPS; ++k) sum += p[(r + k - half) * stride + x] * cv[k];
+          if (rnd) val = mm_clip((int)(int16_t)((sum + f.off1l) >> f.shift1l), lo, hi);
+          else val = (int)(int16_t)((sum + f.off1) >> f.shift1);
+        }
+        dst[r * dstStride + x] = (int16_t)val;
+      }
+    return;
+  }
+  int16_t tmp[(4 + 7) * 4];
+  for (int r = 0; r < sbh + NTAPS - 1; ++r)
+    for (int x = 0; x < sbw; ++x)
+    {
+      int sum = 0;
+      for (int k = 0; k < NTAPS; ++k) sum += p[(r - half) * stride + x + k - half] * ch[k];
+      tmp[r * 4 + x] = (int16_t)((sum + f.off1) >> f.shift1);
+    }
+  for (int r = 0; r < sbh; ++r)
+    for (int x = 0; x < sbw; ++x)
+    {
+      int sum = 0;
+      for (int k = 0; k < NTAPS; ++k) sum += tmp[(r + k) * 4 + x] * cv[k];
+      int val;
+      if (rnd) val = mm_clip((int)(int16_t)((sum + f.off2) >> f.shift2), lo, hi);
+      else val = (int)(int16_t)(sum >> f.shift2bi);
+      dst[r * dstStride + x] = (int16_t)val;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fast luma path: 4x4 sub-block, 8-tap separable FIR on packed 16-bit pairs with dp2a.
+// All (xFrac, yFrac) cases, including 0, run the two-pass form: with the phase-0 kernel {0,0,0,64,0,0,0,0}
+// it equals the reference's single-pass / copy results exactly for rndRes = true ("FIR identity");
+// the copy case skips the clip like filterCopy<true,true>.
+// -------------------------------------------------------------------------------------------------
+struct MmTaps  // packed coefficient words of one phase, built once per CTA in shared memory
+{
+  int32_t a0, a1;      // (c0,c1,c2,c3) (c4,c5,c6,c7): output aligned with the sample pair
+  int32_t b0, b1, b2;  // (0,c0,c1,c2) (c3,c4,c5,c6) (c7,0,0,0): output starts on the odd sample
+};
+
+__device__ __forceinline__ int mm_pack4(int c0, int c1, int c2, int c3)
+{
+  return (c0 & 0xff) | ((c1 & 0xff) << 8) | ((c2 & 0xff) << 16) | ((c3 & 0xff) << 24);
+}
+__device__ __forceinline__ void mm_build_taps(MmTaps* t /* [16] in shared memory */)
+{
+  for (int ph = threadIdx.x; ph < 16; ph += blockDim.x)
+  {
+    const int8_t* c = c_lumaFilter[ph];
+    t[ph].a0 = mm_pack4(c[0], c[1], c[2], c[3]);
+    t[ph].a1 = mm_pack4(c[4], c[5], c[6], c[7]);
+    t[ph].b0 = mm_pack4(0, c[0], c[1], c[2]);
+    t[ph].b1 = mm_pack4(c[3], c[4], c[5], c[6]);
+    t[ph].b2 = mm_pack4(c[7], 0, 0, 0);
+  }
+}
+// four outputs of an 8-tap filter over 12 packed samples w0..w5 (output j starts at sample j)
+__device__ __forceinline__ void mm_fir4(const int w0, const int w1, const int w2, const int w3, const int w4,
+                                        const int w5, const MmTaps& t, int init, int& o0, int& o1, int& o2, int& o3)
+{
+  o0 = __dp2a_lo(w0, t.a0, __dp2a_hi(w1, t.a0, __dp2a_lo(w2, t.a1, __dp2a_hi(w3, t.a1, init))));
+  o1 = __dp2a_lo(w0, t.b0, __dp2a_hi(w1, t.b0, __dp2a_lo(w2, t.b1, __dp2a_hi(w3, t.b1, __dp2a_lo(w4, t.b2, init)))));
+  o2 = __dp2a_lo(w1, t.a0, __dp2a_hi(w2, t.a0, __dp2a_lo(w3, t.a1, __dp2a_hi(w4, t.a1, init))));
+  o3 = __dp2a_lo(w1, t.b0, __dp2a_hi(w2, t.b0, __dp2a_lo(w3, t.b1, __dp2a_hi(w4, t.b1, __dp2a_lo(w5, t.b2, init)))));
+}
+
+// pred[r*4+c]; BI = false: clipped prediction, BI = true: 14-bit intermediate
+template <bool BI>
+__device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* taps, const int16_t* __restrict__ ref,
+                                               int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
+                                               int* pred)
+{
+  const MmTaps th = taps[xFrac], tv = taps[yFrac];
+  const int a = xPos - 3;
+  const int sh = (a & 1) << 4;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(ref + (long)(yPos - 3) * stride + (a & ~1));
+  const int wstride = stride >> 1;
+  int P[6][4];  // vertical pairs of first-pass rows, per column
+  int hprev[4];
+#pragma unroll
+  for (int r = 0; r < 11; ++r)
+  {
+    const uint32_t* rowp = base + (long)r * wstride;
+    uint32_t w0 = __ldg(rowp + 0), w1 = __ldg(rowp + 1), w2 = __ldg(rowp + 2), w3 = __ldg(rowp + 3), w4 = __ldg(rowp + 4),
+             w5 = __ldg(rowp + 5);
+    w0 = __funnelshift_r(w0, w1, sh);
+    w1 = __funnelshift_r(w1, w2, sh);
+    w2 = __funnelshift_r(w2, w3, sh);
+    w3 = __funnelshift_r(w3, w4, sh);
+    w4 = __funnelshift_r(w4, w5, sh);
+    w5 = __funnelshift_r(w5, w5, sh);
+    int h0, h1, h2, h3;
+    mm_fir4((int)w0, (int)w1, (int)w2, (int)w3, (int)w4, (int)w5, th, f.off1, h0, h1, h2, h3);
+    h0 >>= f.shift1; h1 >>= f.shift1; h2 >>= f.shift1; h3 >>= f.shift1;
+    if (r & 1)
+    {
+      P[r >> 1][0] = __byte_perm(hprev[0], h0, 0x5410);
+      P[r >> 1][1] = __byte_perm(hprev[1], h1, 0x5410);
+      P[r >> 1][2] = __byte_perm(hprev[2], h2, 0x5410);
+      P[r >> 1][3] = __byte_perm(hprev[3], h3, 0x5410);
+    }
+    else if (r == 10)
+    {
+      P[5][0] = h0 & 0xffff; P[5][1] = h1 & 0xffff; P[5][2] = h2 & 0xffff; P[5][3] = h3 & 0xffff;
+    }
+    else
+    {
+      hprev[0] = h0; hprev[1] = h1; hprev[2] = h2; hprev[3] = h3;
+    }
+  }
+  const bool copy = (xFrac | yFrac) == 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+  {
+    int o0, o1, o2, o3;
+    mm_fir4(P[0][c], P[1][c], P[2][c], P[3][c], P[4][c], P[5][c], tv, BI ? 0 : f.off2, o0, o1, o2, o3);
+    if (BI)
+    {
+      pred[0 * 4 + c] = (int)(int16_t)(o0 >> f.shift2bi);
+      pred[1 * 4 + c] = (int)(int16_t)(o1 >> f.shift2bi);
+      pred[2 * 4 + c] = (int)(int16_t)(o2 >> f.shift2bi);
+      pred[3 * 4 + c] = (int)(int16_t)(o3 >> f.shift2bi);
+    }
+    else
+    {
+      o0 = (int)(int16_t)(o0 >> f.shift2); o1 = (int)(int16_t)(o1 >> f.shift2);
+      o2 = (int)(int16_t)(o2 >> f.shift2); o3 = (int)(int16_t)(o3 >> f.shift2);
+      pred[0 * 4 + c] = copy ? o0 : mm_clip(o0, lo, hi);
+      pred[1 * 4 + c] = copy ? o1 : mm_clip(o1, lo, hi);
+      pred[2 * 4 + c] = copy ? o2 : mm_clip(o2, lo, hi);
+      pred[3 * 4 + c] = copy ? o3 : mm_clip(o3, lo, hi);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Distortion pieces
+// -------------------------------------------------------------------------------------------------
+// 4x4 2-D Hadamard in place (d[r*4+c]); coefficient order/sign is irrelevant for the sum of magnitudes,
+// d[0] ends up as the DC term (sum of all differences).
+__device__ __forceinline__ void mm_had4x4(int* d)
+{
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+  {
+    const int a = d[r * 4 + 0] + d[r * 4 + 1], b = d[r * 4 + 0] - d[r * 4 + 1];
+    const int c = d[r * 4 + 2] + d[r * 4 + 3], e = d[r * 4 + 2] - d[r * 4 + 3];
+    d[r * 4 + 0] = a + c; d[r * 4 + 1] = b + e; d[r * 4 + 2] = a - c; d[r * 4 + 3] = b - e;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+  {
+    const int a = d[0 * 4 + c] + d[1 * 4 + c], b = d[0 * 4 + c] - d[1 * 4 + c];
+    const int g = d[2 * 4 + c] + d[3 * 4 + c], e = d[2 * 4 + c] - d[3 * 4 + c];
+    d[0 * 4 + c] = a + g; d[1 * 4 + c] = b + e; d[2 * 4 + c] = a - g; d[3 * 4 + c] = b - e;
+  }
+}
+// one cross-lane butterfly stage of the tile transform: lanes `lane` and `lane^bit` hold the 16
+// coefficients of neighbouring sub-blocks; afterwards the lower lane holds sums/differences of
+// elements 0..7, the upper lane those of elements 8..15 (8 shuffles instead of 16).
+__device__ __forceinline__ void mm_had_xlane(int* d, int bit, bool upper)
+{
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+  {
+    const int send = upper ? d[i] : d[i + 8];
+    const int keep = upper ? d[i + 8] : d[i];
+    const int recv = __shfl_xor_sync(0xffffffffu, send, bit);
+    d[i] = keep + recv;
+    d[i + 8] = keep - recv;
+  }
+}

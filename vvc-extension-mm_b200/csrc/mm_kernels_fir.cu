@@ -1,0 +1,167 @@
+// mm_kernels_fir.cu -- integer side of the path: 8-tap separable interpolation at the positions k_map wrote, then SAD /
+// Hadamard SATD per candidate or prediction write-out (a5); border extension and addAvg.
+#include "mm_fir.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// k_fir: one warp per work item (32 sub-block-candidates of one block), one 4x4 sub-block per lane.
+// -------------------------------------------------------------------------------------------------
+#ifndef MM_FIR_MINBLOCKS
+#define MM_FIR_MINBLOCKS 8
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P, const int2* __restrict__ pos)
+{
+  __shared__ MmTaps s_taps[16];
+  mm_build_taps(s_taps);
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= P.nItems) return;
+  const MmItem it = P.items[warp];
+  const int2 fp = __ldg(&pos[(long)warp * 32 + lane]);
+  const mmgpu_block b = P.blocks[it.block];
+  const int n = (b.w >> 2) * (b.h >> 2);
+  int cand, sb;
+  if (n >= 32) { cand = it.cand; sb = it.sb + lane; }
+  else { cand = it.cand + lane / n; sb = lane % n; }
+  const bool valid = cand < b.cand_first + b.cand_count;
+  const MmSub s = mm_sub_from_index(b.w, b.h, sb);
+  const MmRef ref = P.refs[b.ref_slot];
+
+  int pred[16];
+  if (fp.x == MM_POS_OOB)
+  {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pred[i] = 0;
+  }
+  else
+  {
+    mm_fir_luma4x4<false>(P.fir, s_taps, ref.plane00[0], ref.stride[0], fp.x >> 4, fp.y >> 4, fp.x & 15, fp.y & 15, P.clpMin,
+                          P.clpMax, pred);
+  }
+
+  if (MODE == MM_MODE_PRED)
+  {
+    if (!valid) return;
+    int16_t* d = P.dst + (long)(b.y + s.row * 4) * P.dstStride + (b.x + s.col * 4);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+      const uint32_t lo = (uint32_t)(pred[r * 4 + 0] & 0xffff) | ((uint32_t)pred[r * 4 + 1] << 16);
+      const uint32_t hi = (uint32_t)(pred[r * 4 + 2] & 0xffff) | ((uint32_t)pred[r * 4 + 3] << 16);
+      *reinterpret_cast<uint2*>(d + (long)r * P.dstStride) = make_uint2(lo, hi);
+    }
+    return;
+  }
+
+  // differences org - pred
+  const int16_t* o = P.org + (long)(b.org_y + s.row * 4) * P.orgStride + (b.org_x + s.col * 4);
+  int d[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+  {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(o + (long)r * P.orgStride));
+    d[r * 4 + 0] = (int)(int16_t)(v.x & 0xffff) - pred[r * 4 + 0];
+    d[r * 4 + 1] = (int)(int16_t)(v.x >> 16) - pred[r * 4 + 1];
+    d[r * 4 + 2] = (int)(int16_t)(v.y & 0xffff) - pred[r * 4 + 2];
+    d[r * 4 + 3] = (int)(int16_t)(v.y >> 16) - pred[r * 4 + 3];
+  }
+  unsigned int part;
+  if (P.distKind == MMGPU_DIST_SAD)
+  {
+    // RdCost::xGetSAD*: rows stepped by 1 << subShift, sum << subShift (block rows are 4-aligned)
+    unsigned int sad = 0;
+    const int step = 1 << P.subShift;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if ((r & (step - 1)) == 0)
+        sad += abs(d[r * 4 + 0]) + abs(d[r * 4 + 1]) + abs(d[r * 4 + 2]) + abs(d[r * 4 + 3]);
+    part = sad << P.subShift;
+  }
+  else
+  {
+    mm_had4x4(d);
+    // tile transform across the T adjacent lanes (q = lane & (T-1)); uniform per warp (same block)
+    if (s.T >= 2) mm_had_xlane(d, 1, (lane & 1) != 0);
+    if (s.T >= 4) mm_had_xlane(d, 2, (lane & 2) != 0);
+    if (s.T >= 8) mm_had_xlane(d, 4, (lane & 4) != 0);
+    unsigned int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sum += (unsigned int)abs(d[i]);
+    if (s.q == 0)
+    {
+      const unsigned int dc = (unsigned int)abs(d[0]);  // JVET_R0164_MEAN_SCALED_SATD
+      sum = sum - dc + (dc >> 2);
+    }
+    if (s.T >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (s.T >= 4) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (s.T >= 8) sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    unsigned int t;
+    if (s.tileKind == 0) t = (sum + 1) >> 1;
+    else if (s.tileKind == 1) t = (sum + 2) >> 2;
+    else if (P.hadMode == MMGPU_HAD_SIMD)
+    {
+      t = (unsigned int)(((unsigned long long)sum * 0xb504f334ULL) >> 32);
+      t = (s.tileKind == 2) ? (t >> 2) : (t >> 1);
+    }
+    else
+    {
+      const double div = (s.tileKind == 2) ? 0x1.6a09e667f3bcdp+3 /* sqrt(16.0*8) */ : 0x1.6a09e667f3bcdp+2 /* sqrt(4.0*8) */;
+      t = (unsigned int)(int)__dmul_rn(__ddiv_rn((double)sum, div), 2.0);
+    }
+    part = (s.q == 0) ? t : 0u;
+  }
+  // candidate reduction
+  if (n >= 32)
+  {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0) atomicAdd(&P.dist[cand], (unsigned long long)part);
+  }
+  else
+  {
+    for (int off = n >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (valid && sb == 0) P.dist[cand] = (unsigned long long)part;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Picture::extendPicBorder on the device (Picture.cpp:1008-1046): one thread per margin sample
+// -------------------------------------------------------------------------------------------------
+__global__ void k_extend_border(int16_t* plane00, int stride, int w, int h, int mx, int my)
+{
+  const int X = blockIdx.x * blockDim.x + threadIdx.x - mx;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y - my;
+  if (X >= w + mx || Y >= h + my) return;
+  if (X >= 0 && X < w && Y >= 0 && Y < h) return;
+  const int sx = min(max(X, 0), w - 1), sy = min(max(Y, 0), h - 1);
+  plane00[(long)Y * stride + X] = plane00[(long)sy * stride + sx];
+}
+
+__global__ void k_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
+                          int shift, int offset, int lo, int hi)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  dst[(long)y * ds + x] = (int16_t)mm_clip(((int)s0[(long)y * st0 + x] + (int)s1[(long)y * st1 + x] + offset) >> shift, lo, hi);
+}
+
+// ---- launch wrappers -----------------------------------------------------------------------------
+void mmk_fir(cudaStream_t s, const MmParams& P, int mode, const int2* pos)
+{
+  if (P.nItems <= 0) return;
+  const int grid = (P.nItems + 3) / 4;
+  if (mode == MM_MODE_DIST) k_fir<MM_MODE_DIST><<<grid, 128, 0, s>>>(P, pos);
+  else k_fir<MM_MODE_PRED><<<grid, 128, 0, s>>>(P, pos);
+}
+void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my)
+{
+  dim3 tb(32, 8), gr((w + 2 * mx + 31) / 32, (h + 2 * my + 7) / 8);
+  k_extend_border<<<gr, tb, 0, s>>>(plane00, stride, w, h, mx, my);
+}
+void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
+                 int shift, int offset, int lo, int hi)
+{
+  dim3 tb(32, 4), gr((w + 31) / 32, (h + 3) / 4);
+  k_add_avg<<<gr, tb, 0, s>>>(s0, st0, s1, st1, dst, ds, w, h, shift, offset, lo, hi);
+}

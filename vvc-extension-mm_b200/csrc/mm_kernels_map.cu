@@ -1,0 +1,220 @@
+// mm_kernels_map.cu -- float side of the path: per-sequence caches, per-candidate scalars and the positions of every
+// sub-block of every candidate.  See mm_common.cuh for the kernel list.
+#include "mm_sbpos.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// k_mpa_cache: picture-wide motion-plane cache (always the vectorised Eigen path: n = W/4*H/4)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_mpa_cache(MmGeom g, int model, float2* out, uint8_t* vip)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.rows4 * g.cols4) return;
+  const int row = idx / g.cols4, col = idx - row * g.cols4;
+  const float X = MM_FADD((float)(4 * col), g.off), Y = MM_FADD((float)(4 * row), g.off);
+  const long n = (long)g.rows4 * g.cols4;
+  const bool pk = ((long)col * g.rows4 + row) < (n & ~3L);
+  float PX, PY;
+  bool v;
+  MmTrig none; none.valid = false; none.st = none.ct = none.sp = none.cp = 0.f;
+  mm_mpa_to_perspective(g, model, X, Y, pk, none, &PX, &PY, &v);
+  out[idx] = make_float2(PX, PY);
+  vip[idx] = v ? 1 : 0;
+}
+
+// ERP toSphere angles of the picture grid, scalar-libm and Eigen-packet variants (Projection.cpp:213-221,
+// Coordinate.cpp:53-60): tab[0] = scalar, tab[1] = packet; th over rows, ph over columns.
+__global__ void k_trig_tables(MmGeom g, float2* th0, float2* th1, float2* ph0, float2* ph1)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fma = g.fmaBuild != 0;
+  if (i < g.rows4)
+  {
+    float th, ph, s, c;
+    mm_erp_angles(g, 0.0f, MM_FADD((float)(4 * i), g.off), &th, &ph);
+    mm_sincos_pk(th, false, fma, &s, &c); th0[i] = make_float2(s, c);
+    mm_sincos_pk(th, true, fma, &s, &c);  th1[i] = make_float2(s, c);
+  }
+  if (i < g.cols4)
+  {
+    float th, ph, s, c;
+    mm_erp_angles(g, MM_FADD((float)(4 * i), g.off), 0.0f, &th, &ph);
+    mm_sincos_pk(ph, false, fma, &s, &c); ph0[i] = make_float2(s, c);
+    mm_sincos_pk(ph, true, fma, &s, &c);  ph1[i] = make_float2(s, c);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_build_items: the work list of a batch, one warp per block.  itemBase[b] = first work item of block b
+// (host-computed, grouped by motion model); also fills the candidate -> block map used by k_cand_setup.
+// -------------------------------------------------------------------------------------------------
+__global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ itemBase, int nBlocks,
+                              int candChunk, MmItem* __restrict__ items, int32_t* __restrict__ candBlock)
+{
+  const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (bi >= nBlocks) return;
+  const mmgpu_block b = blocks[bi];
+  const int n = (b.w >> 2) * (b.h >> 2);
+  const int base = itemBase[bi];
+  for (int j = lane; j < b.cand_count; j += 32) candBlock[b.cand_first + j] = bi;
+  // a work item = up to candChunk candidates (n >= 32) or candChunk steps of 32/n candidates (n < 32) of one
+  // 32-sub-block chunk: the warp prepares the candidate-independent state once and loops over the candidates
+  if (n >= 32)
+  {
+    const int chunks = n >> 5, groups = (b.cand_count + candChunk - 1) / candChunk, total = groups * chunks;
+    for (int t = lane; t < total; t += 32)
+    {
+      const int gidx = t / chunks, ch = t - gidx * chunks;
+      const int c0 = gidx * candChunk;
+      items[base + t] = MmItem{bi, b.cand_first + c0, ch << 5, min(candChunk, b.cand_count - c0)};
+    }
+  }
+  else
+  {
+    const int per = (32 / n) * candChunk, total = (b.cand_count + per - 1) / per;
+    for (int t = lane; t < total; t += 32)
+      items[base + t] = MmItem{bi, b.cand_first + t * per, 0, min(per, b.cand_count - t * per)};
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_cand_setup: one thread per candidate MV
+// -------------------------------------------------------------------------------------------------
+__global__ void k_cand_setup(MmGeom g, const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ candBlock,
+                             const mmgpu_mv* __restrict__ mvs, int mvShift, const float* __restrict__ rot, int nCands,
+                             MmCand* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nCands) return;
+  const mmgpu_block b = blocks[candBlock[i]];
+  const mmgpu_mv mv = mvs[i];
+  MmCand c;
+  // Mv::changePrecision(mvPrec, MV_PRECISION_INTERNAL) is a left shift (Mv.h)
+  const int mh = mv.hor * (1 << mvShift), mvv = mv.ver * (1 << mvShift);
+  if (b.model == MM_CLASSIC)
+  {
+    c.mvX = 0.f; c.mvY = 0.f; c.mvZero = 0;
+    for (int k = 0; k < 9; ++k) c.p[k] = 0.f;
+    c.p[0] = __int_as_float(mh);
+    c.p[1] = __int_as_float(mvv);
+  }
+  else
+  {
+    mm_cand_setup(g, b.model, true, b.x, b.y, b.w, b.h, mh, mvv, mm_rot_ptr(rot, b.model, b.rot_slot), &c);
+  }
+  out[i] = c;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_reproject: positions of one block (parity entry point a1)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_reproject(MmParams P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv, int model,
+                            int rotSlot, int32_t* outX, int32_t* outY)
+{
+  const int sbw = 4 >> csx, sbh = 4 >> csy;
+  const int rows = h / sbh, cols = w / sbw;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int col = i / rows, row = i - col * rows;
+  const float* R = mm_rot_ptr(P.rot, model, rotSlot);
+  MmCand c;
+  mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
+  int fx, fy;
+  mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
+  outX[i] = fx;
+  outY[i] = fy;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_map: one lane per (candidate, sub-block) entry of the batch; writes its 1/16-pel position, or MM_POS_OOB in .x
+// when the sub-block falls outside the picture by the caller's OOB rule (InterPrediction.cpp:776-780 /
+// InterSearch.cpp:6329-6332: the prediction of such a sub-block is 0).
+// MODEL >= 0: every item of the launch uses that motion model (items are grouped by model); MODEL < 0: generic.
+// -------------------------------------------------------------------------------------------------
+#ifndef MM_MAP_MINBLOCKS
+#define MM_MAP_MINBLOCKS 8
+#endif
+template <int MODEL>
+__global__ void __launch_bounds__(128, MM_MAP_MINBLOCKS) k_map(const MmParams P, int first, int count, int2* __restrict__ pos)
+{
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w0 >= count) return;
+  const int warp = first + w0;
+  const MmItem it = P.items[warp];
+  const mmgpu_block b = P.blocks[it.block];
+  const int n = (b.w >> 2) * (b.h >> 2);
+  int cand, sb;
+  if (n >= 32) { cand = it.cand; sb = it.sb + lane; }
+  else { cand = it.cand + lane / n; sb = lane % n; }
+  const bool valid = cand < b.cand_first + b.cand_count;
+  const int candc = valid ? cand : it.cand;  // lanes past the last candidate redo a valid one, result unused
+  const MmSub s = mm_sub_from_index(b.w, b.h, sb);
+  const MmCand c = P.cands[candc];
+  int fx, fy;
+  const int model = (MODEL >= 0) ? MODEL : b.model;
+  if (model == MM_CLASSIC)
+  {
+    fx = ((b.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
+    fy = ((b.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
+  }
+  else
+  {
+    const float* R = mm_rot_ptr(P.rot, model, b.rot_slot);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, b.x, b.y, b.w, b.h, c, R, s.row, s.col, &fx, &fy);
+    const int mc = (P.oobMode == MMGPU_OOB_ME) ? 0 : P.maxCU;
+    const int xP = fx >> 4, yP = fy >> 4;
+    if (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4) fx = MM_POS_OOB;
+  }
+  pos[(long)warp * 32 + lane] = make_int2(fx, fy);
+}
+
+// ---- launch wrappers -----------------------------------------------------------------------------
+void mmk_mpa_cache(cudaStream_t s, const MmGeom& g, int model, float2* out, uint8_t* vip)
+{
+  const int n4 = g.rows4 * g.cols4;
+  k_mpa_cache<<<(n4 + 127) / 128, 128, 0, s>>>(g, model, out, vip);
+}
+void mmk_trig_tables(cudaStream_t s, const MmGeom& g, float2* th0, float2* th1, float2* ph0, float2* ph1)
+{
+  const int nt = g.rows4 > g.cols4 ? g.rows4 : g.cols4;
+  k_trig_tables<<<(nt + 127) / 128, 128, 0, s>>>(g, th0, th1, ph0, ph1);
+}
+void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* itemBase, int nBlocks, int candChunk,
+                     MmItem* items, int32_t* candBlock)
+{
+  k_build_items<<<(nBlocks + 3) / 4, 128, 0, s>>>(blocks, itemBase, nBlocks, candChunk, items, candBlock);
+}
+void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
+                    int mvShift, const float* rot, int nCands, MmCand* out)
+{
+  k_cand_setup<<<(nCands + 127) / 128, 128, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, nCands, out);
+}
+void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
+                   int model, int rotSlot, int32_t* outX, int32_t* outY)
+{
+  const int n = (w / (4 >> csx)) * (h / (4 >> csy));
+  k_reproject<<<(n + 63) / 64, 64, 0, s>>>(P, comp, csx, csy, x, y, w, h, mv, model, rotSlot, outX, outY);
+}
+void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model, int2* pos)
+{
+  if (count <= 0) return;
+  const int grid = (count + 3) / 4;
+  switch (model)
+  {
+#ifdef MM_MAP_PER_MODEL
+    case MM_CLASSIC: k_map<MM_CLASSIC><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_MPA_FRONT_BACK: k_map<MM_MPA_FRONT_BACK><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_MPA_LEFT_RIGHT: k_map<MM_MPA_LEFT_RIGHT><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_MPA_TOP_BOTTOM: k_map<MM_MPA_TOP_BOTTOM><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_TANGENTIAL: k_map<MM_TANGENTIAL><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_THREE_D_TRANSLATIONAL: k_map<MM_THREE_D_TRANSLATIONAL><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_ROTATIONAL: k_map<MM_ROTATIONAL><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_X: k_map<MM_GEODESIC_X><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_Y: k_map<MM_GEODESIC_Y><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_Z: k_map<MM_GEODESIC_Z><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_CAMPOSE: k_map<MM_GEODESIC_CAMPOSE><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+#endif
+    default: k_map<-1><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+  }
+}

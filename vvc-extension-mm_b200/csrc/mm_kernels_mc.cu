@@ -1,0 +1,198 @@
+// mm_kernels_mc.cu -- block-level entry points that map and interpolate in one kernel: single-block MC of any
+// component (parity twin of xPredInterBlkMM / xPredInterBlk), whole-picture reconstruction jobs, DMVR costs.
+#include "mm_sbpos.cuh"
+#include "mm_fir.cuh"
+
+// One thread per sub-block of ONE block (mmgpu_mc).  model == CLASSIC: one MV for the block (xPredInterBlk).
+__global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
+                             int model, int rotSlot, int bi, int16_t* dst, int dstStride)
+{
+  const int sbw = 4 >> csx, sbh = 4 >> csy;
+  const int rows = h / sbh, cols = w / sbw;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int col = i / rows, row = i - col * rows;
+  const MmRef ref = P.refs[refSlot];
+  const int shH = 4 + csx, shV = 4 + csy;
+  int fx, fy;
+  int16_t* d = dst + (long)row * sbh * dstStride + col * sbw;
+  if (model == MM_CLASSIC)
+  {
+    // xPredInterBlk (InterPrediction.cpp:928-1096, no wrap / RPR): every sample uses the block MV
+    fx = ((x + col * sbw) << shH) + mv.hor;
+    fy = ((y + row * sbh) << shV) + mv.ver;
+  }
+  else
+  {
+    const float* R = mm_rot_ptr(P.rot, model, rotSlot);
+    MmCand c;
+    mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
+    const int xP = fx >> shH, yP = fy >> shV;
+    const int picw = P.picW >> csx, pich = P.picH >> csy;
+    const int mcw = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csx);
+    const int mch = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csy);
+    if (xP < -mcw || yP < -mch || xP >= picw + mcw - sbw || yP >= pich + mch - sbh)
+    {
+      for (int r = 0; r < sbh; ++r)
+        for (int q = 0; q < sbw; ++q) d[r * dstStride + q] = 0;
+      return;
+    }
+  }
+  const int xP = fx >> shH, yP = fy >> shV, xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  if (comp == 0)
+    mm_fir_generic<8>(P.fir, ref.plane00[0], ref.stride[0], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, d, dstStride);
+  else
+    mm_fir_generic<4>(P.fir, ref.plane00[comp], ref.stride[comp], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, d,
+                      dstStride);
+}
+
+// One sub-block of one component into `out` (row stride 4): mapping (or classic MV) + OOB rule + FIR.
+__device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w,
+                                               int h, mmgpu_mv mv, int model, int rotSlot, bool bi, int row, int col,
+                                               int16_t* out)
+{
+  const int sbw = 4 >> csx, sbh = 4 >> csy;
+  const MmRef ref = P.refs[refSlot];
+  const int shH = 4 + csx, shV = 4 + csy;
+  int fx, fy;
+  if (model == MM_CLASSIC)
+  {
+    fx = ((x + col * sbw) << shH) + mv.hor;
+    fy = ((y + row * sbh) << shV) + mv.ver;
+  }
+  else
+  {
+    const float* R = mm_rot_ptr(P.rot, model, rotSlot);
+    MmCand c;
+    mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
+    const int xP = fx >> shH, yP = fy >> shV;
+    const int picw = P.picW >> csx, pich = P.picH >> csy;
+    const int mcw = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csx);
+    const int mch = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csy);
+    if (xP < -mcw || yP < -mch || xP >= picw + mcw - sbw || yP >= pich + mch - sbh)
+    {
+      for (int i = 0; i < 16; ++i) out[i] = 0;
+      return;
+    }
+  }
+  const int xP = fx >> shH, yP = fy >> shV, xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  if (comp == 0)
+    mm_fir_generic<8>(P.fir, ref.plane00[0], ref.stride[0], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
+  else
+    mm_fir_generic<4>(P.fir, ref.plane00[comp], ref.stride[comp], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
+}
+
+// Whole-picture reconstruction shape (DecCu::xReconInter -> motionCompensation -> xPredInterUni / xPredInterBi,
+// InterPrediction.cpp:455-681): one CTA per job (one component of one PU); uni-prediction writes the clipped
+// prediction, bi-prediction interpolates both lists at 14 bit and applies PelBuf::addAvg (Buffer.cpp:551-587) in
+// registers before the store.  dst planes are un-padded device pictures.
+__global__ void k_mc_jobs(MmParams P, const mmgpu_mc_job* __restrict__ jobs, int16_t* dstY, int16_t* dstCb, int16_t* dstCr,
+                          int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset)
+{
+  const mmgpu_mc_job j = jobs[blockIdx.x];
+  const int csx = j.comp ? csxC : 0, csy = j.comp ? csyC : 0;
+  const int sbw = 4 >> csx, sbh = 4 >> csy;
+  const int rows = j.h / sbh, cols = j.w / sbw;
+  int16_t* plane = j.comp == 0 ? dstY : (j.comp == 1 ? dstCb : dstCr);
+  const int stride = j.comp == 0 ? strideY : strideC;
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+  {
+    const int col = i / rows, row = i - col * rows;
+    int16_t a[16], b[16];
+    mm_mc_subblock(P, j.ref_slot0, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv0, j.model, j.rot_slot0, j.bi != 0, row, col, a);
+    if (j.bi)
+    {
+      mm_mc_subblock(P, j.ref_slot1, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv1, j.model, j.rot_slot1, true, row, col, b);
+      for (int r = 0; r < sbh; ++r)
+        for (int q = 0; q < sbw; ++q)
+          a[r * 4 + q] = (int16_t)mm_clip(((int)a[r * 4 + q] + (int)b[r * 4 + q] + avgOffset) >> avgShift, P.clpMin, P.clpMax);
+    }
+    int16_t* d = plane + (long)(j.y + row * sbh) * stride + (j.x + col * sbw);
+    for (int r = 0; r < sbh; ++r)
+      for (int q = 0; q < sbw; ++q) d[(long)r * stride + q] = a[r * 4 + q];
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_dmvr: xProcessDMVRProjected's cost evaluations (InterPrediction.cpp:2510-2567).  One group of 2n lanes per
+// (sub-PU, search offset): n lanes interpolate the L0 prediction of the sub-PU's n sub-blocks at mv0 + offset,
+// n lanes the L1 prediction at mv1 - offset (bi = true: 14-bit intermediates, +-maxCU OOB rule, the sub-PU is
+// "the block": quirk Q6); xDMVRCost = SAD over even rows (subShift 1), << 1, >> 1.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dmvr(const MmParams P, const mmgpu_dmvr_subpu* __restrict__ subpus,
+                                              const MmDmvrItem* __restrict__ items, int nItems, int simdSad,
+                                              unsigned long long* __restrict__ costs)
+{
+  __shared__ MmTaps s_taps[16];
+  mm_build_taps(s_taps);
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nItems) return;
+  const MmDmvrItem it = items[warp];
+  const mmgpu_dmvr_subpu sp = subpus[it.subpu];
+  const int cols = sp.w >> 2, rows = sp.h >> 2;
+  const int n = cols * rows;                    // 4, 8 or 16 sub-blocks
+  const int g = lane / (2 * n), within = lane - g * 2 * n;
+  const int list = within / n, sb = within - list * n;
+  const int off = it.off + g;
+  const bool valid = off < 25;
+  const int offc = valid ? off : it.off;
+  const int oh = (offc % 5 - 2) * 16, ov = (offc / 5 - 2) * 16;   // m_pSearchOffset << MV_FRACTIONAL_BITS_INTERNAL
+  const int mh = list ? (sp.mv1.hor - oh) : (sp.mv0.hor + oh);
+  const int mv = list ? (sp.mv1.ver - ov) : (sp.mv0.ver + ov);
+  const int row = sb / cols, col = sb - row * cols;
+  const MmRef ref = P.refs[list ? sp.ref_slot1 : sp.ref_slot0];
+  const float* R = mm_rot_ptr(P.rot, sp.model, list ? sp.rot_slot1 : sp.rot_slot0);
+  MmCand c;
+  mm_cand_setup(P.g, sp.model, true, sp.x, sp.y, sp.w, sp.h, mh, mv, R, &c);
+  int fx, fy;
+  mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, sp.model, 0, 0, 0, sp.x, sp.y, sp.w, sp.h, c, R, row, col, &fx, &fy);
+  const int xP = fx >> 4, yP = fy >> 4;
+  const bool oob = (xP < -P.maxCU || yP < -P.maxCU || xP >= P.picW + P.maxCU - 4 || yP >= P.picH + P.maxCU - 4);
+  int pred[16];
+  if (oob)
+  {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pred[i] = 0;
+  }
+  else
+  {
+    mm_fir_luma4x4<true>(P.fir, s_taps, ref.plane00[0], ref.stride[0], xP, yP, fx & 15, fy & 15, P.clpMin, P.clpMax, pred);
+  }
+  // rows 0 and 2 of the sub-block (even rows of the sub-PU): L0 lanes receive the L1 samples of lane ^ n
+  unsigned int sad = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+  {
+    const int mine = pred[(i >> 2) * 8 + (i & 3)];
+    const int other = __shfl_xor_sync(0xffffffffu, mine, n);
+    int d = mine - other;
+    if (simdSad) { d = (int)(int16_t)d; d = abs(d) & 0xffff; }   // _mm_sub_epi16 + _mm_abs_epi16, zero-extended
+    else d = abs(d);
+    sad += (unsigned int)d;
+  }
+  if (list) sad = 0;
+  for (int o = n >> 1; o > 0; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+  if (valid && within == 0) costs[(long)it.subpu * 25 + off] = ((unsigned long long)sad << 1) >> 1;
+}
+
+// ---- launch wrappers -----------------------------------------------------------------------------
+void mmk_mc_generic(cudaStream_t s, const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h,
+                    mmgpu_mv mv, int model, int rotSlot, int bi, int16_t* dst, int dstStride)
+{
+  const int n = (w / (4 >> csx)) * (h / (4 >> csy));
+  k_mc_generic<<<(n + 63) / 64, 64, 0, s>>>(P, refSlot, comp, csx, csy, x, y, w, h, mv, model, rotSlot, bi, dst, dstStride);
+}
+void mmk_mc_jobs(cudaStream_t s, const MmParams& P, int nJobs, const mmgpu_mc_job* jobs, int16_t* dstY, int16_t* dstCb,
+                 int16_t* dstCr, int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset)
+{
+  k_mc_jobs<<<nJobs, 64, 0, s>>>(P, jobs, dstY, dstCb, dstCr, strideY, strideC, csxC, csyC, avgShift, avgOffset);
+}
+void mmk_dmvr(cudaStream_t s, const MmParams& P, const mmgpu_dmvr_subpu* subpus, const MmDmvrItem* items, int nItems,
+              int simdSad, unsigned long long* costs)
+{
+  k_dmvr<<<(nItems + 3) / 4, 128, 0, s>>>(P, subpus, items, nItems, simdSad, costs);
+}

@@ -24,9 +24,10 @@
 
 #if defined(__CUDACC__)
 #define MM_HD __host__ __device__ __forceinline__
-// the big libm routines: inlined by default; -DMM_NOINLINE_LIBM keeps one copy each (smaller kernel code)
-#ifdef MM_NOINLINE_LIBM
-#define MM_HDL __host__ __device__ __noinline__
+// the big libm routines: one copy each by default (k_map shrinks from 12k to 2.8k SASS instructions, which is what the
+// instruction cache needs); -DMM_INLINE_LIBM inlines them at every call site
+#ifndef MM_INLINE_LIBM
+#define MM_HDL static __host__ __device__ __noinline__
 #else
 #define MM_HDL __host__ __device__ __forceinline__
 #endif

@@ -8,7 +8,7 @@
 #include <algorithm>
 #include <string>
 #include <vector>
-#include "mm_kernels.cuh"
+#include "mm_common.cuh"
 
 #define MM_MAX_ROT 64
 
@@ -22,8 +22,9 @@ struct mmgpu_plan
   int32_t* dCandBlock;
   MmCand* dCands;
   int32_t* dItemBase;
+  int2* dPos;  // 1/16-pel position of every (candidate, sub-block) entry: k_map -> k_fir
   int modelFirst[MM_NUM_MODELS], modelCount[MM_NUM_MODELS];  // work items of each motion model (contiguous)
-  size_t capBlocks, capItems, capCands, capCandParams, capItemBase;
+  size_t capBlocks, capItems, capCands, capCandParams, capItemBase, capPos;
 };
 
 struct mmgpu_ctx
@@ -67,16 +68,17 @@ struct mmgpu_ctx
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
   // pinned host staging for small per-call tables (reused; guarded by an event)
+  bool mapPerModel;
   int candChunk;  // candidates evaluated by one warp per work item (amortises the candidate-independent part)
   void* hStage;
   size_t capStage;
   cudaEvent_t stageFree;
   bool stageBusy;
-  // optional CUDA-event timing of k_me
+  // optional CUDA-event timing of the batch kernels: events t0 | k_map | t1 | k_fir | t2 per launchMe
   bool timing;
-  std::vector<cudaEvent_t> evPool;   // start/stop pairs
+  std::vector<cudaEvent_t> evPool;   // triples
   size_t evUsed;
-  double evAccumMs;
+  double evAccumMs[2];               // [0] = k_map, [1] = k_fir
   uint64_t evAccumN;
 };
 
@@ -200,10 +202,11 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   ctx->timing = false;
   ctx->hStage = nullptr;
   ctx->capStage = 0;
+  ctx->mapPerModel = getenv("MMGPU_MAP_PER_MODEL") != nullptr;
   ctx->candChunk = 1;  // k_me evaluates one candidate per work item (a candidate loop was measured slower: DESIGN.md 4)
   ctx->stageBusy = false;
   ctx->evUsed = 0;
-  ctx->evAccumMs = 0;
+  ctx->evAccumMs[0] = ctx->evAccumMs[1] = 0;
   ctx->evAccumN = 0;
   MmGeom& g = ctx->g;
   g.picW = (float)cfg->pic_w;
@@ -247,7 +250,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   {
     CU(cudaMalloc(&ctx->dMpa[m], sizeof(float2) * n4));
     CU(cudaMalloc(&ctx->dMpaVip[m], n4));
-    k_mpa_cache<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(g, m + 1, ctx->dMpa[m], ctx->dMpaVip[m]);
+    mmk_mpa_cache(ctx->stream, g, m + 1, ctx->dMpa[m], ctx->dMpaVip[m]);
     ctx->launches++;
   }
   for (int v = 0; v < 2; ++v)
@@ -255,11 +258,8 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     CU(cudaMalloc(&ctx->dThTab[v], sizeof(float2) * g.rows4));
     CU(cudaMalloc(&ctx->dPhTab[v], sizeof(float2) * g.cols4));
   }
-  {
-    const int nt = g.rows4 > g.cols4 ? g.rows4 : g.cols4;
-    k_trig_tables<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(g, ctx->dThTab[0], ctx->dThTab[1], ctx->dPhTab[0], ctx->dPhTab[1]);
-    ctx->launches++;
-  }
+  mmk_trig_tables(ctx->stream, g, ctx->dThTab[0], ctx->dThTab[1], ctx->dPhTab[0], ctx->dPhTab[1]);
+  ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   *out = ctx;
@@ -273,8 +273,10 @@ static void freePlan(mmgpu_plan* p)
   cudaFree(p->dCandBlock);
   cudaFree(p->dCands);
   cudaFree(p->dItemBase);
+  cudaFree(p->dPos);
   p->dItemBase = nullptr;
-  p->capItemBase = 0;
+  p->dPos = nullptr;
+  p->capItemBase = p->capPos = 0;
   p->dBlocks = nullptr; p->dItems = nullptr; p->dCandBlock = nullptr; p->dCands = nullptr;
   p->capBlocks = p->capItems = p->capCands = p->capCandParams = 0;
 }
@@ -314,11 +316,13 @@ extern "C" int mmgpu_sync(mmgpu_ctx* ctx)
 static int drainTiming(mmgpu_ctx* ctx)
 {
   CU(cudaStreamSynchronize(ctx->stream));
-  for (size_t i = 0; i + 1 < ctx->evUsed; i += 2)
+  for (size_t i = 0; i + 2 < ctx->evUsed; i += 3)
   {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->evPool[i], ctx->evPool[i + 1]));
-    ctx->evAccumMs += ms;
+    ctx->evAccumMs[0] += ms;
+    CU(cudaEventElapsedTime(&ms, ctx->evPool[i + 1], ctx->evPool[i + 2]));
+    ctx->evAccumMs[1] += ms;
     ctx->evAccumN++;
   }
   ctx->evUsed = 0;
@@ -331,26 +335,27 @@ extern "C" int mmgpu_kernel_timing_enable(mmgpu_ctx* ctx, int on)
   int rc = drainTiming(ctx);
   if (rc) return rc;
   ctx->timing = on != 0;
-  ctx->evAccumMs = 0;
+  ctx->evAccumMs[0] = ctx->evAccumMs[1] = 0;
   ctx->evAccumN = 0;
   return MMGPU_OK;
 }
-extern "C" int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* total_ms, uint64_t* launches)
+extern "C" int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* map_ms, double* fir_ms, uint64_t* launches)
 {
-  if (!ctx || !total_ms || !launches) return MMGPU_ERR_ARG;
+  if (!ctx || !map_ms || !fir_ms || !launches) return MMGPU_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
   int rc = drainTiming(ctx);
   if (rc) return rc;
-  *total_ms = ctx->evAccumMs;
+  *map_ms = ctx->evAccumMs[0];
+  *fir_ms = ctx->evAccumMs[1];
   *launches = ctx->evAccumN;
-  ctx->evAccumMs = 0;
+  ctx->evAccumMs[0] = ctx->evAccumMs[1] = 0;
   ctx->evAccumN = 0;
   return MMGPU_OK;
 }
 static int timingEvent(mmgpu_ctx* ctx)
 {
   if (!ctx->timing) return MMGPU_OK;
-  if (ctx->evUsed >= 4096) { int rc = drainTiming(ctx); if (rc) return rc; }
+  if (ctx->evUsed >= 3 * 1024 && ctx->evUsed % 3 == 0) { int rc = drainTiming(ctx); if (rc) return rc; }
   if (ctx->evUsed >= ctx->evPool.size())
   {
     cudaEvent_t e;
@@ -459,8 +464,7 @@ extern "C" int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const i
     if (rc) return rc;
     CU(cudaMemcpy2DAsync(d00, sizeof(int16_t) * pitch, plane[c], sizeof(int16_t) * stride[c], sizeof(int16_t) * w, h,
                          cudaMemcpyHostToDevice, ctx->stream));
-    dim3 tb(32, 8), gr((w + 2 * mx + 31) / 32, (h + 2 * my + 7) / 8);
-    k_extend_border<<<gr, tb, 0, ctx->stream>>>(d00, pitch, w, h, mx, my);
+    mmk_extend_border(ctx->stream, d00, pitch, w, h, mx, my);
     ctx->launches++;
     r.plane00[c] = d00;
     r.stride[c] = pitch;
@@ -535,7 +539,7 @@ extern "C" int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, 
   int32_t* dx = reinterpret_cast<int32_t*>(ctx->dTmp);
   int32_t* dy = dx + n;
   MmParams P = baseParams(ctx);
-  k_reproject<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P, comp, csx, csy, x, y, w, h, mv, model, rot_slot, dx, dy);
+  mmk_reproject(ctx->stream, P, comp, csx, csy, x, y, w, h, mv, model, rot_slot, dx, dy);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_x, dx, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -557,15 +561,13 @@ extern "C" int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, 
   if (rc) return rc;
   cudaSetDevice(ctx->cfg.device);
   const int csx = scaleX(comp, chroma_fmt), csy = scaleY(comp, chroma_fmt);
-  const int n = (w / (4 >> csx)) * (h / (4 >> csy));
   rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)w * h + 64);
   if (rc) return rc;
   MmParams P = baseParams(ctx);
   P.clpMin = clp_min;
   P.clpMax = clp_max;
   P.oobMode = oob_mode;
-  k_mc_generic<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P, ref_slot, comp, csx, csy, x, y, w, h, mv, model, rot_slot, bi,
-                                                      ctx->dTmp, w);
+  mmk_mc_generic(ctx->stream, P, ref_slot, comp, csx, csy, x, y, w, h, mv, model, rot_slot, bi, ctx->dTmp, w);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpy2DAsync(dst, sizeof(int16_t) * dst_stride, ctx->dTmp, sizeof(int16_t) * w, sizeof(int16_t) * w, h,
@@ -586,8 +588,7 @@ extern "C" int mmgpu_add_avg(mmgpu_ctx* ctx, const int16_t* src0, int s0_stride,
   CU(cudaMemcpy2DAsync(d1, 2 * w, src1, 2 * s1_stride, 2 * w, h, cudaMemcpyHostToDevice, ctx->stream));
   const int hr = ctx->fir.cpShift;
   const int shift = hr + 1, offset = (1 << (shift - 1)) + 2 * 8192;
-  dim3 tb(32, 4), gr((w + 31) / 32, (h + 3) / 4);
-  k_add_avg<<<gr, tb, 0, ctx->stream>>>(d0, w, d1, w, dd, w, w, h, shift, offset, clp_min, clp_max);
+  mmk_add_avg(ctx->stream, d0, w, d1, w, dd, w, w, h, shift, offset, clp_min, clp_max);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpy2DAsync(dst, 2 * dst_stride, dd, 2 * w, 2 * w, h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -685,10 +686,10 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   if ((rc = ensureCap(ctx, &p->dItems, &p->capItems, (size_t)total))) return rc;
   if ((rc = ensureCap(ctx, &p->dCandBlock, &p->capCands, (size_t)n_cands))) return rc;
   if ((rc = ensureCap(ctx, &p->dCands, &p->capCandParams, (size_t)n_cands))) return rc;
+  if ((rc = ensureCap(ctx, &p->dPos, &p->capPos, (size_t)total * 32))) return rc;
   CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(p->dItemBase, itemBase, sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-  k_build_items<<<(n_blocks + 3) / 4, 128, 0, ctx->stream>>>(p->dBlocks, p->dItemBase, n_blocks, ctx->candChunk, p->dItems,
-                                                            p->dCandBlock);
+  mmk_build_items(ctx->stream, p->dBlocks, p->dItemBase, n_blocks, ctx->candChunk, p->dItems, p->dCandBlock);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->stageFree, ctx->stream));  // the pinned staging buffer may be rewritten after this point
@@ -740,26 +741,31 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
   P.dist = d_dist;
   P.dst = d_dst;
   P.dstStride = dst_stride;
-  k_cand_setup<<<(plan->nCands + 127) / 128, 128, 0, ctx->stream>>>(ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs,
-                                                                   mv_prec_shift, ctx->dRot, plan->nCands, plan->dCands);
+  mmk_cand_setup(ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot, plan->nCands, plan->dCands);
   ctx->launches++;
   int rc;
   P.oobMode = (mode == MM_MODE_DIST) ? MMGPU_OOB_ME : MMGPU_OOB_PRED;
   if (mode == MM_MODE_DIST) CU(cudaMemsetAsync(d_dist, 0, sizeof(unsigned long long) * plan->nCands, ctx->stream));
   if ((rc = timingEvent(ctx))) return rc;
-  // One launch over all work items (grouped by motion model).  Per-model specialised launches (k_me<MODE, model>)
-  // were measured slower (0.194 vs 0.168 ms per frame batch): the tails of five kernels cost more than the smaller
-  // code saves; the template parameter is kept for single-model batches.
+  // k_map: positions of all entries.  Work items are grouped by motion model; ctx->mapPerModel launches one
+  // specialised kernel per model present, otherwise one generic launch covers all items.
+  if (ctx->mapPerModel)
   {
-    const int grid = (plan->nItems + 3) / 4;
-    int only = -1, nModels = 0;
     for (int m = 0; m < MM_NUM_MODELS; ++m)
-      if (plan->modelCount[m]) { only = m; nModels++; }
-    (void)only;
-    if (mode == MM_MODE_DIST) k_me<MM_MODE_DIST, -1><<<grid, 128, 0, ctx->stream>>>(P);
-    else k_me<MM_MODE_PRED, -1><<<grid, 128, 0, ctx->stream>>>(P);
+      if (plan->modelCount[m])
+      {
+        mmk_map(ctx->stream, P, plan->modelFirst[m], plan->modelCount[m], m, plan->dPos);
+        ctx->launches++;
+      }
+  }
+  else
+  {
+    mmk_map(ctx->stream, P, 0, plan->nItems, -1, plan->dPos);
     ctx->launches++;
   }
+  if ((rc = timingEvent(ctx))) return rc;
+  mmk_fir(ctx->stream, P, mode, plan->dPos);
+  ctx->launches++;
   if ((rc = timingEvent(ctx))) return rc;
   CU(cudaGetLastError());
   return MMGPU_OK;
@@ -839,8 +845,7 @@ extern "C" int mmgpu_dmvr_costs(mmgpu_ctx* ctx, int n_subpus, const mmgpu_dmvr_s
   P.clpMax = clp_max;
   P.oobMode = MMGPU_OOB_PRED;
   const int nItems = (int)items.size();
-  k_dmvr<<<(nItems + 3) / 4, 128, 0, ctx->stream>>>(P, ctx->dSubpus, ctx->dDmvrItems, nItems, ctx->cfg.had_mode == MMGPU_HAD_SIMD,
-                                                  ctx->dDist);
+  mmk_dmvr(ctx->stream, P, ctx->dSubpus, ctx->dDmvrItems, nItems, ctx->cfg.had_mode == MMGPU_HAD_SIMD, ctx->dDist);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(costs, ctx->dDist, sizeof(uint64_t) * (size_t)n_subpus * 25, cudaMemcpyDeviceToHost, ctx->stream));
@@ -957,8 +962,8 @@ extern "C" int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* job
   P.clpMax = clp_max;
   P.oobMode = MMGPU_OOB_PRED;
   const int shift = ctx->fir.cpShift + 1, offset = (1 << (shift - 1)) + 2 * 8192;
-  k_mc_jobs<<<n_jobs, 64, 0, ctx->stream>>>(P, ctx->dJobs, ctx->dPic[0], ctx->dPic[1], ctx->dPic[2], pitch[0], pitch[1],
-                                           scaleX(1, fmt), scaleY(1, fmt), shift, offset);
+  mmk_mc_jobs(ctx->stream, P, n_jobs, ctx->dJobs, ctx->dPic[0], ctx->dPic[1], ctx->dPic[2], pitch[0], pitch[1], scaleX(1, fmt),
+              scaleY(1, fmt), shift, offset);
   ctx->launches++;
   CU(cudaGetLastError());
   for (int c = 0; c < numComps(ctx); ++c)
