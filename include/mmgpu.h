@@ -81,7 +81,8 @@ int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* map_ms, double* fir_ms, uin
 /* ---- reference pictures: Picture::getRecoBuf(compID, wrapRef) after extendPicBorder (Picture.cpp:988-1092) */
 /* plane00[c] points at sample (0,0) of component c in HOST memory; the margins around it are copied too. */
 int mmgpu_set_ref(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3]);
-/* same, but plane00[c] are DEVICE pointers owned by the caller (kept resident, zero copy): used when the
+/* same, but plane00[c] are DEVICE pointers owned by the caller (kept resident, zero copy; 8-byte aligned, stride a
+ * multiple of 4 samples): used when the
  * picture arrives by ncclBroadcast or was reconstructed on the device. */
 int mmgpu_set_ref_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3]);
 /* un-padded planes in host memory: upload + Picture::extendPicBorder on the device. */

@@ -12,7 +12,7 @@ OBJ = os.path.join(CSRC, "_obj")
 HDRS = ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_sbpos.cuh", "mm_fir.cuh"]
 # unit -> headers it depends on (besides include/mmgpu.h)
 UNITS = {
-    "mmgpu.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh"],
+    "mmgpu.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_fir.cuh"],
     "mm_kernels_map.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_sbpos.cuh"],
     "mm_kernels_fir.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_fir.cuh"],
     "mm_kernels_mc.cu": HDRS,

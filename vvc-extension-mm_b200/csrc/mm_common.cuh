@@ -33,12 +33,15 @@ struct MmRef
   int32_t poc;
 };
 
-struct MmItem  // one warp of work
+struct __align__(16) MmItem  // one warp of work: everything k_map / k_fir need to know about their block (two 16-byte loads)
 {
-  int32_t block;  // index into blocks
-  int32_t cand;   // first candidate (global index) handled by this warp
-  int32_t sb;     // first sub-block (tile-major index) handled by this warp
-  int32_t ncand;  // number of consecutive candidates this warp evaluates
+  int32_t x, y;      // luma position of the block
+  uint32_t wh;       // w | h << 16
+  uint32_t rmr;      // ref_slot | model << 16 | rot_slot << 24
+  uint32_t orgxy;    // org_x | org_y << 16
+  int32_t cand;      // first candidate (global index) handled by this warp
+  int32_t sb;        // first sub-block (tile-major index) handled by this warp
+  int32_t candEnd;   // cand_first + cand_count of the block
 };
 
 struct MmFir  // InterpolationFilter::filter<> shifts/offsets for the context's bit depth
@@ -66,6 +69,7 @@ struct MmParams
   const uint8_t* mpaVip[3];
   const float2* thTab[2];    // [scalar|packet][rows4]: (sin, cos) of theta(4*row + off)   (ERP toSphere hoisted)
   const float2* phTab[2];    // [scalar|packet][cols4]: (sin, cos) of phi(4*col + off)
+  const uint32_t* hTaps;     // mm_build_htaps table (MM_HTAPS_WORDS words) in global memory
   const int16_t* org;
   int32_t orgStride;
   int32_t distKind, subShift, hadMode;
@@ -88,13 +92,17 @@ __device__ __forceinline__ const float* mm_rot_ptr(const float* rot, int model, 
 // -------------------------------------------------------------------------------------------------
 // Filter tables (InterpolationFilter.cpp:82-100, 187-221)
 // -------------------------------------------------------------------------------------------------
+#define MM_LUMA_FILTER_INIT \
+  {0, 0, 0, 64, 0, 0, 0, 0},       {0, 1, -3, 63, 4, -2, 1, 0},      {-1, 2, -5, 62, 8, -3, 1, 0}, \
+  {-1, 3, -8, 60, 13, -4, 1, 0},   {-1, 4, -10, 58, 17, -5, 1, 0},   {-1, 4, -11, 52, 26, -8, 3, -1}, \
+  {-1, 3, -9, 47, 31, -10, 4, -1}, {-1, 4, -11, 45, 34, -10, 4, -1}, {-1, 4, -11, 40, 40, -11, 4, -1}, \
+  {-1, 4, -10, 34, 45, -11, 4, -1}, {-1, 4, -10, 31, 47, -9, 3, -1}, {-1, 3, -8, 26, 52, -11, 4, -1}, \
+  {0, 1, -5, 17, 58, -10, 4, -1},  {0, 1, -4, 13, 60, -8, 3, -1},    {0, 1, -3, 8, 62, -5, 2, -1}, \
+  {0, 1, -2, 4, 63, -3, 1, 0}
 static __constant__ int8_t c_lumaFilter[16][8] = {
-  {0, 0, 0, 64, 0, 0, 0, 0},       {0, 1, -3, 63, 4, -2, 1, 0},      {-1, 2, -5, 62, 8, -3, 1, 0},
-  {-1, 3, -8, 60, 13, -4, 1, 0},   {-1, 4, -10, 58, 17, -5, 1, 0},   {-1, 4, -11, 52, 26, -8, 3, -1},
-  {-1, 3, -9, 47, 31, -10, 4, -1}, {-1, 4, -11, 45, 34, -10, 4, -1}, {-1, 4, -11, 40, 40, -11, 4, -1},
-  {-1, 4, -10, 34, 45, -11, 4, -1}, {-1, 4, -10, 31, 47, -9, 3, -1}, {-1, 3, -8, 26, 52, -11, 4, -1},
-  {0, 1, -5, 17, 58, -10, 4, -1},  {0, 1, -4, 13, 60, -8, 3, -1},    {0, 1, -3, 8, 62, -5, 2, -1},
-  {0, 1, -2, 4, 63, -3, 1, 0}};
+  MM_LUMA_FILTER_INIT};
+static const int8_t h_lumaFilter[16][8] = {
+  MM_LUMA_FILTER_INIT};
 static __constant__ int8_t c_chromaFilter[32][4] = {
   {0, 64, 0, 0},    {-1, 63, 2, 0},   {-2, 62, 4, 0},   {-2, 60, 7, -1},  {-2, 58, 10, -2}, {-3, 57, 12, -2},
   {-4, 56, 14, -2}, {-4, 55, 15, -2}, {-4, 54, 16, -2}, {-5, 53, 18, -2}, {-6, 52, 20, -2}, {-6, 49, 24, -3},
@@ -153,8 +161,8 @@ struct MmDmvrItem
 // ---- launch wrappers (defined next to their kernels) ---------------------------------------------------------
 void mmk_mpa_cache(cudaStream_t s, const MmGeom& g, int model, float2* out, uint8_t* vip);
 void mmk_trig_tables(cudaStream_t s, const MmGeom& g, float2* th0, float2* th1, float2* ph0, float2* ph1);
-void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* itemBase, int nBlocks, int candChunk,
-                     MmItem* items, int32_t* candBlock);
+void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* itemBase, int nBlocks, MmItem* items,
+                     int32_t* candBlock);
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
                     int mvShift, const float* rot, int nCands, MmCand* out);
 void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,

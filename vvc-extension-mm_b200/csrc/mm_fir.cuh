@@ -101,24 +101,57 @@ __device__ __forceinline__ void mm_fir4(const int w0, const int w1, const int w2
 }
 
 // pred[r*4+c]; BI = false: clipped prediction, BI = true: 14-bit intermediate
+// Second (vertical) pass over the packed first-pass rows P[pair][column]; pred[r*4+c].
 template <bool BI>
-__device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* taps, const int16_t* __restrict__ ref,
-                                               int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
-                                               int* pred)
+__device__ __forceinline__ void mm_fir_vpass(const MmFir& f, const int (*P)[4], const MmTaps& tv, bool copy, int lo, int hi,
+                                             int* pred)
 {
-  const MmTaps th = taps[xFrac], tv = taps[yFrac];
-  const int a = xPos - 3;
-  const int sh = (a & 1) << 4;
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(ref + (long)(yPos - 3) * stride + (a & ~1));
-  const int wstride = stride >> 1;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+  {
+    int o0, o1, o2, o3;
+    mm_fir4(P[0][c], P[1][c], P[2][c], P[3][c], P[4][c], P[5][c], tv, BI ? 0 : f.off2, o0, o1, o2, o3);
+    if (BI)
+    {
+      pred[0 * 4 + c] = (int)(int16_t)(o0 >> f.shift2bi);
+      pred[1 * 4 + c] = (int)(int16_t)(o1 >> f.shift2bi);
+      pred[2 * 4 + c] = (int)(int16_t)(o2 >> f.shift2bi);
+      pred[3 * 4 + c] = (int)(int16_t)(o3 >> f.shift2bi);
+    }
+    else
+    {
+      o0 = (int)(int16_t)(o0 >> f.shift2); o1 = (int)(int16_t)(o1 >> f.shift2);
+      o2 = (int)(int16_t)(o2 >> f.shift2); o3 = (int)(int16_t)(o3 >> f.shift2);
+      pred[0 * 4 + c] = copy ? o0 : mm_clip(o0, lo, hi);
+      pred[1 * 4 + c] = copy ? o1 : mm_clip(o1, lo, hi);
+      pred[2 * 4 + c] = copy ? o2 : mm_clip(o2, lo, hi);
+      pred[3 * 4 + c] = copy ? o3 : mm_clip(o3, lo, hi);
+    }
+  }
+}
+
+// Core.  SMEM = false: `base` points at the 32-bit word holding sample (xPos-3)&~1 of row yPos-3 in global memory (read-only
+// path, word stride `wstride`).  SMEM = true: the window is read from a staged box in shared memory whose row R starts
+// at word R*wstride + (R>>2) (mm_stage_row: the skew spreads lanes that sit 4 rows apart over the banks); `base` points
+// at the window's first word inside row 0 of the box and `row0` is the box row of the window's first row.
+// sh = 16 if xPos-3 is odd.
+__device__ __forceinline__ int mm_stage_row(int R, int pitchW) { return R * pitchW + (R >> 2); }
+
+template <bool BI, bool SMEM>
+__device__ __forceinline__ void mm_fir_luma4x4_core(const MmFir& f, const MmTaps* taps, const uint32_t* base, int wstride,
+                                                    int row0, int sh, int xFrac, int yFrac, int lo, int hi, int* pred)
+{
+  const MmTaps th = taps[xFrac];
+  const MmTaps tv = taps[yFrac];
   int P[6][4];  // vertical pairs of first-pass rows, per column
   int hprev[4];
 #pragma unroll
   for (int r = 0; r < 11; ++r)
   {
-    const uint32_t* rowp = base + (long)r * wstride;
-    uint32_t w0 = __ldg(rowp + 0), w1 = __ldg(rowp + 1), w2 = __ldg(rowp + 2), w3 = __ldg(rowp + 3), w4 = __ldg(rowp + 4),
-             w5 = __ldg(rowp + 5);
+    const uint32_t* rowp = SMEM ? (base + mm_stage_row(row0 + r, wstride)) : (base + (long)r * wstride);
+    uint32_t w0, w1, w2, w3, w4, w5;
+    if (SMEM) { w0 = rowp[0]; w1 = rowp[1]; w2 = rowp[2]; w3 = rowp[3]; w4 = rowp[4]; w5 = rowp[5]; }
+    else { w0 = __ldg(rowp + 0); w1 = __ldg(rowp + 1); w2 = __ldg(rowp + 2); w3 = __ldg(rowp + 3); w4 = __ldg(rowp + 4); w5 = __ldg(rowp + 5); }
     w0 = __funnelshift_r(w0, w1, sh);
     w1 = __funnelshift_r(w1, w2, sh);
     w2 = __funnelshift_r(w2, w3, sh);
@@ -144,29 +177,109 @@ __device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* tap
       hprev[0] = h0; hprev[1] = h1; hprev[2] = h2; hprev[3] = h3;
     }
   }
-  const bool copy = (xFrac | yFrac) == 0;
+  mm_fir_vpass<BI>(f, P, tv, (xFrac | yFrac) == 0, lo, hi, pred);
+}
+
+template <bool BI>
+__device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* taps, const int16_t* __restrict__ ref,
+                                               int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
+                                               int* pred)
+{
+  const int a = xPos - 3;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(ref + (long)(yPos - 3) * stride + (a & ~1));
+  mm_fir_luma4x4_core<BI, false>(f, taps, base, stride >> 1, 0, (a & 1) << 4, xFrac, yFrac, lo, hi, pred);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Wide-load variant of the luma path (k_fir).  A row is read as four aligned 8-byte words (16 samples starting at
+// (xPos-3)&~3): half the load requests of the 4-byte gather and fewer L1 wavefronts.  The horizontal alignment
+// o = (xPos-3)&3 is folded into per-lane coefficient words, so no realignment shifts are needed:
+//   h_j = sum_{k=0..5} dp2a(v[(j>>1)+k], C[o][xFrac][j][k]),  C = the 8 taps placed at sample offset o+j, zeros elsewhere.
+// Table (built on the host, mm_build_htaps): t[((o*16 + phase)*4 + j)*3 + m] packs pairs k=2m (low half) and 2m+1 (high half).
+// Entry o = 0 also holds the vertical pass' words: j=0 -> (a0,a1,0), j=1 -> (b0,b1,b2) of MmTaps.
+// -------------------------------------------------------------------------------------------------
+#define MM_HTAPS_WORDS (4 * 16 * 12)
+static inline void mm_build_htaps(uint32_t* t, const int8_t (*lf)[8])
+{
+  for (int o = 0; o < 4; ++o)
+    for (int ph = 0; ph < 16; ++ph)
+      for (int j = 0; j < 4; ++j)
+        for (int m = 0; m < 3; ++m)
+        {
+          uint32_t w = 0;
+          for (int b = 0; b < 4; ++b)
+          {
+            const int k = 2 * m + (b >> 1);                 // pair index inside the output's 6 pairs
+            const int sample = 2 * ((j >> 1) + k) + (b & 1);  // sample index inside the 16-sample row
+            const int tap = sample - (o + j);
+            const int c = (tap >= 0 && tap < 8) ? lf[ph][tap] : 0;
+            w |= (uint32_t)(c & 0xff) << (8 * b);
+          }
+          t[((o * 16 + ph) * 4 + j) * 3 + m] = w;
+        }
+}
+
+__device__ __forceinline__ int mm_fir6(int v0, int v1, int v2, int v3, int v4, int v5, uint32_t c0, uint32_t c1, uint32_t c2,
+                                       int init)
+{
+  return __dp2a_lo(v0, (int)c0, __dp2a_hi(v1, (int)c0, __dp2a_lo(v2, (int)c1, __dp2a_hi(v3, (int)c1,
+         __dp2a_lo(v4, (int)c2, __dp2a_hi(v5, (int)c2, init))))));
+}
+
+// htaps: the table in shared memory; ref plane 8-byte aligned with a stride that is a multiple of 4 samples.
+template <bool BI>
+__device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32_t* htaps, const int16_t* __restrict__ ref,
+                                                    int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
+                                                    int* pred)
+{
+  const int a = xPos - 3;
+  const uint4* e = reinterpret_cast<const uint4*>(htaps + (((a & 3) * 16 + xFrac) * 12));
+#ifdef MM_HTAPS_SMEM
+#define MM_TLD(p) (*(p))
+#else
+#define MM_TLD(p) __ldg(p)
+#endif
+  const uint4 e0 = MM_TLD(e), e1 = MM_TLD(e + 1), e2 = MM_TLD(e + 2);   // c[j][m] = word j*3+m: e0 = c00 c01 c02 c10, e1 = c11 c12 c20 c21, e2 = c22 c30 c31 c32
+  const uint2* base = reinterpret_cast<const uint2*>(ref + (long)(yPos - 3) * stride + (a & ~3));
+  const int qstride = stride >> 2;
+  int P[6][4];  // vertical pairs of first-pass rows, per column
+  int hprev[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int r = 0; r < 11; ++r)
   {
-    int o0, o1, o2, o3;
-    mm_fir4(P[0][c], P[1][c], P[2][c], P[3][c], P[4][c], P[5][c], tv, BI ? 0 : f.off2, o0, o1, o2, o3);
-    if (BI)
+    const uint2* rowp = base + (long)r * qstride;
+#ifdef MM_ABL_NOLOAD   // ablation build only (tools/): no reference loads
+    const uint2 q0 = make_uint2(r + xPos, yPos), q1 = make_uint2(xPos, r ^ yPos), q2 = q0, q3 = q1;
+    (void)rowp;
+#else
+    const uint2 q0 = __ldg(rowp + 0), q1 = __ldg(rowp + 1), q2 = __ldg(rowp + 2), q3 = __ldg(rowp + 3);
+#endif
+    int h0 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0.x, e0.y, e0.z, f.off1);
+    int h1 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0.w, e1.x, e1.y, f.off1);
+    int h2 = mm_fir6((int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, (int)q3.x, e1.z, e1.w, e2.x, f.off1);
+    int h3 = mm_fir6((int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, (int)q3.x, e2.y, e2.z, e2.w, f.off1);
+    h0 >>= f.shift1; h1 >>= f.shift1; h2 >>= f.shift1; h3 >>= f.shift1;
+    if (r & 1)
     {
-      pred[0 * 4 + c] = (int)(int16_t)(o0 >> f.shift2bi);
-      pred[1 * 4 + c] = (int)(int16_t)(o1 >> f.shift2bi);
-      pred[2 * 4 + c] = (int)(int16_t)(o2 >> f.shift2bi);
-      pred[3 * 4 + c] = (int)(int16_t)(o3 >> f.shift2bi);
+      P[r >> 1][0] = __byte_perm(hprev[0], h0, 0x5410);
+      P[r >> 1][1] = __byte_perm(hprev[1], h1, 0x5410);
+      P[r >> 1][2] = __byte_perm(hprev[2], h2, 0x5410);
+      P[r >> 1][3] = __byte_perm(hprev[3], h3, 0x5410);
+    }
+    else if (r == 10)
+    {
+      P[5][0] = h0 & 0xffff; P[5][1] = h1 & 0xffff; P[5][2] = h2 & 0xffff; P[5][3] = h3 & 0xffff;
     }
     else
     {
-      o0 = (int)(int16_t)(o0 >> f.shift2); o1 = (int)(int16_t)(o1 >> f.shift2);
-      o2 = (int)(int16_t)(o2 >> f.shift2); o3 = (int)(int16_t)(o3 >> f.shift2);
-      pred[0 * 4 + c] = copy ? o0 : mm_clip(o0, lo, hi);
-      pred[1 * 4 + c] = copy ? o1 : mm_clip(o1, lo, hi);
-      pred[2 * 4 + c] = copy ? o2 : mm_clip(o2, lo, hi);
-      pred[3 * 4 + c] = copy ? o3 : mm_clip(o3, lo, hi);
+      hprev[0] = h0; hprev[1] = h1; hprev[2] = h2; hprev[3] = h3;
     }
   }
+  const uint32_t* ev = htaps + yFrac * 12;   // entry o = 0: words 0,1 = a0,a1; 3,4,5 = b0,b1,b2
+  MmTaps tv;
+  tv.a0 = (int)MM_TLD(ev); tv.a1 = (int)MM_TLD(ev + 1); tv.b0 = (int)MM_TLD(ev + 3); tv.b1 = (int)MM_TLD(ev + 4);
+  tv.b2 = (int)MM_TLD(ev + 5);
+  mm_fir_vpass<BI>(f, P, tv, (xFrac | yFrac) == 0, lo, hi, pred);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ __global__ void k_trig_tables(MmGeom g, float2* th0, float2* th1, float2* ph0, f
 // (host-computed, grouped by motion model); also fills the candidate -> block map used by k_cand_setup.
 // -------------------------------------------------------------------------------------------------
 __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ itemBase, int nBlocks,
-                              int candChunk, MmItem* __restrict__ items, int32_t* __restrict__ candBlock)
+                              MmItem* __restrict__ items, int32_t* __restrict__ candBlock)
 {
   const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,23 +57,34 @@ __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int3
   const int n = (b.w >> 2) * (b.h >> 2);
   const int base = itemBase[bi];
   for (int j = lane; j < b.cand_count; j += 32) candBlock[b.cand_first + j] = bi;
-  // a work item = up to candChunk candidates (n >= 32) or candChunk steps of 32/n candidates (n < 32) of one
-  // 32-sub-block chunk: the warp prepares the candidate-independent state once and loops over the candidates
+  // a work item = 32 consecutive (candidate, sub-block) entries of the block: one candidate's 32-sub-block chunk
+  // (n >= 32) or 32/n candidates (n < 32)
+  MmItem it;
+  it.x = b.x; it.y = b.y;
+  it.wh = (uint32_t)b.w | ((uint32_t)b.h << 16);
+  it.rmr = (uint32_t)b.ref_slot | ((uint32_t)b.model << 16) | ((uint32_t)b.rot_slot << 24);
+  it.orgxy = (uint32_t)b.org_x | ((uint32_t)b.org_y << 16);
+  it.candEnd = b.cand_first + b.cand_count;
   if (n >= 32)
   {
-    const int chunks = n >> 5, groups = (b.cand_count + candChunk - 1) / candChunk, total = groups * chunks;
+    const int chunks = n >> 5, total = b.cand_count * chunks;
     for (int t = lane; t < total; t += 32)
     {
-      const int gidx = t / chunks, ch = t - gidx * chunks;
-      const int c0 = gidx * candChunk;
-      items[base + t] = MmItem{bi, b.cand_first + c0, ch << 5, min(candChunk, b.cand_count - c0)};
+      const int c0 = t / chunks, ch = t - c0 * chunks;
+      it.cand = b.cand_first + c0;
+      it.sb = ch << 5;
+      items[base + t] = it;
     }
   }
   else
   {
-    const int per = (32 / n) * candChunk, total = (b.cand_count + per - 1) / per;
+    const int per = 32 / n, total = (b.cand_count + per - 1) / per;
     for (int t = lane; t < total; t += 32)
-      items[base + t] = MmItem{bi, b.cand_first + t * per, 0, min(per, b.cand_count - t * per)};
+    {
+      it.cand = b.cand_first + t * per;
+      it.sb = 0;
+      items[base + t] = it;
+    }
   }
 }
 
@@ -142,26 +153,25 @@ __global__ void __launch_bounds__(128, MM_MAP_MINBLOCKS) k_map(const MmParams P,
   if (w0 >= count) return;
   const int warp = first + w0;
   const MmItem it = P.items[warp];
-  const mmgpu_block b = P.blocks[it.block];
-  const int n = (b.w >> 2) * (b.h >> 2);
+  const int bw = it.wh & 0xffff, bh = it.wh >> 16;
+  const int n = (bw >> 2) * (bh >> 2);
   int cand, sb;
   if (n >= 32) { cand = it.cand; sb = it.sb + lane; }
   else { cand = it.cand + lane / n; sb = lane % n; }
-  const bool valid = cand < b.cand_first + b.cand_count;
-  const int candc = valid ? cand : it.cand;  // lanes past the last candidate redo a valid one, result unused
-  const MmSub s = mm_sub_from_index(b.w, b.h, sb);
+  const int candc = (cand < it.candEnd) ? cand : it.cand;  // lanes past the last candidate redo a valid one, result unused
+  const MmSub s = mm_sub_from_index(bw, bh, sb);
   const MmCand c = P.cands[candc];
   int fx, fy;
-  const int model = (MODEL >= 0) ? MODEL : b.model;
+  const int model = (MODEL >= 0) ? MODEL : (int)((it.rmr >> 16) & 0xff);
   if (model == MM_CLASSIC)
   {
-    fx = ((b.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
-    fy = ((b.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
+    fx = ((it.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
+    fy = ((it.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
   }
   else
   {
-    const float* R = mm_rot_ptr(P.rot, model, b.rot_slot);
-    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, b.x, b.y, b.w, b.h, c, R, s.row, s.col, &fx, &fy);
+    const float* R = mm_rot_ptr(P.rot, model, (int)(it.rmr >> 24));
+    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, it.x, it.y, bw, bh, c, R, s.row, s.col, &fx, &fy);
     const int mc = (P.oobMode == MMGPU_OOB_ME) ? 0 : P.maxCU;
     const int xP = fx >> 4, yP = fy >> 4;
     if (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4) fx = MM_POS_OOB;
@@ -180,10 +190,10 @@ void mmk_trig_tables(cudaStream_t s, const MmGeom& g, float2* th0, float2* th1, 
   const int nt = g.rows4 > g.cols4 ? g.rows4 : g.cols4;
   k_trig_tables<<<(nt + 127) / 128, 128, 0, s>>>(g, th0, th1, ph0, ph1);
 }
-void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* itemBase, int nBlocks, int candChunk,
-                     MmItem* items, int32_t* candBlock)
+void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* itemBase, int nBlocks, MmItem* items,
+                     int32_t* candBlock)
 {
-  k_build_items<<<(nBlocks + 3) / 4, 128, 0, s>>>(blocks, itemBase, nBlocks, candChunk, items, candBlock);
+  k_build_items<<<(nBlocks + 3) / 4, 128, 0, s>>>(blocks, itemBase, nBlocks, items, candBlock);
 }
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
                     int mvShift, const float* rot, int nCands, MmCand* out)

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include "mm_common.cuh"
+#include "mm_fir.cuh"
 
 #define MM_MAX_ROT 64
 
@@ -46,6 +47,7 @@ struct mmgpu_ctx
   uint8_t* dMpaVip[3];
   float2* dThTab[2];
   float2* dPhTab[2];
+  uint32_t* dHTaps;  // mm_build_htaps: alignment-folded luma coefficient words for k_fir
   // original picture
   int16_t* dOrgOwned;
   size_t orgCap;
@@ -69,7 +71,6 @@ struct mmgpu_ctx
   size_t capDmvrItems;
   // pinned host staging for small per-call tables (reused; guarded by an event)
   bool mapPerModel;
-  int candChunk;  // candidates evaluated by one warp per work item (amortises the candidate-independent part)
   void* hStage;
   size_t capStage;
   cudaEvent_t stageFree;
@@ -112,6 +113,7 @@ static MmParams baseParams(mmgpu_ctx* ctx)
   P.rot = ctx->dRot;
   for (int i = 0; i < 3; ++i) { P.mpa[i] = ctx->dMpa[i]; P.mpaVip[i] = ctx->dMpaVip[i]; }
   for (int i = 0; i < 2; ++i) { P.thTab[i] = ctx->dThTab[i]; P.phTab[i] = ctx->dPhTab[i]; }
+  P.hTaps = ctx->dHTaps;
   P.org = ctx->dOrg;
   P.orgStride = ctx->orgStride;
   P.hadMode = ctx->cfg.had_mode;
@@ -203,7 +205,6 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   ctx->hStage = nullptr;
   ctx->capStage = 0;
   ctx->mapPerModel = getenv("MMGPU_MAP_PER_MODEL") != nullptr;
-  ctx->candChunk = 1;  // k_me evaluates one candidate per work item (a candidate loop was measured slower: DESIGN.md 4)
   ctx->stageBusy = false;
   ctx->evUsed = 0;
   ctx->evAccumMs[0] = ctx->evAccumMs[1] = 0;
@@ -258,6 +259,12 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     CU(cudaMalloc(&ctx->dThTab[v], sizeof(float2) * g.rows4));
     CU(cudaMalloc(&ctx->dPhTab[v], sizeof(float2) * g.cols4));
   }
+  {
+    std::vector<uint32_t> ht(MM_HTAPS_WORDS);
+    mm_build_htaps(ht.data(), h_lumaFilter);
+    CU(cudaMalloc(&ctx->dHTaps, sizeof(uint32_t) * MM_HTAPS_WORDS));
+    CU(cudaMemcpy(ctx->dHTaps, ht.data(), sizeof(uint32_t) * MM_HTAPS_WORDS, cudaMemcpyHostToDevice));
+  }
   mmk_trig_tables(ctx->stream, g, ctx->dThTab[0], ctx->dThTab[1], ctx->dPhTab[0], ctx->dPhTab[1]);
   ctx->launches++;
   CU(cudaGetLastError());
@@ -291,6 +298,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dRot);
   for (int m = 0; m < 3; ++m) { cudaFree(ctx->dMpa[m]); cudaFree(ctx->dMpaVip[m]); }
   for (int v = 0; v < 2; ++v) { cudaFree(ctx->dThTab[v]); cudaFree(ctx->dPhTab[v]); }
+  cudaFree(ctx->dHTaps);
   cudaFree(ctx->dOrgOwned);
   freePlan(&ctx->scratchPlan);
   cudaFree(ctx->dMvs);
@@ -437,7 +445,8 @@ extern "C" int mmgpu_set_ref_device(mmgpu_ctx* ctx, int slot, int poc, const int
   for (int c = 0; c < numComps(ctx); ++c)
   {
     if (!plane00[c]) { if (c == 0) return fail(ctx, MMGPU_ERR_ARG, "null luma plane"); continue; }
-    if (((uintptr_t)plane00[c] & 3) || (stride[c] & 1)) return fail(ctx, MMGPU_ERR_ARG, "device plane must be 4-byte aligned with even stride");
+    if (((uintptr_t)plane00[c] & 7) || (stride[c] & 3))
+      return fail(ctx, MMGPU_ERR_ARG, "device plane must be 8-byte aligned with a stride that is a multiple of 4 samples");
     r.plane00[c] = plane00[c];
     r.stride[c] = stride[c];
   }
@@ -645,12 +654,11 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
       return fail(ctx, MMGPU_ERR_STATE, "block references an unset reference slot");
     if (b.cand_count < 0 || b.cand_first < 0 || (long)b.cand_first + b.cand_count > n_cands)
       return fail(ctx, MMGPU_ERR_ARG, "candidate range outside the mv array");
-    if (needOrg && ((b.org_x & 3) || b.org_x < 0 || b.org_y < 0 || b.org_x + b.w > ctx->orgW || b.org_y + b.h > ctx->orgH))
+    if (b.org_x < 0 || b.org_y < 0 || b.org_x > 0xffff || b.org_y > 0xffff) return fail(ctx, MMGPU_ERR_ARG, "org_x / org_y must be in 0..65535");
+    if (needOrg && ((b.org_x & 3) || b.org_x + b.w > ctx->orgW || b.org_y + b.h > ctx->orgH))
       return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane (or org_x not a multiple of 4)");
     const int n = (b.w >> 2) * (b.h >> 2);
-    const int chunk = ctx->candChunk;
-    const int nItems = (n >= 32) ? ((b.cand_count + chunk - 1) / chunk) * (n >> 5)
-                                 : (b.cand_count + (32 / n) * chunk - 1) / ((32 / n) * chunk);
+    const int nItems = (n >= 32) ? b.cand_count * (n >> 5) : (b.cand_count + (32 / n) - 1) / (32 / n);
     itemBase[bi] = nItems;
     order[bi] = bi;
     modelItems[b.model] += nItems;
@@ -689,7 +697,7 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   if ((rc = ensureCap(ctx, &p->dPos, &p->capPos, (size_t)total * 32))) return rc;
   CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(p->dItemBase, itemBase, sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-  mmk_build_items(ctx->stream, p->dBlocks, p->dItemBase, n_blocks, ctx->candChunk, p->dItems, p->dCandBlock);
+  mmk_build_items(ctx->stream, p->dBlocks, p->dItemBase, n_blocks, p->dItems, p->dCandBlock);
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->stageFree, ctx->stream));  // the pinned staging buffer may be rewritten after this point
