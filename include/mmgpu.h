@@ -153,6 +153,16 @@ int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stride, int w, 
 int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* blocks, int n_cands, const mmgpu_mv* mvs,
                    int mv_prec_shift, int dist_kind, int sub_shift, int clp_min, int clp_max, uint64_t* dist);
 
+/* Pipelined form of the same call for callers that have the next batch ready while this one runs (frame-level
+ * look-ahead ME): submit copies org/blocks/mvs on a copy stream into buffers owned by `slot` (0..3) and queues the
+ * kernels and the read-back of dist behind them; wait returns when dist[] of that slot is filled.  With two slots the
+ * host->device copies of batch i+1 overlap the kernels of batch i.  All host buffers must stay valid (and should be
+ * pinned) until the wait; a slot must be waited for before it is submitted again. */
+int mmgpu_me_batch_submit(mmgpu_ctx* ctx, int slot, const int16_t* org, int org_stride, int org_w, int org_h, int n_blocks,
+                          const mmgpu_block* blocks, int n_cands, const mmgpu_mv* mvs, int mv_prec_shift, int dist_kind,
+                          int sub_shift, int clp_min, int clp_max, uint64_t* dist);
+int mmgpu_me_batch_wait(mmgpu_ctx* ctx, int slot);
+
 /* Frame-wide microbench entry (SURVEY 8b mmgpu_frame_batch): the same evaluation with blocks, mvs and dist
  * already resident in HBM; asynchronous on mmgpu_stream().  `plan` comes from mmgpu_plan_create (host-built
  * work list for these blocks, uploaded once) and can be reused while the block list is unchanged. */

@@ -290,6 +290,36 @@ def test_full_frame_properties(env):
     plan.close()
 
 
+def test_pipelined_submit_wait_equals_synchronous_call(env):
+    """mmgpu_me_batch_submit / _wait (two batches in flight on two slots, copies on their own stream) return exactly
+    what the synchronous mmgpu_set_org + mmgpu_me_batch pair returns; slot misuse is reported, not ignored."""
+    import torch
+    o, g, planes, ref, cur = env
+    orgs, batches, expect = [], [], []
+    for i in range(4):
+        blocks, mvs, prec = wl.frame_batch(W, H, seed=40 + i, cands_per_block=4, mv_range=24,
+                                           models=(mm.MPA_FB, mm.ROT, mm.GED_CAMPOSE, mm.TAN, mm.T3D))
+        org = wl.synth_plane(W, H, 900 + i, shift=(1.0 + i, 0.5))
+        g.set_org(org)
+        expect.append(g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=mm.DIST_HAD).copy())
+        pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory().numpy()
+        orgs.append(pin(org).view(np.int16).reshape(H, W))
+        batches.append((pin(blocks).view(mm.api.BLOCK_DTYPE), pin(mvs).view(mm.api.MV_DTYPE),
+                        pin(np.zeros(len(mvs), dtype=np.uint64)).view(np.uint64), prec))
+    for i in range(4):
+        b, m, out, prec = batches[i]
+        if i >= 2:
+            got = g.me_batch_wait(i % 2)
+            assert np.array_equal(got, expect[i - 2]), i - 2
+        g.me_batch_submit(i % 2, orgs[i], b, m, out, mv_prec_shift=prec, dist=mm.DIST_HAD)
+    with pytest.raises(mm.MmGpuError):
+        g.me_batch_submit(0, orgs[0], *batches[0][:3])      # slot 0 is still in flight
+    for i in (2, 3):
+        assert np.array_equal(g.me_batch_wait(i % 2), expect[i]), i
+    with pytest.raises(mm.MmGpuError):
+        g.me_batch_wait(0)                                    # nothing pending
+
+
 def test_cpp_host_adapter_matches_oracle():
     """The C++ adapter (reference-shaped argument lists) end to end: MC of a GED_CAMPOSE block and
     xPatternRefinementProjected's 9-point HAD refinement equal the oracle."""

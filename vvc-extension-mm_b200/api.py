@@ -20,7 +20,7 @@ EXPORTS = [
     "mmgpu_kernel_timing_enable", "mmgpu_kernel_timing_read",
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
-    "mmgpu_me_batch", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
+    "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
     "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs",
 ]
 
@@ -92,6 +92,8 @@ def load_library():
     L.mmgpu_set_org.argtypes = [vp, vp, i32, i32, i32]
     L.mmgpu_set_org_device.argtypes = [vp, vp, i32, i32, i32]
     L.mmgpu_me_batch.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    L.mmgpu_me_batch_submit.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    L.mmgpu_me_batch_wait.argtypes = [vp, i32]
     L.mmgpu_plan_create.argtypes = [vp, i32, vp, i32, C.POINTER(vp)]
     L.mmgpu_plan_destroy.argtypes = [vp]
     L.mmgpu_me_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
@@ -283,6 +285,21 @@ class MmGpu:
         self._chk(self.L.mmgpu_me_batch(self.h, len(blocks), blocks.ctypes.data, len(mvs), mvs.ctypes.data, mv_prec_shift,
                                         dist, sub_shift, clp[0], clp[1], out.ctypes.data))
         return out
+
+    def me_batch_submit(self, slot, org, blocks, mvs, out, mv_prec_shift=4, dist=DIST_SAD, sub_shift=0, clp=(0, 1023)):
+        """Pipelined me_batch: org (2-D int16), blocks (BLOCK_DTYPE), mvs (MV_DTYPE) and out (uint64) are numpy arrays
+        (pinned for real overlap) that must stay alive and untouched until me_batch_wait(slot)."""
+        assert org.dtype == np.int16 and blocks.dtype == BLOCK_DTYPE and mvs.dtype == MV_DTYPE and out.dtype == np.uint64
+        assert blocks.flags.c_contiguous and mvs.flags.c_contiguous and out.flags.c_contiguous and len(out) == len(mvs)
+        h, w = org.shape
+        self._chk(self.L.mmgpu_me_batch_submit(self.h, slot, org.ctypes.data, org.strides[0] // 2, w, h, len(blocks),
+                                               blocks.ctypes.data, len(mvs), mvs.ctypes.data, mv_prec_shift, dist, sub_shift,
+                                               clp[0], clp[1], out.ctypes.data))
+        self._keep[("submit", slot)] = (org, blocks, mvs, out)
+
+    def me_batch_wait(self, slot):
+        self._chk(self.L.mmgpu_me_batch_wait(self.h, slot))
+        return self._keep.pop(("submit", slot))[3]
 
     def mc_jobs(self, jobs, planes, clp=(0, 1023)):
         """Whole-picture reconstruction shape: jobs (JOB_DTYPE) write their predictions into `planes`

@@ -242,6 +242,11 @@ __device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32
   const uint4 e0 = MM_TLD(e), e1 = MM_TLD(e + 1), e2 = MM_TLD(e + 2);   // c[j][m] = word j*3+m: e0 = c00 c01 c02 c10, e1 = c11 c12 c20 c21, e2 = c22 c30 c31 c32
   const uint2* base = reinterpret_cast<const uint2*>(ref + (long)(yPos - 3) * stride + (a & ~3));
   const int qstride = stride >> 2;
+#ifdef MM_FIR_PREFETCH
+  // all 11 rows of the window are requested up front (no destination registers): the row loop then hits L1
+#pragma unroll
+  for (int r = MM_FIR_PREFETCH; r < 11; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long)r * qstride));
+#endif
   int P[6][4];  // vertical pairs of first-pass rows, per column
   int hprev[4];
 #pragma unroll

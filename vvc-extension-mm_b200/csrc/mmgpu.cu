@@ -28,6 +28,29 @@ struct mmgpu_plan
   size_t capBlocks, capItems, capCands, capCandParams, capItemBase, capPos;
 };
 
+struct MmStage  // pinned host staging for the small per-call tables of a plan (reused; guarded by an event)
+{
+  void* h;
+  size_t cap;
+  cudaEvent_t freeEv;
+  bool busy;
+};
+
+#define MM_MAX_INFLIGHT 4
+struct MmSlot  // one in-flight mmgpu_me_batch_submit: its own device buffers, so copies of the next batch overlap kernels
+{
+  mmgpu_plan plan;
+  MmStage stage;
+  mmgpu_mv* dMvs;
+  size_t capMvs;
+  unsigned long long* dDist;
+  size_t capDist;
+  int16_t* dOrg;
+  size_t capOrg;
+  cudaEvent_t copied, done;
+  bool init, pending;
+};
+
 struct mmgpu_ctx
 {
   mmgpu_config cfg;
@@ -69,12 +92,10 @@ struct mmgpu_ctx
   size_t capPic[3];
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
-  // pinned host staging for small per-call tables (reused; guarded by an event)
   bool mapPerModel;
-  void* hStage;
-  size_t capStage;
-  cudaEvent_t stageFree;
-  bool stageBusy;
+  MmStage stage;            // staging of the synchronous entry points
+  cudaStream_t copyStream;  // host->device copies of submitted batches
+  MmSlot slots[MM_MAX_INFLIGHT];
   // optional CUDA-event timing of the batch kernels: events t0 | k_map | t1 | k_fir | t2 per launchMe
   bool timing;
   std::vector<cudaEvent_t> evPool;   // triples
@@ -202,10 +223,9 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   }
   ctx->launches = 0;
   ctx->timing = false;
-  ctx->hStage = nullptr;
-  ctx->capStage = 0;
+  memset(&ctx->stage, 0, sizeof(ctx->stage));
+  memset(ctx->slots, 0, sizeof(ctx->slots));
   ctx->mapPerModel = getenv("MMGPU_MAP_PER_MODEL") != nullptr;
-  ctx->stageBusy = false;
   ctx->evUsed = 0;
   ctx->evAccumMs[0] = ctx->evAccumMs[1] = 0;
   ctx->evAccumN = 0;
@@ -231,7 +251,8 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   f.cpShift = hr;
 
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&ctx->stageFree, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->stage.freeEv, cudaEventDisableTiming));
   ctx->hRefs.assign(cfg->max_refs, MmRef());
   ctx->ownedPlanes.assign((size_t)cfg->max_refs * 3, nullptr);
   CU(cudaMalloc(&ctx->dRefs, sizeof(MmRef) * cfg->max_refs));
@@ -304,8 +325,23 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dMvs);
   cudaFree(ctx->dDist);
   cudaFree(ctx->dTmp);
-  if (ctx->hStage) cudaFreeHost(ctx->hStage);
-  cudaEventDestroy(ctx->stageFree);
+  if (ctx->stage.h) cudaFreeHost(ctx->stage.h);
+  cudaEventDestroy(ctx->stage.freeEv);
+  cudaStreamSynchronize(ctx->copyStream);
+  for (int i = 0; i < MM_MAX_INFLIGHT; ++i)
+  {
+    MmSlot& sl = ctx->slots[i];
+    if (!sl.init) continue;
+    freePlan(&sl.plan);
+    if (sl.stage.h) cudaFreeHost(sl.stage.h);
+    cudaEventDestroy(sl.stage.freeEv);
+    cudaEventDestroy(sl.copied);
+    cudaEventDestroy(sl.done);
+    cudaFree(sl.dMvs);
+    cudaFree(sl.dDist);
+    cudaFree(sl.dOrg);
+  }
+  cudaStreamDestroy(ctx->copyStream);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
   cudaFree(ctx->dJobs);
@@ -494,16 +530,16 @@ extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9]
 }
 
 // ---- scratch -------------------------------------------------------------------------------------
-static int ensurePinned(mmgpu_ctx* ctx, size_t bytes)
+static int ensurePinned(mmgpu_ctx* ctx, MmStage* st, size_t bytes)
 {
-  if (ctx->stageBusy) { CU(cudaEventSynchronize(ctx->stageFree)); ctx->stageBusy = false; }
-  if (ctx->capStage >= bytes) return MMGPU_OK;
-  if (ctx->hStage) cudaFreeHost(ctx->hStage);
-  ctx->hStage = nullptr;
-  ctx->capStage = 0;
+  if (st->busy) { CU(cudaEventSynchronize(st->freeEv)); st->busy = false; }
+  if (st->cap >= bytes) return MMGPU_OK;
+  if (st->h) cudaFreeHost(st->h);
+  st->h = nullptr;
+  st->cap = 0;
   const size_t n = bytes + bytes / 2 + 4096;
-  CU(cudaMallocHost(&ctx->hStage, n));
-  ctx->capStage = n;
+  CU(cudaMallocHost(&st->h, n));
+  st->cap = n;
   return MMGPU_OK;
 }
 
@@ -635,11 +671,15 @@ extern "C" int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stri
 // Host part of a plan: validate the blocks, count the warps of work of each and lay them out grouped by motion model
 // (so the warps resident on an SM run the same model's code).  The work list itself and the candidate->block map are
 // written by k_build_items on the device; nothing here is O(candidates).
-static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_block* blocks, int n_cands, bool needOrg)
+// Copies go to `copyStream`; the device-side work list is built on `execStream` (which waits for the copies through
+// `copied` when the two differ).  orgW/orgH >= 0: also check the org rectangles against that plane.
+static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_block* blocks, int n_cands, int orgW, int orgH,
+                     MmStage* st, cudaStream_t copyStream, cudaStream_t execStream, cudaEvent_t copied)
 {
   int rc;
-  if ((rc = ensurePinned(ctx, (size_t)n_blocks * sizeof(int32_t) * 2))) return rc;
-  int32_t* itemBase = reinterpret_cast<int32_t*>(ctx->hStage);
+  const bool needOrg = orgW >= 0;
+  if ((rc = ensurePinned(ctx, st, (size_t)n_blocks * sizeof(int32_t) * 2))) return rc;
+  int32_t* itemBase = reinterpret_cast<int32_t*>(st->h);
   int32_t* order = itemBase + n_blocks;
   long modelItems[MM_NUM_MODELS] = {0};
   uint64_t samples = 0;
@@ -655,7 +695,7 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
     if (b.cand_count < 0 || b.cand_first < 0 || (long)b.cand_first + b.cand_count > n_cands)
       return fail(ctx, MMGPU_ERR_ARG, "candidate range outside the mv array");
     if (b.org_x < 0 || b.org_y < 0 || b.org_x > 0xffff || b.org_y > 0xffff) return fail(ctx, MMGPU_ERR_ARG, "org_x / org_y must be in 0..65535");
-    if (needOrg && ((b.org_x & 3) || b.org_x + b.w > ctx->orgW || b.org_y + b.h > ctx->orgH))
+    if (needOrg && ((b.org_x & 3) || b.org_x + b.w > orgW || b.org_y + b.h > orgH))
       return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane (or org_x not a multiple of 4)");
     const int n = (b.w >> 2) * (b.h >> 2);
     const int nItems = (n >= 32) ? b.cand_count * (n >> 5) : (b.cand_count + (32 / n) - 1) / (32 / n);
@@ -695,13 +735,18 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   if ((rc = ensureCap(ctx, &p->dCandBlock, &p->capCands, (size_t)n_cands))) return rc;
   if ((rc = ensureCap(ctx, &p->dCands, &p->capCandParams, (size_t)n_cands))) return rc;
   if ((rc = ensureCap(ctx, &p->dPos, &p->capPos, (size_t)total * 32))) return rc;
-  CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(p->dItemBase, itemBase, sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-  mmk_build_items(ctx->stream, p->dBlocks, p->dItemBase, n_blocks, p->dItems, p->dCandBlock);
+  CU(cudaMemcpyAsync(p->dBlocks, blocks, sizeof(mmgpu_block) * n_blocks, cudaMemcpyHostToDevice, copyStream));
+  CU(cudaMemcpyAsync(p->dItemBase, itemBase, sizeof(int32_t) * n_blocks, cudaMemcpyHostToDevice, copyStream));
+  CU(cudaEventRecord(st->freeEv, copyStream));  // the pinned staging buffer may be rewritten after this point
+  st->busy = true;
+  if (copyStream != execStream)
+  {
+    CU(cudaEventRecord(copied, copyStream));
+    CU(cudaStreamWaitEvent(execStream, copied, 0));
+  }
+  mmk_build_items(execStream, p->dBlocks, p->dItemBase, n_blocks, p->dItems, p->dCandBlock);
   ctx->launches++;
   CU(cudaGetLastError());
-  CU(cudaEventRecord(ctx->stageFree, ctx->stream));  // the pinned staging buffer may be rewritten after this point
-  ctx->stageBusy = true;
   p->ctx = ctx;
   p->nBlocks = n_blocks;
   p->nCands = n_cands;
@@ -716,7 +761,7 @@ extern "C" int mmgpu_plan_create(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block
   cudaSetDevice(ctx->cfg.device);
   mmgpu_plan* p = new mmgpu_plan();
   memset(p, 0, sizeof(*p));
-  int rc = buildPlan(ctx, p, n_blocks, blocks, n_cands, false);
+  int rc = buildPlan(ctx, p, n_blocks, blocks, n_cands, -1, -1, &ctx->stage, ctx->stream, ctx->stream, nullptr);
   if (rc) { freePlan(p); delete p; return rc; }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { freePlan(p); delete p; return fail(ctx, MMGPU_ERR_CUDA, "plan upload failed"); }
   *out = p;
@@ -732,10 +777,12 @@ extern "C" void mmgpu_plan_destroy(mmgpu_plan* p)
 extern "C" uint64_t mmgpu_plan_samples(const mmgpu_plan* p) { return p ? p->samples : 0; }
 
 static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int mode, int dist_kind,
-                    int sub_shift, int clp_min, int clp_max, unsigned long long* d_dist, int16_t* d_dst, int dst_stride)
+                    int sub_shift, int clp_min, int clp_max, unsigned long long* d_dist, int16_t* d_dst, int dst_stride,
+                    const int16_t* d_org = nullptr, int org_stride = 0)
 {
   if (mv_prec_shift < 0 || mv_prec_shift > 4) return fail(ctx, MMGPU_ERR_ARG, "mv_prec_shift must be 0..4");
   MmParams P = baseParams(ctx);
+  if (d_org) { P.org = d_org; P.orgStride = org_stride; }
   P.blocks = plan->dBlocks;
   P.items = plan->dItems;
   P.nItems = plan->nItems;
@@ -806,7 +853,8 @@ extern "C" int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* b
   if (!ctx || !blocks || !mvs || !dist || n_blocks <= 0 || n_cands <= 0) return MMGPU_ERR_ARG;
   if (!ctx->dOrg) return fail(ctx, MMGPU_ERR_STATE, "mmgpu_set_org* has not been called");
   cudaSetDevice(ctx->cfg.device);
-  int rc = buildPlan(ctx, &ctx->scratchPlan, n_blocks, blocks, n_cands, true);
+  int rc = buildPlan(ctx, &ctx->scratchPlan, n_blocks, blocks, n_cands, ctx->orgW, ctx->orgH, &ctx->stage, ctx->stream, ctx->stream,
+                     nullptr);
   if (rc) return rc;
   if ((rc = ensureCap(ctx, &ctx->dMvs, &ctx->capMvs, (size_t)n_cands))) return rc;
   if ((rc = ensureCap(ctx, &ctx->dDist, &ctx->capDist, (size_t)n_cands))) return rc;
@@ -816,6 +864,61 @@ extern "C" int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* b
   if (rc) return rc;
   CU(cudaMemcpyAsync(dist, ctx->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+// ---- pipelined variant: the copies of batch i+1 overlap the kernels of batch i ----------------------------------
+static int slotInit(mmgpu_ctx* ctx, MmSlot* sl)
+{
+  if (sl->init) return MMGPU_OK;
+  CU(cudaEventCreateWithFlags(&sl->stage.freeEv, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&sl->copied, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+  sl->init = true;
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_me_batch_submit(mmgpu_ctx* ctx, int slot, const int16_t* org, int org_stride, int org_w, int org_h,
+                                     int n_blocks, const mmgpu_block* blocks, int n_cands, const mmgpu_mv* mvs,
+                                     int mv_prec_shift, int dist_kind, int sub_shift, int clp_min, int clp_max, uint64_t* dist)
+{
+  if (!ctx || !org || !blocks || !mvs || !dist || n_blocks <= 0 || n_cands <= 0 || org_w <= 0 || org_h <= 0 || org_stride < org_w)
+    return MMGPU_ERR_ARG;
+  if (slot < 0 || slot >= MM_MAX_INFLIGHT) return fail(ctx, MMGPU_ERR_ARG, "slot out of range");
+  if (dist_kind != MMGPU_DIST_SAD && dist_kind != MMGPU_DIST_HAD) return fail(ctx, MMGPU_ERR_ARG, "bad dist_kind");
+  if (sub_shift < 0 || sub_shift > 2 || (dist_kind == MMGPU_DIST_HAD && sub_shift != 0)) return fail(ctx, MMGPU_ERR_ARG, "bad sub_shift");
+  cudaSetDevice(ctx->cfg.device);
+  MmSlot* sl = &ctx->slots[slot];
+  int rc;
+  if ((rc = slotInit(ctx, sl))) return rc;
+  if (sl->pending) return fail(ctx, MMGPU_ERR_STATE, "slot still in flight: call mmgpu_me_batch_wait first");
+  const int pitch = (org_w + 63) / 64 * 64;
+  if ((rc = ensureCap(ctx, &sl->dOrg, &sl->capOrg, (size_t)pitch * org_h))) return rc;
+  if ((rc = ensureCap(ctx, &sl->dMvs, &sl->capMvs, (size_t)n_cands))) return rc;
+  if ((rc = ensureCap(ctx, &sl->dDist, &sl->capDist, (size_t)n_cands))) return rc;
+  CU(cudaMemcpy2DAsync(sl->dOrg, 2 * (size_t)pitch, org, 2 * (size_t)org_stride, 2 * (size_t)org_w, org_h, cudaMemcpyHostToDevice,
+                       ctx->copyStream));
+  CU(cudaMemcpyAsync(sl->dMvs, mvs, sizeof(mmgpu_mv) * n_cands, cudaMemcpyHostToDevice, ctx->copyStream));
+  if ((rc = buildPlan(ctx, &sl->plan, n_blocks, blocks, n_cands, org_w, org_h, &sl->stage, ctx->copyStream, ctx->stream, sl->copied)))
+    return rc;
+  if ((rc = launchMe(ctx, &sl->plan, sl->dMvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max, sl->dDist, nullptr,
+                     0, sl->dOrg, pitch)))
+    return rc;
+  CU(cudaMemcpyAsync(dist, sl->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(sl->done, ctx->stream));
+  sl->pending = true;
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_me_batch_wait(mmgpu_ctx* ctx, int slot)
+{
+  if (!ctx) return MMGPU_ERR_ARG;
+  if (slot < 0 || slot >= MM_MAX_INFLIGHT) return fail(ctx, MMGPU_ERR_ARG, "slot out of range");
+  MmSlot* sl = &ctx->slots[slot];
+  if (!sl->init || !sl->pending) return fail(ctx, MMGPU_ERR_STATE, "nothing submitted on this slot");
+  cudaSetDevice(ctx->cfg.device);
+  CU(cudaEventSynchronize(sl->done));
+  sl->pending = false;
   return MMGPU_OK;
 }
 
