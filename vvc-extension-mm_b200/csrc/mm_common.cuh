@@ -31,7 +31,16 @@ struct MmRef
   const int16_t* plane00[3];
   int32_t stride[3];
   int32_t poc;
+  int32_t tma;     // 1: the slot's luma plane has TMA descriptors (MmParams::tmaps[slot * MM_TMA_TYPES ..])
+  int32_t pad;
 };
+
+// Shared-memory boxes of k_fir, filled by TMA (cp.async.bulk.tensor.2d) from the padded luma plane.  One box shape per
+// arrangement of a warp's 32 sub-blocks; the box pitch (words) is = 4 mod 8 so that lanes 4 picture rows apart land 16
+// banks apart.  Box bytes = w * h * 2 <= MM_TMA_BOX_BYTES.
+#define MM_TMA_TYPES 3
+#define MM_TMA_BOX_BYTES 3840
+#define MM_TMA_BOX_DIMS {{104, 18}, {56, 32}, {40, 46}}   // 16x2, 8x4 and 4x8 sub-block arrangements
 
 struct __align__(16) MmItem  // one warp of work: everything k_map / k_fir need to know about their block (two 16-byte loads)
 {
@@ -70,6 +79,8 @@ struct MmParams
   const float2* thTab[2];    // [scalar|packet][rows4]: (sin, cos) of theta(4*row + off)   (ERP toSphere hoisted)
   const float2* phTab[2];    // [scalar|packet][cols4]: (sin, cos) of phi(4*col + off)
   const uint32_t* hTaps;     // mm_build_htaps table (MM_HTAPS_WORDS words) in global memory
+  const void* tmaps;         // CUtensorMap[max_refs][MM_TMA_TYPES] in global memory (128 bytes each)
+  int32_t tmaOffX, tmaOffY;  // luma margins: tensor coordinates = picture coordinates + offset
   const int16_t* org;
   int32_t orgStride;
   int32_t distKind, subShift, hadMode;

@@ -226,13 +226,12 @@ __device__ __forceinline__ int mm_fir6(int v0, int v1, int v2, int v3, int v4, i
          __dp2a_lo(v4, (int)c2, __dp2a_hi(v5, (int)c2, init))))));
 }
 
-// htaps: the table in shared memory; ref plane 8-byte aligned with a stride that is a multiple of 4 samples.
-template <bool BI>
-__device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32_t* htaps, const int16_t* __restrict__ ref,
-                                                    int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
-                                                    int* pred)
+// htaps: the coefficient table; `base` = 8-byte word holding sample (xPos-3)&~3 of row yPos-3, `qstride` = row stride in
+// 8-byte words.  SMEM = false: global memory (read-only path); SMEM = true: a TMA-filled box in shared memory.
+template <bool BI, bool SMEM>
+__device__ __forceinline__ void mm_fir_luma4x4_wide_core(const MmFir& f, const uint32_t* htaps, const uint2* base, int qstride,
+                                                         int a, int xFrac, int yFrac, int lo, int hi, int* pred)
 {
-  const int a = xPos - 3;
   const uint4* e = reinterpret_cast<const uint4*>(htaps + (((a & 3) * 16 + xFrac) * 12));
 #ifdef MM_HTAPS_SMEM
 #define MM_TLD(p) (*(p))
@@ -240,24 +239,19 @@ __device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32
 #define MM_TLD(p) __ldg(p)
 #endif
   const uint4 e0 = MM_TLD(e), e1 = MM_TLD(e + 1), e2 = MM_TLD(e + 2);   // c[j][m] = word j*3+m: e0 = c00 c01 c02 c10, e1 = c11 c12 c20 c21, e2 = c22 c30 c31 c32
-  const uint2* base = reinterpret_cast<const uint2*>(ref + (long)(yPos - 3) * stride + (a & ~3));
-  const int qstride = stride >> 2;
-#ifdef MM_FIR_PREFETCH
-  // all 11 rows of the window are requested up front (no destination registers): the row loop then hits L1
-#pragma unroll
-  for (int r = MM_FIR_PREFETCH; r < 11; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long)r * qstride));
-#endif
   int P[6][4];  // vertical pairs of first-pass rows, per column
   int hprev[4];
 #pragma unroll
   for (int r = 0; r < 11; ++r)
   {
-    const uint2* rowp = base + (long)r * qstride;
+    const uint2* rowp = SMEM ? (base + r * qstride) : (base + (long)r * qstride);
+    uint2 q0, q1, q2, q3;
 #ifdef MM_ABL_NOLOAD   // ablation build only (tools/): no reference loads
-    const uint2 q0 = make_uint2(r + xPos, yPos), q1 = make_uint2(xPos, r ^ yPos), q2 = q0, q3 = q1;
+    q0 = make_uint2(r + a, yFrac); q1 = make_uint2(a, r ^ xFrac); q2 = q0; q3 = q1;
     (void)rowp;
 #else
-    const uint2 q0 = __ldg(rowp + 0), q1 = __ldg(rowp + 1), q2 = __ldg(rowp + 2), q3 = __ldg(rowp + 3);
+    if (SMEM) { q0 = rowp[0]; q1 = rowp[1]; q2 = rowp[2]; q3.x = reinterpret_cast<const uint32_t*>(rowp + 3)[0]; q3.y = 0; }
+    else { q0 = __ldg(rowp + 0); q1 = __ldg(rowp + 1); q2 = __ldg(rowp + 2); q3 = __ldg(rowp + 3); }
 #endif
     int h0 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0.x, e0.y, e0.z, f.off1);
     int h1 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0.w, e1.x, e1.y, f.off1);
@@ -285,6 +279,51 @@ __device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32
   tv.a0 = (int)MM_TLD(ev); tv.a1 = (int)MM_TLD(ev + 1); tv.b0 = (int)MM_TLD(ev + 3); tv.b1 = (int)MM_TLD(ev + 4);
   tv.b2 = (int)MM_TLD(ev + 5);
   mm_fir_vpass<BI>(f, P, tv, (xFrac | yFrac) == 0, lo, hi, pred);
+}
+
+// ref plane 8-byte aligned with a stride that is a multiple of 4 samples
+template <bool BI>
+__device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32_t* htaps, const int16_t* __restrict__ ref,
+                                                    int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
+                                                    int* pred)
+{
+  const int a = xPos - 3;
+  const uint2* base = reinterpret_cast<const uint2*>(ref + (long)(yPos - 3) * stride + (a & ~3));
+  mm_fir_luma4x4_wide_core<BI, false>(f, htaps, base, stride >> 2, a, xFrac, yFrac, lo, hi, pred);
+}
+
+// -------------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives (sm_100a) used by k_fir to stage a box of the reference plane in shared memory
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mm_mbar_init(unsigned long long* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mm_smem_u32(bar)), "r"(count));
+  // make the initialised barrier visible to the async proxy (TMA); the cluster-scope fence.mbarrier_init would
+  // invalidate L1 (CCTL.IVALL) once per warp
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mm_mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mm_mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(mm_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 2-D tile load: box of the tensor map at element coordinates (x, y) -> shared memory, completion on `bar`
+__device__ __forceinline__ void mm_tma_load_2d(void* dst, const void* tmap, int x, int y, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(mm_smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(mm_smem_u32(bar)) : "memory");
 }
 
 // -------------------------------------------------------------------------------------------------

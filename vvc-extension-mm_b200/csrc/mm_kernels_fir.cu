@@ -8,31 +8,14 @@
 #ifndef MM_FIR_MINBLOCKS
 #define MM_FIR_MINBLOCKS 8
 #endif
-#ifndef MM_STAGE_CAP
-#define MM_STAGE_CAP 0     // samples of the per-warp shared-memory boxes (2560 = 5 KB); 0 = gather from global memory.
-                           // Measured: staging cuts L1 wavefronts but its extra instructions cost more.
-#endif
-#ifndef MM_STAGE_MIN_LGN
-#define MM_STAGE_MIN_LGN 4  // smallest group (2^4 = 16 sub-blocks of one candidate) that is staged
-#endif
 template <int MODE>
 __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P, const int2* __restrict__ pos)
 {
-  __shared__ MmTaps s_taps[16];
-#if MM_STAGE_CAP > 0
-  __shared__ uint4 s_stage[4][MM_STAGE_CAP / 8];
+#ifndef MM_NO_TMA
+  __shared__ __align__(128) unsigned char s_box[4][MM_TMA_BOX_BYTES];
+  __shared__ __align__(8) unsigned long long s_bar[4];
 #endif
-#ifdef MM_HTAPS_SMEM
-  __shared__ __align__(16) uint32_t s_htaps[MM_HTAPS_WORDS];
-  for (int i = threadIdx.x; i < MM_HTAPS_WORDS / 4; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_htaps)[i] = __ldg(reinterpret_cast<const uint4*>(P.hTaps) + i);
-#else
-  const uint32_t* s_htaps = P.hTaps;   // 3 KB table, L1 resident: no per-CTA prologue, no barrier
-#endif
-#if MM_STAGE_CAP > 0 || defined(MM_HTAPS_SMEM)
-  mm_build_taps(s_taps);
-  __syncthreads();
-#endif
+  const uint32_t* s_htaps = P.hTaps;   // 3 KB coefficient table, L1 resident: no per-CTA prologue, no barrier
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= P.nItems) return;
@@ -47,46 +30,48 @@ __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P,
   const MmSub s = mm_sub_from_index(bw, bh, sb);
   const MmRef ref = P.refs[it.rmr & 0xffff];
 
-  // The windows of a group of lanes (11 rows x 12 samples each, neighbours overlapping by 2/3) are read once from global
-  // memory into a shared-memory box with 16-byte loads and gathered from there.  A group = the 32 sub-blocks of the warp,
-  // or the n sub-blocks of one candidate of a small block (n = 16, 8, ..).  Groups whose windows do not fit their box
-  // (strongly diverging motion) gather from global memory directly.
+  // Reference samples.  The 32 windows of a warp (11 rows x 14 samples each, neighbours overlapping by 2/3) lie inside a
+  // small box of the plane: one lane asks the TMA unit to copy that box into shared memory and the lanes gather their
+  // windows from there (per-lane 8-byte reads of shared memory instead of scattered global requests).  Warps whose
+  // windows do not fit a box shape (strongly diverging motion, candidates of small blocks sharing a warp, planes
+  // without descriptors) gather from global memory directly.
   const bool oob = fp.x == MM_POS_OOB;
   const int xP = fp.x >> 4, yP = fp.y >> 4;
-  const int ax = (xP - 3) & ~1, ay = yP - 3;
-  bool staged = false;
-  int x0 = 0, y0 = 0, pitchW = 0;
-#if MM_STAGE_CAP > 0
-  const int lgn = (n >= 32) ? 5 : (31 - __clz(n));          // lanes per group = 2^lgn
-  const int li = lane & ((1 << lgn) - 1);
-  uint32_t* sbox = reinterpret_cast<uint32_t*>(s_stage[threadIdx.x >> 5]) + (lane >> lgn) * ((MM_STAGE_CAP / 2) >> (5 - lgn));
-  if (lgn >= MM_STAGE_MIN_LGN)                                // warp-uniform
+  const int ax = (xP - 3) & ~3, ay = yP - 3;
+  int boxType = -1, x0 = 0, y0 = 0;
+#ifndef MM_NO_TMA
+  if (n >= 32 && ref.tma)   // warp-uniform
   {
-    const unsigned gmask = (lgn == 5) ? 0xffffffffu : (((1u << (1 << lgn)) - 1u) << (lane & ~((1 << lgn) - 1)));
     const int BIG = 1 << 28;
-    x0 = __reduce_min_sync(gmask, oob ? BIG : ax) & ~7;
-    y0 = __reduce_min_sync(gmask, oob ? BIG : ay);
-    const int x1 = __reduce_max_sync(gmask, oob ? -BIG : ax + 12);
-    const int y1 = __reduce_max_sync(gmask, oob ? -BIG : ay + 11);
-    const int cpr = (x1 - x0 + 7) >> 3;        // 16-byte chunks per box row
-    const int hb = y1 - y0;
-    pitchW = ((4 * cpr + 5) & ~7) + 2;         // words; = 2 mod 8, >= 4*cpr
-    const int lg = 32 - __clz(cpr - 1);        // lanes form rows of 2^lg >= cpr chunks
-    const bool aligned = ((reinterpret_cast<uintptr_t>(ref.plane00[0]) | (uintptr_t)(ref.stride[0] * 2)) & 15) == 0;
-    staged = aligned && cpr > 0 && hb > 0 && lg <= lgn && mm_stage_row(hb, pitchW) <= ((MM_STAGE_CAP / 2) >> (5 - lgn));
-    if (staged)
+    x0 = __reduce_min_sync(0xffffffffu, oob ? BIG : ax) & ~7;   // TMA: the box must start on a 16-byte boundary
+    y0 = __reduce_min_sync(0xffffffffu, oob ? BIG : ay);
+    const int wbx = __reduce_max_sync(0xffffffffu, oob ? -BIG : ax + 16) - x0;
+    const int hbx = __reduce_max_sync(0xffffffffu, oob ? -BIG : ay + 11) - y0;
+    const int dims[MM_TMA_TYPES][2] = MM_TMA_BOX_DIMS;
+    if (wbx > 0)
     {
-      const int lc = li & ((1 << lg) - 1), lr = li >> lg, rpp = (1 << lgn) >> lg;
-      const int16_t* g = ref.plane00[0] + (long)y0 * ref.stride[0] + x0;
-      if (lc < cpr)
-        for (int row = lr; row < hb; row += rpp)
-        {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + (long)row * ref.stride[0]) + lc);
-          uint32_t* d = sbox + mm_stage_row(row, pitchW) + 4 * lc;
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
+      if (wbx <= dims[0][0] && hbx <= dims[0][1]) boxType = 0;
+      else if (wbx <= dims[1][0] && hbx <= dims[1][1]) boxType = 1;
+      else if (wbx <= dims[2][0] && hbx <= dims[2][1]) boxType = 2;
+    }
+  }
+  int pitchQ = 0;   // box row pitch in 8-byte words
+  if (boxType >= 0)
+  {
+    const int dims[MM_TMA_TYPES][2] = MM_TMA_BOX_DIMS;
+    const int bxw = boxType == 0 ? dims[0][0] : (boxType == 1 ? dims[1][0] : dims[2][0]);
+    const int bxh = boxType == 0 ? dims[0][1] : (boxType == 1 ? dims[1][1] : dims[2][1]);
+    pitchQ = bxw >> 2;
+    unsigned long long* bar = &s_bar[threadIdx.x >> 5];
+    if (lane == 0)
+    {
+      mm_mbar_init(bar, 1);
+      mm_mbar_expect_tx(bar, (uint32_t)(bxw * bxh * 2));
+      const char* tmap = reinterpret_cast<const char*>(P.tmaps) + ((size_t)(it.rmr & 0xffff) * MM_TMA_TYPES + boxType) * 128;
+      mm_tma_load_2d(s_box[threadIdx.x >> 5], tmap, x0 + P.tmaOffX, y0 + P.tmaOffY, bar);
     }
     __syncwarp();
+    mm_mbar_wait(bar, 0);
   }
 #endif
   int pred[16];
@@ -95,11 +80,11 @@ __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P,
 #pragma unroll
     for (int i = 0; i < 16; ++i) pred[i] = 0;
   }
-#if MM_STAGE_CAP > 0
-  else if (staged)
+#ifndef MM_NO_TMA
+  else if (boxType >= 0)
   {
-    mm_fir_luma4x4_core<false, true>(P.fir, s_taps, sbox + ((ax - x0) >> 1), pitchW, ay - y0, ((xP - 3) & 1) << 4, fp.x & 15,
-                                     fp.y & 15, P.clpMin, P.clpMax, pred);
+    const uint2* base = reinterpret_cast<const uint2*>(s_box[threadIdx.x >> 5]) + (ay - y0) * pitchQ + ((ax - x0) >> 2);
+    mm_fir_luma4x4_wide_core<false, true>(P.fir, s_htaps, base, pitchQ, xP - 3, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax, pred);
   }
 #endif
   else

@@ -1,5 +1,6 @@
 // mmgpu.cu -- C ABI (include/mmgpu.h) over the sm_100a kernels in mm_kernels.cuh.
 // Host side is plain C++ + CUDA runtime; no torch types, no CPU fallback of the compute path.
+#include <cuda.h>          // CUtensorMap types; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -71,6 +72,8 @@ struct mmgpu_ctx
   float2* dThTab[2];
   float2* dPhTab[2];
   uint32_t* dHTaps;  // mm_build_htaps: alignment-folded luma coefficient words for k_fir
+  CUtensorMap* dTmaps;  // [max_refs][MM_TMA_TYPES] TMA descriptors of the padded luma planes (k_fir's shared-memory boxes)
+  void* encodeTiled;    // cuTensorMapEncodeTiled
   // original picture
   int16_t* dOrgOwned;
   size_t orgCap;
@@ -135,6 +138,9 @@ static MmParams baseParams(mmgpu_ctx* ctx)
   for (int i = 0; i < 3; ++i) { P.mpa[i] = ctx->dMpa[i]; P.mpaVip[i] = ctx->dMpaVip[i]; }
   for (int i = 0; i < 2; ++i) { P.thTab[i] = ctx->dThTab[i]; P.phTab[i] = ctx->dPhTab[i]; }
   P.hTaps = ctx->dHTaps;
+  P.tmaps = ctx->dTmaps;
+  P.tmaOffX = ctx->cfg.margin;
+  P.tmaOffY = ctx->cfg.margin;
   P.org = ctx->dOrg;
   P.orgStride = ctx->orgStride;
   P.hadMode = ctx->cfg.had_mode;
@@ -281,6 +287,16 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     CU(cudaMalloc(&ctx->dPhTab[v], sizeof(float2) * g.cols4));
   }
   {
+    cudaDriverEntryPointQueryResult qres;
+    ctx->encodeTiled = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encodeTiled, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      ctx->encodeTiled = nullptr;   // no descriptors: k_fir gathers from global memory
+    cudaGetLastError();
+    CU(cudaMalloc(&ctx->dTmaps, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
+    CU(cudaMemset(ctx->dTmaps, 0, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
+  }
+  {
     std::vector<uint32_t> ht(MM_HTAPS_WORDS);
     mm_build_htaps(ht.data(), h_lumaFilter);
     CU(cudaMalloc(&ctx->dHTaps, sizeof(uint32_t) * MM_HTAPS_WORDS));
@@ -320,6 +336,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   for (int m = 0; m < 3; ++m) { cudaFree(ctx->dMpa[m]); cudaFree(ctx->dMpaVip[m]); }
   for (int v = 0; v < 2; ++v) { cudaFree(ctx->dThTab[v]); cudaFree(ctx->dPhTab[v]); }
   cudaFree(ctx->dHTaps);
+  cudaFree(ctx->dTmaps);
   cudaFree(ctx->dOrgOwned);
   freePlan(&ctx->scratchPlan);
   cudaFree(ctx->dMvs);
@@ -436,8 +453,43 @@ static int ensureOwnedPlane(mmgpu_ctx* ctx, int slot, int c, int16_t** plane00, 
   *pitch = p;
   return MMGPU_OK;
 }
+typedef CUresult (*MmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptors of a slot's padded luma plane (one per box shape).  Needs a 16-byte aligned allocation and pitch;
+// otherwise the slot simply has none (r->tma = 0) and k_fir gathers from global memory.
+static int makeTmaps(mmgpu_ctx* ctx, int slot, MmRef* r)
+{
+  r->tma = 0;
+  if (!ctx->encodeTiled || getenv("MMGPU_NO_TMA")) return MMGPU_OK;
+  int w, h, mx, my;
+  compDims(ctx, 0, &w, &h, &mx, &my);
+  const int16_t* base = r->plane00[0] - (ptrdiff_t)my * r->stride[0] - mx;
+  if (((uintptr_t)base & 15) || ((size_t)r->stride[0] * 2) % 16) return MMGPU_OK;
+  const uint32_t dims[MM_TMA_TYPES][2] = MM_TMA_BOX_DIMS;
+  CUtensorMap maps[MM_TMA_TYPES];
+  for (int t = 0; t < MM_TMA_TYPES; ++t)
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)(w + 2 * mx), (cuuint64_t)(h + 2 * my)};
+    const cuuint64_t gstr[1] = {(cuuint64_t)r->stride[0] * 2};
+    const cuuint32_t box[2] = {dims[t][0], dims[t][1]};
+    const cuuint32_t estr[2] = {1, 1};
+    if (box[0] * box[1] * 2 > MM_TMA_BOX_BYTES) return fail(ctx, MMGPU_ERR_STATE, "TMA box larger than its shared-memory buffer");
+    CUresult cr = ((MmEncodeTiled)ctx->encodeTiled)(&maps[t], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)base, gdim, gstr, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return MMGPU_OK;   // not encodable: gather path
+  }
+  CU(cudaMemcpy(ctx->dTmaps + (size_t)slot * MM_TMA_TYPES, maps, sizeof(maps), cudaMemcpyHostToDevice));
+  r->tma = 1;
+  return MMGPU_OK;
+}
+
 static int publishRef(mmgpu_ctx* ctx, int slot)
 {
+  int rc = makeTmaps(ctx, slot, &ctx->hRefs[slot]);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->dRefs + slot, &ctx->hRefs[slot], sizeof(MmRef), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));  // hRefs may change right after
   return MMGPU_OK;
