@@ -363,3 +363,36 @@ __device__ __forceinline__ void mm_had_xlane(int* d, int bit, bool upper)
     d[i + 8] = keep - recv;
   }
 }
+
+// FP32 twins of the two transforms above, used by k_fir: every value is an integer below 2^24 (|coefficient| <= 128 * 1023,
+// sum of magnitudes of a tile <= 128 * sqrt(128) * 1023), so float add/sub/fma are exact, and they issue on the FP32 pipes
+// that the integer FIR leaves idle instead of the integer ALU / IMAD pipes that it saturates.
+__device__ __forceinline__ void mm_had4x4_f(float* d)
+{
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+  {
+    const float a = d[r * 4 + 0] + d[r * 4 + 1], b = d[r * 4 + 0] - d[r * 4 + 1];
+    const float c = d[r * 4 + 2] + d[r * 4 + 3], e = d[r * 4 + 2] - d[r * 4 + 3];
+    d[r * 4 + 0] = a + c; d[r * 4 + 1] = b + e; d[r * 4 + 2] = a - c; d[r * 4 + 3] = b - e;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+  {
+    const float a = d[0 * 4 + c] + d[1 * 4 + c], b = d[0 * 4 + c] - d[1 * 4 + c];
+    const float g = d[2 * 4 + c] + d[3 * 4 + c], e = d[2 * 4 + c] - d[3 * 4 + c];
+    d[0 * 4 + c] = a + g; d[1 * 4 + c] = b + e; d[2 * 4 + c] = a - g; d[3 * 4 + c] = b - e;
+  }
+}
+// cross-lane butterfly: every lane ends with d[i] (lower lane) + / - d[i] (upper lane): the lower lane keeps the sums, the
+// upper lane the differences (sign irrelevant for the sum of magnitudes): one shuffle and one fma per element, no selects.
+// d[0] of lane q = 0 stays the DC term.
+__device__ __forceinline__ void mm_had_xlane_f(float* d, int bit, float sgn /* +1 lower lane, -1 upper lane */)
+{
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+  {
+    const float recv = __shfl_xor_sync(0xffffffffu, d[i], bit);
+    d[i] = fmaf(sgn, d[i], recv);
+  }
+}

@@ -133,21 +133,21 @@ __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P,
   }
   else
   {
-#ifndef MM_ABL_NOHAD   // ablation build only: no 4x4 transform / cross-lane butterflies
-    mm_had4x4(d);
-#endif
-    // tile transform across the T adjacent lanes (q = lane & (T-1)); uniform per warp (same block)
-#ifndef MM_ABL_NOHAD
-    if (s.T >= 2) mm_had_xlane(d, 1, (lane & 1) != 0);
-    if (s.T >= 4) mm_had_xlane(d, 2, (lane & 2) != 0);
-    if (s.T >= 8) mm_had_xlane(d, 4, (lane & 4) != 0);
-#endif
-    unsigned int sum = 0;
+    float df[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sum += (unsigned int)abs(d[i]);
+    for (int i = 0; i < 16; ++i) df[i] = (float)d[i];
+    mm_had4x4_f(df);
+    // tile transform across the T adjacent lanes (q = lane & (T-1)); uniform per warp (same block)
+    if (s.T >= 2) mm_had_xlane_f(df, 1, (lane & 1) ? -1.0f : 1.0f);
+    if (s.T >= 4) mm_had_xlane_f(df, 2, (lane & 2) ? -1.0f : 1.0f);
+    if (s.T >= 8) mm_had_xlane_f(df, 4, (lane & 4) ? -1.0f : 1.0f);
+    float fsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fsum += fabsf(df[i]);
+    unsigned int sum = (unsigned int)fsum;
     if (s.q == 0)
     {
-      const unsigned int dc = (unsigned int)abs(d[0]);  // JVET_R0164_MEAN_SCALED_SATD
+      const unsigned int dc = (unsigned int)fabsf(df[0]);  // JVET_R0164_MEAN_SCALED_SATD
       sum = sum - dc + (dc >> 2);
     }
     if (s.T >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
