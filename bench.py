@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 W, H, CTU = 2048, 1024, 128
 CANDS = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fir<DIST> launch of this workload, from the committed
-# `ncu --set full` capture (profiles/ncu_k_fir_r01c_summary.csv); None until that capture exists for the current kernel.
-NCU_TRAFFIC_BYTES = None
+# `ncu --set full` capture (profiles/ncu_k_map_k_fir_r01d_summary.csv: 27.645696 MB read + 4.096 KB written).
+NCU_TRAFFIC_BYTES = 27649792
 POOL = 32            # synthetic frames resident per GPU (references cycle through them: 270 MB > L2)
 MV_RANGE = 64
 EPIPOLE = (1.0, 0.0, 0.0)
