@@ -38,9 +38,11 @@ struct MmRef
 // Shared-memory boxes of k_fir, filled by TMA (cp.async.bulk.tensor.2d) from the padded luma plane.  One box shape per
 // arrangement of a warp's 32 sub-blocks; the box pitch (words) is = 4 mod 8 so that lanes 4 picture rows apart land 16
 // banks apart.  Box bytes = w * h * 2 <= MM_TMA_BOX_BYTES.
-#define MM_TMA_TYPES 3
-#define MM_TMA_BOX_BYTES 3840
-#define MM_TMA_BOX_DIMS {{104, 18}, {56, 32}, {40, 46}}   // 16x2, 8x4 and 4x8 sub-block arrangements
+#define MM_TMA_TYPES 6
+#define MM_TMA_BOX_BYTES 5120
+// 16x2, 8x4 and 4x8 sub-block arrangements: tight boxes first (less L2 -> shared-memory traffic), then taller ones for
+// warps whose motion shears the arrangement vertically
+#define MM_TMA_BOX_DIMS {{104, 18}, {56, 32}, {40, 46}, {104, 24}, {56, 44}, {40, 62}}
 
 struct __align__(16) MmItem  // one warp of work: everything k_map / k_fir need to know about their block (two 16-byte loads)
 {

@@ -50,17 +50,19 @@ __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P,
     const int dims[MM_TMA_TYPES][2] = MM_TMA_BOX_DIMS;
     if (wbx > 0)
     {
-      if (wbx <= dims[0][0] && hbx <= dims[0][1]) boxType = 0;
-      else if (wbx <= dims[1][0] && hbx <= dims[1][1]) boxType = 1;
-      else if (wbx <= dims[2][0] && hbx <= dims[2][1]) boxType = 2;
+#pragma unroll
+      for (int t = MM_TMA_TYPES - 1; t >= 0; --t)
+        if (wbx <= dims[t][0] && hbx <= dims[t][1]) boxType = t;
     }
   }
   int pitchQ = 0;   // box row pitch in 8-byte words
   if (boxType >= 0)
   {
     const int dims[MM_TMA_TYPES][2] = MM_TMA_BOX_DIMS;
-    const int bxw = boxType == 0 ? dims[0][0] : (boxType == 1 ? dims[1][0] : dims[2][0]);
-    const int bxh = boxType == 0 ? dims[0][1] : (boxType == 1 ? dims[1][1] : dims[2][1]);
+    int bxw = dims[0][0], bxh = dims[0][1];
+#pragma unroll
+    for (int t = 1; t < MM_TMA_TYPES; ++t)
+      if (boxType == t) { bxw = dims[t][0]; bxh = dims[t][1]; }
     pitchQ = bxw >> 2;
     unsigned long long* bar = &s_bar[threadIdx.x >> 5];
     if (lane == 0)

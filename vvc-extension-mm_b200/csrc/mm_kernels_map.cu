@@ -67,10 +67,11 @@ __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int3
   it.candEnd = b.cand_first + b.cand_count;
   if (n >= 32)
   {
+    // chunk-major: the candidates of one 32-sub-block chunk are consecutive items (k_map prepares the chunk once)
     const int chunks = n >> 5, total = b.cand_count * chunks;
     for (int t = lane; t < total; t += 32)
     {
-      const int c0 = t / chunks, ch = t - c0 * chunks;
+      const int ch = t / b.cand_count, c0 = t - ch * b.cand_count;
       it.cand = b.cand_first + c0;
       it.sb = ch << 5;
       items[base + t] = it;
@@ -140,43 +141,66 @@ __global__ void k_reproject(MmParams P, int comp, int csx, int csy, int x, int y
 // k_map: one lane per (candidate, sub-block) entry of the batch; writes its 1/16-pel position, or MM_POS_OOB in .x
 // when the sub-block falls outside the picture by the caller's OOB rule (InterPrediction.cpp:776-780 /
 // InterSearch.cpp:6329-6332: the prediction of such a sub-block is 0).
+// A warp walks MM_MAP_K consecutive work items.  Items of one 32-sub-block chunk (or of one small block) are consecutive
+// and differ only in the candidate, so the candidate-independent part of the mapping (grid look-ups, toSphere, the
+// model's prepare step: mm_subblock_prepare) is computed once and only mm_subblock_apply runs per candidate; it is
+// recomputed whenever the next item belongs to another chunk / block / model.
 // MODEL >= 0: every item of the launch uses that motion model (items are grouped by model); MODEL < 0: generic.
 // -------------------------------------------------------------------------------------------------
 #ifndef MM_MAP_MINBLOCKS
 #define MM_MAP_MINBLOCKS 8
 #endif
+#ifndef MM_MAP_K
+#define MM_MAP_K 4
+#endif
 template <int MODEL>
 __global__ void __launch_bounds__(128, MM_MAP_MINBLOCKS) k_map(const MmParams P, int first, int count, int2* __restrict__ pos)
 {
-  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * MM_MAP_K;
   const int lane = threadIdx.x & 31;
   if (w0 >= count) return;
-  const int warp = first + w0;
-  const MmItem it = P.items[warp];
-  const int bw = it.wh & 0xffff, bh = it.wh >> 16;
-  const int n = (bw >> 2) * (bh >> 2);
-  int cand, sb;
-  if (n >= 32) { cand = it.cand; sb = it.sb + lane; }
-  else { cand = it.cand + lane / n; sb = lane % n; }
-  const int candc = (cand < it.candEnd) ? cand : it.cand;  // lanes past the last candidate redo a valid one, result unused
-  const MmSub s = mm_sub_from_index(bw, bh, sb);
-  const MmCand c = P.cands[candc];
-  int fx, fy;
-  const int model = (MODEL >= 0) ? MODEL : (int)((it.rmr >> 16) & 0xff);
-  if (model == MM_CLASSIC)
+  const int nIt = min(MM_MAP_K, count - w0);
+  const int mc = (P.oobMode == MMGPU_OOB_ME) ? 0 : P.maxCU;
+  MmSbState st;
+  MmSub s;
+  int4 key = make_int4(-1, -1, -1, -1);   // (x, y, wh, rmr) of the prepared chunk; sb is checked separately
+  int keySb = -1, n = 0, bw = 0, bh = 0, model = 0;
+  const float* R = P.rot;
+#pragma unroll 1
+  for (int j = 0; j < nIt; ++j)
   {
-    fx = ((it.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
-    fy = ((it.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
+    const int warp = first + w0 + j;
+    const MmItem it = P.items[warp];
+    const bool fresh = it.x != key.x || it.y != key.y || (int)it.wh != key.z || (int)it.rmr != key.w || it.sb != keySb;
+    if (fresh)
+    {
+      bw = it.wh & 0xffff; bh = it.wh >> 16;
+      n = (bw >> 2) * (bh >> 2);
+      s = mm_sub_from_index(bw, bh, (n >= 32) ? it.sb + lane : lane % n);
+      model = (MODEL >= 0) ? MODEL : (int)((it.rmr >> 16) & 0xff);
+      R = mm_rot_ptr(P.rot, model, (int)(it.rmr >> 24));
+    }
+    const int cand = (n >= 32) ? it.cand : it.cand + lane / n;
+    const int candc = (cand < it.candEnd) ? cand : it.cand;  // lanes past the last candidate redo a valid one, result unused
+    const MmCand c = P.cands[candc];
+    int fx, fy;
+    if (model == MM_CLASSIC)
+    {
+      fx = ((it.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
+      fy = ((it.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
+    }
+    else
+    {
+      if (fresh)
+        mm_subblock_prepare(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, it.x, it.y, bw, bh, c, R, s.row, s.col, &st);
+      mm_subblock_apply(P.g, model, 0, 0, 0, c, R, st, &fx, &fy);
+      const int xP = fx >> 4, yP = fy >> 4;
+      if (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4) fx = MM_POS_OOB;
+    }
+    key = make_int4(it.x, it.y, (int)it.wh, (int)it.rmr);
+    keySb = it.sb;
+    pos[(long)warp * 32 + lane] = make_int2(fx, fy);
   }
-  else
-  {
-    const float* R = mm_rot_ptr(P.rot, model, (int)(it.rmr >> 24));
-    mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, it.x, it.y, bw, bh, c, R, s.row, s.col, &fx, &fy);
-    const int mc = (P.oobMode == MMGPU_OOB_ME) ? 0 : P.maxCU;
-    const int xP = fx >> 4, yP = fy >> 4;
-    if (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4) fx = MM_POS_OOB;
-  }
-  pos[(long)warp * 32 + lane] = make_int2(fx, fy);
 }
 
 // ---- launch wrappers -----------------------------------------------------------------------------
@@ -209,7 +233,7 @@ void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy
 void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model, int2* pos)
 {
   if (count <= 0) return;
-  const int grid = (count + 3) / 4;
+  const int grid = ((count + MM_MAP_K - 1) / MM_MAP_K + 3) / 4;
   switch (model)
   {
 #ifdef MM_MAP_PER_MODEL
