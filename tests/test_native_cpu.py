@@ -17,7 +17,8 @@ CXXFLAGS = ["-O2", "-std=c++17", "-msse4.1", "-ffp-contract=off", "-fno-builtin"
 
 def _build(src, out, extra):
     os.makedirs(BUILD, exist_ok=True)
-    deps = [os.path.join(NATIVE, src)] + [os.path.join(ROOT, "vvc-extension-mm_b200", "csrc", f) for f in ("mm_libm.cuh", "mm_map.cuh")]
+    deps = [os.path.join(NATIVE, src)] + [os.path.join(ROOT, "vvc-extension-mm_b200", "csrc", f)
+                                          for f in ("mm_libm.cuh", "mm_map.cuh", "mm_htaps.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++"] + CXXFLAGS + extra + ["-x", "c++", os.path.join(NATIVE, src), "-o", out, "-lm"])
     return out
@@ -30,6 +31,15 @@ def test_libm_port_pinned_against_box_libm():
     out = subprocess.run([exe, "509", "8"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "total mismatches 0" in out.stdout
+
+
+def test_fir_coefficient_table_equals_eight_tap_filter():
+    """csrc/mm_htaps.h (k_fir's alignment-folded coefficient words, built on the host) reproduces the plain 8-tap sum for
+    all 4 alignments x 16 phases x 4 outputs, and carries the vertical pass' words."""
+    exe = _build("htaps_check.cpp", os.path.join(BUILD, "htaps_check"), [])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches" in out.stdout
 
 
 def test_product_mapping_host_build_equals_oracle():

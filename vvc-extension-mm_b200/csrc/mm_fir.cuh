@@ -198,26 +198,7 @@ __device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* tap
 // Table (built on the host, mm_build_htaps): t[((o*16 + phase)*4 + j)*3 + m] packs pairs k=2m (low half) and 2m+1 (high half).
 // Entry o = 0 also holds the vertical pass' words: j=0 -> (a0,a1,0), j=1 -> (b0,b1,b2) of MmTaps.
 // -------------------------------------------------------------------------------------------------
-#define MM_HTAPS_WORDS (4 * 16 * 12)
-static inline void mm_build_htaps(uint32_t* t, const int8_t (*lf)[8])
-{
-  for (int o = 0; o < 4; ++o)
-    for (int ph = 0; ph < 16; ++ph)
-      for (int j = 0; j < 4; ++j)
-        for (int m = 0; m < 3; ++m)
-        {
-          uint32_t w = 0;
-          for (int b = 0; b < 4; ++b)
-          {
-            const int k = 2 * m + (b >> 1);                 // pair index inside the output's 6 pairs
-            const int sample = 2 * ((j >> 1) + k) + (b & 1);  // sample index inside the 16-sample row
-            const int tap = sample - (o + j);
-            const int c = (tap >= 0 && tap < 8) ? lf[ph][tap] : 0;
-            w |= (uint32_t)(c & 0xff) << (8 * b);
-          }
-          t[((o * 16 + ph) * 4 + j) * 3 + m] = w;
-        }
-}
+#include "mm_htaps.h"
 
 __device__ __forceinline__ int mm_fir6(int v0, int v1, int v2, int v3, int v4, int v5, uint32_t c0, uint32_t c1, uint32_t c2,
                                        int init)

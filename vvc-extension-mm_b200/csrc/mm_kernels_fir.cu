@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P,
   const bool valid = cand < it.candEnd;
   const MmSub s = mm_sub_from_index(bw, bh, sb);
   const MmRef ref = P.refs[it.rmr & 0xffff];
+  const int16_t* orgp = P.org + (long)((int)(it.orgxy >> 16) + s.row * 4) * P.orgStride + ((int)(it.orgxy & 0xffff) + s.col * 4);
 
   // Reference samples.  The 32 windows of a warp (11 rows x 14 samples each, neighbours overlapping by 2/3) lie inside a
   // small box of the plane: one lane asks the TMA unit to copy that box into shared memory and the lanes gather their
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P,
   }
 
   // differences org - pred
-  const int16_t* o = P.org + (long)((int)(it.orgxy >> 16) + s.row * 4) * P.orgStride + ((int)(it.orgxy & 0xffff) + s.col * 4);
+  const int16_t* o = orgp;
   int d[16];
 #pragma unroll
   for (int r = 0; r < 4; ++r)

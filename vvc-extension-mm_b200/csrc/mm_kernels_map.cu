@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(128, MM_MAP_MINBLOCKS) k_map(const MmParams P,
   }
 }
 
+#ifndef MM_CS_THREADS
+#define MM_CS_THREADS 128
+#endif
 // ---- launch wrappers -----------------------------------------------------------------------------
 void mmk_mpa_cache(cudaStream_t s, const MmGeom& g, int model, float2* out, uint8_t* vip)
 {
@@ -222,7 +225,7 @@ void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* i
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
                     int mvShift, const float* rot, int nCands, MmCand* out)
 {
-  k_cand_setup<<<(nCands + 127) / 128, 128, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, nCands, out);
+  k_cand_setup<<<(nCands + MM_CS_THREADS - 1) / MM_CS_THREADS, MM_CS_THREADS, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, nCands, out);
 }
 void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                    int model, int rotSlot, int32_t* outX, int32_t* outY)
