@@ -182,7 +182,8 @@ void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy
                    int model, int rotSlot, int32_t* outX, int32_t* outY);
 // positions of items [first, first+count) of P.items; model >= 0: all of them use that motion model
 void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model, int2* pos);
-void mmk_fir(cudaStream_t s, const MmParams& P, int mode, const int2* pos);
+// FIR + distortion (or prediction write-out) of items [first, first+count)
+void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, const int2* pos);
 void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my);
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi);

@@ -9,16 +9,17 @@
 #define MM_FIR_MINBLOCKS 8
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P, const int2* __restrict__ pos)
+__global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P, int first, int count, const int2* __restrict__ pos)
 {
 #ifndef MM_NO_TMA
   __shared__ __align__(128) unsigned char s_box[4][MM_TMA_BOX_BYTES];
   __shared__ __align__(8) unsigned long long s_bar[4];
 #endif
   const uint32_t* s_htaps = P.hTaps;   // 3 KB coefficient table, L1 resident: no per-CTA prologue, no barrier
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= P.nItems) return;
+  if (w0 >= count) return;
+  const int warp = first + w0;
   const MmItem it = P.items[warp];
   const int2 fp = __ldg(&pos[(long)warp * 32 + lane]);
   const int bw = it.wh & 0xffff, bh = it.wh >> 16;
@@ -207,12 +208,12 @@ __global__ void k_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1
 }
 
 // ---- launch wrappers -----------------------------------------------------------------------------
-void mmk_fir(cudaStream_t s, const MmParams& P, int mode, const int2* pos)
+void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, const int2* pos)
 {
-  if (P.nItems <= 0) return;
-  const int grid = (P.nItems + 3) / 4;
-  if (mode == MM_MODE_DIST) k_fir<MM_MODE_DIST><<<grid, 128, 0, s>>>(P, pos);
-  else k_fir<MM_MODE_PRED><<<grid, 128, 0, s>>>(P, pos);
+  if (count <= 0) return;
+  const int grid = (count + 3) / 4;
+  if (mode == MM_MODE_DIST) k_fir<MM_MODE_DIST><<<grid, 128, 0, s>>>(P, first, count, pos);
+  else k_fir<MM_MODE_PRED><<<grid, 128, 0, s>>>(P, first, count, pos);
 }
 void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my)
 {

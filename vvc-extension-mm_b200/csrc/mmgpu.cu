@@ -871,7 +871,7 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
     ctx->launches++;
   }
   if ((rc = timingEvent(ctx))) return rc;
-  mmk_fir(ctx->stream, P, mode, plan->dPos);
+  mmk_fir(ctx->stream, P, 0, plan->nItems, mode, plan->dPos);
   ctx->launches++;
   if ((rc = timingEvent(ctx))) return rc;
   CU(cudaGetLastError());
