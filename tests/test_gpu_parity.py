@@ -320,6 +320,42 @@ def test_pipelined_submit_wait_equals_synchronous_call(env):
         g.me_batch_wait(0)                                    # nothing pending
 
 
+def test_tma_boxes_equal_gather_path(env):
+    """k_fir reads the reference through TMA-filled shared-memory boxes when the slot has descriptors and gathers from
+    global memory otherwise (MMGPU_NO_TMA at registration time; also what unaligned device planes get).  Both paths,
+    SAD and HAD, all models incl. poles / ERP seam / picture borders, give identical distortions; a sample is checked
+    against the oracle."""
+    import os
+    o, g, planes, ref, cur = env
+    g.set_ref(1, 0, [p.origin for p in ref], [p.stride for p in ref])           # descriptors
+    os.environ["MMGPU_NO_TMA"] = "1"
+    try:
+        g.set_ref(2, 0, [p.origin for p in ref], [p.stride for p in ref])       # gather only
+    finally:
+        del os.environ["MMGPU_NO_TMA"]
+    g.set_org(cur[0])
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=61, cands_per_block=3, mv_range=40,
+                                       models=(mm.MPA_FB, mm.MPA_LR, mm.MPA_TB, mm.TAN, mm.T3D, mm.ROT, mm.GED_CAMPOSE, 0))
+    res = {}
+    for slot in (1, 2):
+        b = blocks.copy(); b["ref_slot"] = slot
+        for dist in (mm.DIST_SAD, mm.DIST_HAD):
+            res[(slot, dist)] = g.me_batch(b, mvs, mv_prec_shift=prec, dist=dist).copy()
+    for dist in (mm.DIST_SAD, mm.DIST_HAD):
+        assert np.array_equal(res[(1, dist)], res[(2, dist)]), dist
+    rng = np.random.default_rng(3)
+    for bi in rng.choice(len(blocks), 60, replace=False):
+        b = blocks[bi]
+        if b["model"] == 0:
+            continue
+        sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+        org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+        m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+        exp = o.me_block(planes[0], org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                         mv_prec_shift=prec, dist=mm.DIST_HAD, had_mode=ol.HAD_SIMD)
+        assert np.array_equal(exp, res[(1, mm.DIST_HAD)][sl]), b
+
+
 def test_cpp_host_adapter_matches_oracle():
     """The C++ adapter (reference-shaped argument lists) end to end: MC of a GED_CAMPOSE block and
     xPatternRefinementProjected's 9-point HAD refinement equal the oracle."""
