@@ -240,7 +240,13 @@ def main():
     d_mvs = torch.from_numpy(mvs.view(np.int32).reshape(-1, 2).copy()).to(dev)
     d_dist = torch.zeros(n_cands, dtype=torch.int64, device=dev)
     d_org = torch.empty((N * H, W), dtype=torch.int16, device=dev)
-    h_org = torch.empty((N * H, W), dtype=torch.int16).pin_memory()
+    # e2e uploads only what this rank evaluates: its CTU rows of the N original pictures, packed into one plane
+    # (frame f, kept row k -> lines (f * len(rows) + k) * CTU ..); blocks of the e2e call point into that plane
+    n_rows = len(rows)
+    h_org = torch.empty((N * n_rows * CTU, W), dtype=torch.int16).pin_memory()
+    row_pos = {r: k for k, r in enumerate(rows)}
+    e2e_org_y = np.array([((int(b["org_y"]) // H) * n_rows + row_pos[(int(b["org_y"]) % H) // CTU]) * CTU + int(b["org_y"]) % CTU
+                          for b in blocks], dtype=np.int32)
     h_blocks = torch.from_numpy(blocks.view(np.int32).reshape(-1, 12).copy()).pin_memory()
     h_mvs = torch.from_numpy(mvs.view(np.int32).reshape(-1, 2).copy()).pin_memory()
     h_dist = torch.zeros(n_cands, dtype=torch.int64).pin_memory()
@@ -303,6 +309,7 @@ def main():
         _, b = step_plan(s)
         hb = h_blocks2[s % 2].numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
         hb["ref_slot"] = b["ref_slot"]
+        hb["org_y"] = e2e_org_y
         gpu.me_batch_submit(s % 2, h_org.numpy(), hb, h_mvs.numpy().view(mm.api.MV_DTYPE).reshape(-1),
                             h_dist2[s % 2].numpy().view(np.uint64), mv_prec_shift=prec, dist=mm.DIST_HAD)
         if N > 1:
@@ -346,7 +353,8 @@ def main():
     with torch.cuda.stream(stream):
         load_orgs(0, d_org, pool_org_d)
     for f in range(N):
-        h_org[f * H:(f + 1) * H].copy_(pool_org_h[(f + 1) % POOL])
+        for k, r in enumerate(rows):
+            h_org[(f * n_rows + k) * CTU:(f * n_rows + k + 1) * CTU].copy_(pool_org_h[(f + 1) % POOL][r * CTU:(r + 1) * CTU])
 
     for s in range(POOL if N == 1 else 2):
         step_plan(s)          # plans (device-resident block / work lists) are built once, outside any timed region
@@ -367,6 +375,21 @@ def main():
     for s in range(4):
         e2e_step(s)
     e2e_drain(4)
+    # self-check: the host-facing call and the device-resident call evaluate the same batch -> identical distortions
+    for p in range(2):
+        freed[p].record(stream)
+    prefetch(0)
+    device_step(0)
+    barrier()
+    chk_dev = d_dist.cpu().numpy().view(np.uint64).copy()
+    for p in range(2):
+        freed[p].record(stream)
+    prefetch(0)
+    e2e_submit(0)
+    gpu.me_batch_wait(0)
+    if not np.array_equal(chk_dev, h_dist2[0].numpy().view(np.uint64)):
+        raise SystemExit("bench self-check failed: e2e distortions differ from the device-resident path")
+    barrier()
     e2e_dev_ms, e2e_wall_ms = timed(e2e_step, args.steps, lambda s: None, e2e_drain)
     clocks = sampler.stop()
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
