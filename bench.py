@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 W, H, CTU = 2048, 1024, 128
 CANDS = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fir<DIST> launch of this workload, from the committed
-# `ncu --set full` capture (profiles/ncu_k_map_k_fir_r01d_summary.csv: 27.645696 MB read + 4.096 KB written).
-NCU_TRAFFIC_BYTES = 27649792
+# `ncu --set full` capture (profiles/ncu_k_map_k_fir_r01e_summary.csv: 27.660544 MB read + 0.768 KB written).
+NCU_TRAFFIC_BYTES = 27661312
 POOL = 32            # synthetic frames resident per GPU (references cycle through them: 270 MB > L2)
 MV_RANGE = 64
 EPIPOLE = (1.0, 0.0, 0.0)

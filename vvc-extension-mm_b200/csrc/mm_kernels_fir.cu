@@ -5,15 +5,18 @@
 // -------------------------------------------------------------------------------------------------
 // k_fir: one warp per work item (32 sub-block-candidates of one block), one 4x4 sub-block per lane.
 // -------------------------------------------------------------------------------------------------
+#ifndef MM_FIR_WARPS
+#define MM_FIR_WARPS 1       // warps per CTA: one, so a finished warp frees its slot at once (1/2/4/8 measured: 0.0967/0.0976/0.0982/0.1020 ms)
+#endif
 #ifndef MM_FIR_MINBLOCKS
-#define MM_FIR_MINBLOCKS 8
+#define MM_FIR_MINBLOCKS (32 / MM_FIR_WARPS)
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(128, MM_FIR_MINBLOCKS) k_fir(const MmParams P, int first, int count, const int2* __restrict__ pos)
+__global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(const MmParams P, int first, int count, const int2* __restrict__ pos)
 {
 #ifndef MM_NO_TMA
-  __shared__ __align__(128) unsigned char s_box[4][MM_TMA_BOX_BYTES];
-  __shared__ __align__(8) unsigned long long s_bar[4];
+  __shared__ __align__(128) unsigned char s_box[MM_FIR_WARPS][MM_TMA_BOX_BYTES];
+  __shared__ __align__(8) unsigned long long s_bar[MM_FIR_WARPS];
 #endif
   const uint32_t* s_htaps = P.hTaps;   // 3 KB coefficient table, L1 resident: no per-CTA prologue, no barrier
   const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -211,9 +214,9 @@ __global__ void k_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1
 void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, const int2* pos)
 {
   if (count <= 0) return;
-  const int grid = (count + 3) / 4;
-  if (mode == MM_MODE_DIST) k_fir<MM_MODE_DIST><<<grid, 128, 0, s>>>(P, first, count, pos);
-  else k_fir<MM_MODE_PRED><<<grid, 128, 0, s>>>(P, first, count, pos);
+  const int grid = (count + MM_FIR_WARPS - 1) / MM_FIR_WARPS;
+  if (mode == MM_MODE_DIST) k_fir<MM_MODE_DIST><<<grid, 32 * MM_FIR_WARPS, 0, s>>>(P, first, count, pos);
+  else k_fir<MM_MODE_PRED><<<grid, 32 * MM_FIR_WARPS, 0, s>>>(P, first, count, pos);
 }
 void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my)
 {

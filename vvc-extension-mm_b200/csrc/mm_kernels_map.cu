@@ -147,14 +147,17 @@ __global__ void k_reproject(MmParams P, int comp, int csx, int csy, int x, int y
 // recomputed whenever the next item belongs to another chunk / block / model.
 // MODEL >= 0: every item of the launch uses that motion model (items are grouped by model); MODEL < 0: generic.
 // -------------------------------------------------------------------------------------------------
+#ifndef MM_MAP_WARPS
+#define MM_MAP_WARPS 4       // warps per CTA
+#endif
 #ifndef MM_MAP_MINBLOCKS
-#define MM_MAP_MINBLOCKS 8
+#define MM_MAP_MINBLOCKS (32 / MM_MAP_WARPS)
 #endif
 #ifndef MM_MAP_K
 #define MM_MAP_K 4
 #endif
 template <int MODEL>
-__global__ void __launch_bounds__(128, MM_MAP_MINBLOCKS) k_map(const MmParams P, int first, int count, int2* __restrict__ pos)
+__global__ void __launch_bounds__(32 * MM_MAP_WARPS, MM_MAP_MINBLOCKS) k_map(const MmParams P, int first, int count, int2* __restrict__ pos)
 {
   const int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * MM_MAP_K;
   const int lane = threadIdx.x & 31;
@@ -236,22 +239,22 @@ void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy
 void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model, int2* pos)
 {
   if (count <= 0) return;
-  const int grid = ((count + MM_MAP_K - 1) / MM_MAP_K + 3) / 4;
+  const int grid = ((count + MM_MAP_K - 1) / MM_MAP_K + MM_MAP_WARPS - 1) / MM_MAP_WARPS;
   switch (model)
   {
 #ifdef MM_MAP_PER_MODEL
-    case MM_CLASSIC: k_map<MM_CLASSIC><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_MPA_FRONT_BACK: k_map<MM_MPA_FRONT_BACK><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_MPA_LEFT_RIGHT: k_map<MM_MPA_LEFT_RIGHT><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_MPA_TOP_BOTTOM: k_map<MM_MPA_TOP_BOTTOM><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_TANGENTIAL: k_map<MM_TANGENTIAL><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_THREE_D_TRANSLATIONAL: k_map<MM_THREE_D_TRANSLATIONAL><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_ROTATIONAL: k_map<MM_ROTATIONAL><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_GEODESIC_X: k_map<MM_GEODESIC_X><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_GEODESIC_Y: k_map<MM_GEODESIC_Y><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_GEODESIC_Z: k_map<MM_GEODESIC_Z><<<grid, 128, 0, s>>>(P, first, count, pos); break;
-    case MM_GEODESIC_CAMPOSE: k_map<MM_GEODESIC_CAMPOSE><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    case MM_CLASSIC: k_map<MM_CLASSIC><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_MPA_FRONT_BACK: k_map<MM_MPA_FRONT_BACK><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_MPA_LEFT_RIGHT: k_map<MM_MPA_LEFT_RIGHT><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_MPA_TOP_BOTTOM: k_map<MM_MPA_TOP_BOTTOM><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_TANGENTIAL: k_map<MM_TANGENTIAL><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_THREE_D_TRANSLATIONAL: k_map<MM_THREE_D_TRANSLATIONAL><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_ROTATIONAL: k_map<MM_ROTATIONAL><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_X: k_map<MM_GEODESIC_X><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_Y: k_map<MM_GEODESIC_Y><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_Z: k_map<MM_GEODESIC_Z><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
+    case MM_GEODESIC_CAMPOSE: k_map<MM_GEODESIC_CAMPOSE><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
 #endif
-    default: k_map<-1><<<grid, 128, 0, s>>>(P, first, count, pos); break;
+    default: k_map<-1><<<grid, 32 * MM_MAP_WARPS, 0, s>>>(P, first, count, pos); break;
   }
 }
