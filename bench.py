@@ -271,6 +271,8 @@ def main():
             plans[key] = (gpu.plan(b, n_cands), b)
         return plans[key]
 
+    exchange = shard.PictureExchange(pic_bytes, dev) if N > 1 else None
+
     def prefetch(s):
         """Rank f owns frame f of step s: it copies its picture into the landing buffer and NCCL-broadcasts it.
         Runs on the communication stream, one step ahead of the compute stream."""
@@ -279,7 +281,7 @@ def main():
         p = s % 2
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(freed[p])
-            shard.allgather_pictures(comm[p], pool_ref[(s * N + rank) % POOL])
+            exchange.allgather(comm[p], pool_ref[(s * N + rank) % POOL])
             ready[p].record(comm_stream)
 
     def load_orgs(s, tgt, src_pool):
@@ -375,10 +377,16 @@ def main():
     for s in range(4):
         e2e_step(s)
     e2e_drain(4)
-    # self-check: the host-facing call and the device-resident call evaluate the same batch -> identical distortions
+    # self-check: the host-facing call and the device-resident call evaluate the same batch -> identical distortions;
+    # with N > 1 the exchanged pictures are what their owners hold (every rank can regenerate every synthetic picture)
     for p in range(2):
         freed[p].record(stream)
     prefetch(0)
+    if N > 1:
+        barrier()
+        for f in range(N):
+            if not torch.equal(comm[0][f * pic_bytes:(f + 1) * pic_bytes], pool_ref[f % POOL]):
+                raise SystemExit("bench self-check failed: picture %d arrived corrupted on rank %d (%s)" % (f, rank, exchange.mode))
     device_step(0)
     barrier()
     chk_dev = d_dist.cpu().numpy().view(np.uint64).copy()
@@ -434,8 +442,9 @@ def main():
                        "candidates_per_rank": int(n_cands), "sample_candidates_per_step": samples_all,
                        "l2": "references cycle through %d resident frames (%.0f MB of luma planes > 126 MB L2)" % (POOL, POOL * 8.4),
                        "parallelism": ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each, one owner rank each) reach "
-                                       "every GPU by one ncclAllGather, prefetched one step ahead on a second stream"
-                                       % (N, N, pic_bytes / 1e6)) if N > 1 else "1 gpu"},
+                                       "every GPU %s, prefetched one step ahead on a second stream"
+                                       % (N, N, pic_bytes / 1e6, "by copy-engine pulls from symmetric (peer) memory over NVLink"
+                                          if exchange.mode == "p2p" else "by one ncclAllGather")) if N > 1 else "1 gpu"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
                          "path": {"kernels": "k_map + k_fir<DIST>", "k_map_ms": kmap_avg_ms, "ms": path_ms,

@@ -45,6 +45,12 @@ def _worker(rank, world, port, ret):
     landing = torch.zeros(world * 1024, dtype=torch.uint8)
     shard.allgather_pictures(landing, mine)
     assert all(int(landing[r * 1024]) == r + 1 and int(landing[r * 1024 + 1023]) == r + 1 for r in range(world))
+    # the exchange object the bench uses: on CPU / gloo it must pick the collective path on every rank, same result
+    ex = shard.PictureExchange(1024, "cpu")
+    assert ex.mode == "nccl"
+    landing2 = torch.zeros(world * 1024, dtype=torch.uint8)
+    ex.allgather(landing2, mine)
+    assert torch.equal(landing, landing2)
 
     class P:
         pass
