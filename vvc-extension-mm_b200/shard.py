@@ -30,12 +30,15 @@ class PictureExchange:
     """The per-step exchange of newly reconstructed reference pictures: every rank contributes one picture, every rank
     ends up with all of them in `landing` (rank order).
 
-    mode "p2p" (default on NVLink boxes): each rank publishes its picture in a symmetric-memory staging buffer and
-    PULLS its peers' pictures with plain device-to-device copies, i.e. on the copy engines over NVLink / NVSwitch peer
-    memory -- no collective kernel occupies SMs while k_map / k_fir of the current step run (an ncclAllGather
-    overlapped with the kernels cost them 30-50 % at 8 GPUs).  Two device-side barriers (signal pads in peer memory)
-    order publish -> pull -> reuse.  mode "nccl": one ncclAllGather (also the fallback when symmetric memory cannot be
-    set up, and what the gloo CPU tests use)."""
+    mode "nccl" (default): one ncclAllGather; also what the gloo CPU tests use.
+    mode "p2p" (MMGPU_EXCHANGE=p2p): each rank publishes its picture in a symmetric-memory staging buffer and PULLS its
+    peers' pictures with plain device-to-device copies, i.e. on the copy engines over NVLink / NVSwitch peer memory, so
+    that no collective kernel occupies SMs while k_map / k_fir of the current step run; two device-side barriers (signal
+    pads in peer memory) order publish -> pull -> reuse.  Measured on 8 B200 (bench.py, 12.6 MB pictures, 88 MB per
+    rank and step): the overlapped ncclAllGather slows the kernels (k_fir 0.096 -> 0.125 ms, k_map 0.064 -> 0.095 ms) but
+    finishes inside the step (0.232 ms per step, 1158 G sample-candidates/s); the copy-engine pulls leave the kernels
+    almost alone (0.108 / 0.077 ms) but move only ~280 GB/s per GPU whether issued on 1, 4 or 7 streams, so the step
+    becomes exchange-bound (0.31 ms, 847 G/s).  At 2 GPUs both are equal (360 vs 357 G/s).  Hence the default."""
 
     def __init__(self, pic_bytes, device, group=None, mode=None):
         import os
@@ -44,7 +47,7 @@ class PictureExchange:
         self.rank = dist.get_rank(group)
         self.n = int(pic_bytes)
         self.mode = "nccl"
-        want = (mode or os.environ.get("MMGPU_EXCHANGE", "p2p")).lower()
+        want = (mode or os.environ.get("MMGPU_EXCHANGE", "nccl")).lower()
         if want == "p2p" and self.world > 1 and torch.device(device).type == "cuda":
             ok = 1
             try:
@@ -59,17 +62,32 @@ class PictureExchange:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             if int(flag.item()) == 1:
                 self.mode = "p2p"
+                # one copy engine moves ~280 GB/s over NVLink (measured: 7 pulls of 12.6 MB in 0.32 ms); several pull
+                # streams keep several engines busy
+                k = max(1, min(self.world - 1, int(os.environ.get("MMGPU_EXCHANGE_STREAMS", "4"))))
+                self.side = [torch.cuda.Stream(device=device) for _ in range(k)]
+                self.fork = torch.cuda.Event()
+                self.join = [torch.cuda.Event() for _ in range(k)]
 
     def allgather(self, landing, mine):
         """Enqueue the exchange on the current stream."""
         if self.mode == "nccl":
             dist.all_gather_into_tensor(landing, mine, group=self.group)
             return
+        cur = torch.cuda.current_stream()
         self.stage.copy_(mine, non_blocking=True)
+        landing[self.rank * self.n:(self.rank + 1) * self.n].copy_(mine, non_blocking=True)
         self.hdl.barrier(channel=0)                     # every rank's picture is published
-        for step in range(self.world):
-            r = (self.rank - step) % self.world         # start with the local copy, then walk the ring
-            landing[r * self.n:(r + 1) * self.n].copy_(self.peers[r], non_blocking=True)
+        self.fork.record(cur)
+        for i, st in enumerate(self.side):              # peers spread over the pull streams, ring order from the neighbour
+            st.wait_event(self.fork)
+            with torch.cuda.stream(st):
+                for step in range(1 + i, self.world, len(self.side)):
+                    r = (self.rank - step) % self.world
+                    landing[r * self.n:(r + 1) * self.n].copy_(self.peers[r], non_blocking=True)
+                self.join[i].record(st)
+        for ev in self.join:
+            cur.wait_event(ev)
         self.hdl.barrier(channel=0)                     # every rank has pulled: staging buffers may be rewritten
 
 
