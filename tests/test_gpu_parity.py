@@ -181,6 +181,38 @@ def test_me_batch_matches_oracle(env, dist, sub_shift, prec):
         assert np.array_equal(exp, got[sl]), (dict(zip(b.dtype.names, b.tolist())), exp, got[sl])
 
 
+def test_me_batch_candidate_counts_of_the_search_loops(env):
+    """Candidate-set sizes the reference's loops produce: 1-2 (AMVP template), 9 (half/quarter
+    refinement), 16 (diamond round), 25 (DMVR), 64, 81 (bi-pred full search) -- mixed in ONE batch with ragged counts per
+    block, small and large blocks, so that work items of different blocks and candidates share warps and the k_map item
+    walk crosses block / chunk boundaries at every offset."""
+    o, g, planes, ref, cur = env
+    rng = np.random.default_rng(4242)
+    g.set_org(cur[0])
+    counts = [1, 2, 9, 16, 25, 64, 81, 3, 7, 33]
+    sizes = [(8, 4), (4, 8), (8, 8), (16, 16), (32, 32), (64, 64), (128, 128), (16, 8), (64, 16), (4, 128)]
+    models = [1, 6, 10, 2, 4, 5, 3, 9, 1, 6]
+    n = len(sizes)
+    blocks = np.zeros(n, dtype=mm.api.BLOCK_DTYPE)
+    first = 0
+    for i, (w, h) in enumerate(sizes):
+        x, y = rand_block(rng, w, h)
+        blocks[i] = (x, y, w, h, models[i], 0, 0, first, counts[i], x, y, 0)
+        first += counts[i]
+    mvs = np.zeros(first, dtype=mm.api.MV_DTYPE)
+    mvs["hor"] = rng.integers(-160, 160, size=first)
+    mvs["ver"] = rng.integers(-120, 120, size=first)
+    for dist in (ol.DIST_SAD, ol.DIST_HAD):
+        got = g.me_batch(blocks, mvs, mv_prec_shift=2, dist=dist)
+        for b in blocks:
+            sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+            org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+            m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+            exp = o.me_block(planes[0], org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                             mv_prec_shift=2, dist=dist, had_mode=ol.HAD_SIMD)
+            assert np.array_equal(exp, got[sl]), (dict(zip(b.dtype.names, b.tolist())), dist)
+
+
 def test_me_batch_scalar_had_mode(oracle_2k):
     """--SIMD=SCALAR hosts use (int)(sad / sqrt(16*8) * 2); selectable per context."""
     o = oracle_2k
