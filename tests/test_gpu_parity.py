@@ -388,6 +388,42 @@ def test_tma_boxes_equal_gather_path(env):
         assert np.array_equal(exp, res[(1, mm.DIST_HAD)][sl]), b
 
 
+def test_reregistered_device_plane_gets_fresh_tma_descriptor(env):
+    """A slot re-registered with another device buffer (what an encoder does for every new reference picture) must be
+    read through its NEW descriptor: evaluate picture A, re-point the slot at picture B in other memory, evaluate again
+    and compare with the gather path on B; then back to A."""
+    import os
+    import torch
+    o, g, planes, ref, cur = env
+    pics = []
+    for seed in (71, 72):
+        pl = wl.pad_frame(wl.synth_frame(W, H, seed=seed), 288, 1)
+        dev = [torch.from_numpy(p.buf.copy()).cuda() for p in pl]
+        pics.append((pl, dev))
+    def register(slot, k, tma):
+        pl, dev = pics[k]
+        if not tma:
+            os.environ["MMGPU_NO_TMA"] = "1"
+        try:
+            g.set_ref_device(slot, k, [d.data_ptr() + 2 * (p.my * p.stride + p.mx) for d, p in zip(dev, pl)],
+                             [p.stride for p in pl], keep=dev)
+        finally:
+            os.environ.pop("MMGPU_NO_TMA", None)
+    g.set_org(cur[0])
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=62, cands_per_block=2, mv_range=32, models=(mm.MPA_LR, mm.ROT, mm.GED_CAMPOSE))
+    b1 = blocks.copy(); b1["ref_slot"] = 1
+    b2 = blocks.copy(); b2["ref_slot"] = 2
+    res = []
+    for k in (0, 1, 0):
+        register(1, k, True)
+        register(2, k, False)
+        a = g.me_batch(b1, mvs, mv_prec_shift=prec, dist=mm.DIST_HAD).copy()
+        b = g.me_batch(b2, mvs, mv_prec_shift=prec, dist=mm.DIST_HAD).copy()
+        assert np.array_equal(a, b), k
+        res.append(a)
+    assert np.array_equal(res[0], res[2]) and not np.array_equal(res[0], res[1])
+
+
 def test_cpp_host_adapter_matches_oracle():
     """The C++ adapter (reference-shaped argument lists) end to end: MC of a GED_CAMPOSE block and
     xPatternRefinementProjected's 9-point HAD refinement equal the oracle."""
