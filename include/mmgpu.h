@@ -87,6 +87,11 @@ int mmgpu_set_ref(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane0
 int mmgpu_set_ref_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3]);
 /* un-padded planes in host memory: upload + Picture::extendPicBorder on the device. */
 int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3], const int32_t stride[3]);
+/* same with the horizontally wrapped border of Picture::extendWrapBorder (Picture.cpp:1049-1092), i.e. the
+ * PIC_RECON_WRAP buffer getRecoBuf(compID, wrapRef = true) returns when the PPS enables wrap-around (360 ERP):
+ * wrap_offset = pps->getWrapAroundOffset() in luma samples (the ERP picture width for a full wrap). */
+int mmgpu_set_ref_unpadded_wrap(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3], const int32_t stride[3],
+                                int wrap_offset);
 
 /* ---- geodesic epipole: GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46) ------------ */
 void mmgpu_rodrigues(const float epipole[3], float R[9]);          /* host helper, row-major R */

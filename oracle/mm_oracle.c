@@ -782,6 +782,33 @@ void orc_extend_border(int16_t* p, int stride, int w, int h, int mx, int my)
   for (int y = 0; y < my; ++y) memcpy(first - (long)(y + 1) * stride, first, sizeof(int16_t) * (w + 2 * mx));
 }
 
+void orc_extend_wrap_border(int16_t* p, int stride, int w, int h, int mx, int my, int xoffset)
+{
+  /* Picture::extendWrapBorder, Picture.cpp:1049-1092 (loop order as in the reference) */
+  int16_t* pi = p;
+  for (int y = 0; y < h; ++y)
+  {
+    for (int x = 0; x < mx; ++x)
+    {
+      if (x < xoffset)
+      {
+        pi[-x - 1] = pi[-x - 1 + xoffset];
+        pi[w + x] = pi[w + x - xoffset];
+      }
+      else
+      {
+        pi[-x - 1] = pi[0];
+        pi[w + x] = pi[w - 1];
+      }
+    }
+    pi += stride;
+  }
+  pi -= (stride + mx);
+  for (int y = 0; y < my; ++y) memcpy(pi + (long)(y + 1) * stride, pi, sizeof(int16_t) * (w + (mx << 1)));
+  pi -= (long)(h - 1) * stride;
+  for (int y = 0; y < my; ++y) memcpy(pi - (long)(y + 1) * stride, pi, sizeof(int16_t) * (w + (mx << 1)));
+}
+
 /* ---------------------------------------------------------------------------------------------
  * DMVR (projected): InterPrediction.cpp:2442-2635, 2147-2155, 1958-2048, 2157-2175
  * ------------------------------------------------------------------------------------------- */

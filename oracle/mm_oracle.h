@@ -126,6 +126,9 @@ uint64_t orc_dmvr_cost(const int16_t* a, int as, const int16_t* b, int bs, int w
 
 /* Picture::extendPicBorder (Picture.cpp:988-1048): replicate a w x h plane into its margins in place. */
 void orc_extend_border(int16_t* plane00, int stride, int w, int h, int margin_x, int margin_y);
+/* Picture::extendWrapBorder (Picture.cpp:1049-1092): margins continue the picture from the opposite side for the first
+ * xoffset columns (component units), replicate beyond; in place. */
+void orc_extend_wrap_border(int16_t* plane00, int stride, int w, int h, int margin_x, int margin_y, int xoffset);
 
 #ifdef __cplusplus
 }

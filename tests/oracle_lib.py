@@ -58,6 +58,7 @@ def lib():
             [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
         L.orc_add_avg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 5
         L.orc_extend_border.argtypes = [C.c_void_p] + [C.c_int] * 5
+        L.orc_extend_wrap_border.argtypes = [C.c_void_p] + [C.c_int] * 6
         L.orc_dmvr_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 9 + \
             [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_dmvr_cost.restype = C.c_uint64
@@ -85,6 +86,9 @@ class PaddedPlane:
 
     def extend(self):
         lib().orc_extend_border(self.origin, self.stride, self.w, self.h, self.mx, self.my)
+
+    def extend_wrap(self, xoffset):
+        lib().orc_extend_wrap_border(self.origin, self.stride, self.w, self.h, self.mx, self.my, int(xoffset))
 
 
 class Oracle:

@@ -253,6 +253,32 @@ def test_unpadded_upload_extends_border_like_reference(env):
             assert np.array_equal(a, b)
 
 
+def test_unpadded_wrap_upload_equals_extend_wrap_border(env):
+    """Picture::extendWrapBorder on the device (PIC_RECON_WRAP of a 360 ERP sequence): MC through a device-wrapped slot ==
+    oracle MC on a plane padded by the oracle's restatement, for blocks whose windows cross the left / right picture
+    border (where the two paddings differ) and for one in the middle; full and partial wrap offsets."""
+    o, g, planes, ref, cur = env
+    inner = [p.inner.copy() for p in ref]
+    rng = np.random.default_rng(19)
+    for xoff in (W, 96):
+        g.set_ref_unpadded_wrap(1, 0, inner, xoff)
+        wrapped = []
+        for c, p in enumerate(ref):
+            q = ol.PaddedPlane(p.w, p.h, p.mx, p.my)
+            q.inner[:] = inner[c]
+            q.extend_wrap(xoff >> (1 if c else 0))
+            wrapped.append(q)
+        differs = False
+        for (x, y) in [(0, 0), (W - 64, 0), (0, H - 64), (W - 64, H - 64), (1024, 512), (0, 384), (W - 64, 640)]:
+            for mv in ((int(rng.integers(-1800, 1800)), int(rng.integers(-600, 600))), (-2000, 33), (1999, -70)):
+                for comp, pos, size in ((0, (x, y), (64, 64)), (1, (x // 2, y // 2), (32, 32)), (2, (x // 2, y // 2), (32, 32))):
+                    exp = o.mc_block_classic(wrapped[comp], comp, 1, pos, size, mv, False)
+                    got = g.mc(1, comp, 1, pos, size, mv, 0)
+                    assert np.array_equal(exp, got), (xoff, x, y, mv, comp)
+                    differs |= not np.array_equal(got, g.mc(0, comp, 1, pos, size, mv, 0))
+        assert differs      # the wrapped margins are not the replicated ones
+
+
 def test_add_avg(env):
     o, g, *_ = env
     rng = np.random.default_rng(3)

@@ -205,6 +205,31 @@ def test_golden_distortion(oracle_2k):
         assert o.me_block(pl, org, None, (int(x), int(y)), (int(w), int(h)), int(model), m, dist=ol.DIST_HAD)[0] == had
 
 
+def test_extend_wrap_border_closed_form():
+    """Picture::extendWrapBorder restated with the reference's loop order == its closed form: the first xoffset margin
+    columns continue the row from the opposite side, the others replicate; top/bottom repeat the extended rows."""
+    rng = np.random.default_rng(5)
+    w, h, mx, my = 40, 24, 16, 8
+    p = rng.integers(0, 1024, size=(h, w)).astype(np.int16)
+    for xoff in (0, 5, 16, 40):
+        pl = ol.PaddedPlane(w, h, mx, my)
+        pl.inner[:] = p
+        pl.extend_wrap(xoff)
+        cols = []
+        for X in range(-mx, w + mx):
+            if X < 0:
+                cols.append(X + xoff if (-1 - X) < xoff else 0)
+            elif X >= w:
+                cols.append(X - xoff if (X - w) < xoff else w - 1)
+            else:
+                cols.append(X)
+        rows = np.clip(np.arange(-my, h + my), 0, h - 1)
+        assert np.array_equal(pl.buf[:, :w + 2 * mx], p[rows][:, cols]), xoff
+    pl = ol.PaddedPlane(w, h, mx, my); pl.inner[:] = p; pl.extend_wrap(0)
+    q = ol.PaddedPlane(w, h, mx, my); q.inner[:] = p; q.extend()
+    assert np.array_equal(pl.buf, q.buf)
+
+
 def test_extend_border_equals_edge_padding():
     from vvc_extension_mm_b200 import workload as wl
     rng = np.random.default_rng(4)

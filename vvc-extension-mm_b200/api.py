@@ -20,7 +20,7 @@ EXPORTS = [
     "mmgpu_kernel_timing_enable", "mmgpu_kernel_timing_read",
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
-    "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
+    "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
     "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs",
 ]
 
@@ -82,6 +82,7 @@ def load_library():
     L.mmgpu_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64)]
     for f in (L.mmgpu_set_ref, L.mmgpu_set_ref_device, L.mmgpu_set_ref_unpadded):
         f.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.mmgpu_set_ref_unpadded_wrap.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32), i32]
     L.mmgpu_rodrigues.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mmgpu_fixed_to_float.restype = C.c_float
     L.mmgpu_fixed_to_float.argtypes = [C.c_int32, C.c_int32]
@@ -236,6 +237,11 @@ class MmGpu:
         """planes: list of 2-D int16 numpy arrays without margins; padding happens on the device."""
         p, s = self._planes([a.ctypes.data for a in planes], [a.strides[0] // 2 for a in planes])
         self._chk(self.L.mmgpu_set_ref_unpadded(self.h, slot, poc, p, s))
+
+    def set_ref_unpadded_wrap(self, slot, poc, planes, wrap_offset):
+        """like set_ref_unpadded with Picture::extendWrapBorder's horizontally wrapped margins (wrap_offset in luma samples)."""
+        p, s = self._planes([a.ctypes.data for a in planes], [a.strides[0] // 2 for a in planes])
+        self._chk(self.L.mmgpu_set_ref_unpadded_wrap(self.h, slot, poc, p, s, int(wrap_offset)))
 
     def set_rotation(self, rot_slot, R):
         r = (C.c_float * 9)(*[float(v) for v in R])

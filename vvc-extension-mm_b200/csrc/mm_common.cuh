@@ -184,7 +184,7 @@ void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy
 void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model, int2* pos);
 // FIR + distortion (or prediction write-out) of items [first, first+count)
 void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, const int2* pos);
-void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my);
+void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my, int xoff);
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi);
 void mmk_mc_generic(cudaStream_t s, const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h,

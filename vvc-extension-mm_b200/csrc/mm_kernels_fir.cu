@@ -190,15 +190,22 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
 }
 
 // -------------------------------------------------------------------------------------------------
-// Picture::extendPicBorder on the device (Picture.cpp:1008-1046): one thread per margin sample
+// Picture::extendPicBorder (Picture.cpp:1008-1046) and Picture::extendWrapBorder (:1049-1092) on the device: one thread
+// per margin sample.  xoff = 0: replicate the border sample; xoff > 0 (PPS wrap-around offset in units of the
+// component): the first xoff margin columns on either side continue the picture from the opposite side, the rest
+// replicate; rows above / below repeat the (horizontally extended) first / last row in both variants.
 // -------------------------------------------------------------------------------------------------
-__global__ void k_extend_border(int16_t* plane00, int stride, int w, int h, int mx, int my)
+__global__ void k_extend_border(int16_t* plane00, int stride, int w, int h, int mx, int my, int xoff)
 {
   const int X = blockIdx.x * blockDim.x + threadIdx.x - mx;
   const int Y = blockIdx.y * blockDim.y + threadIdx.y - my;
   if (X >= w + mx || Y >= h + my) return;
   if (X >= 0 && X < w && Y >= 0 && Y < h) return;
-  const int sx = min(max(X, 0), w - 1), sy = min(max(Y, 0), h - 1);
+  int sx;
+  if (X < 0) sx = (-1 - X < xoff) ? X + xoff : 0;
+  else if (X >= w) sx = (X - w < xoff) ? X - xoff : w - 1;
+  else sx = X;
+  const int sy = min(max(Y, 0), h - 1);
   plane00[(long)Y * stride + X] = plane00[(long)sy * stride + sx];
 }
 
@@ -218,10 +225,10 @@ void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, 
   if (mode == MM_MODE_DIST) k_fir<MM_MODE_DIST><<<grid, 32 * MM_FIR_WARPS, 0, s>>>(P, first, count, pos);
   else k_fir<MM_MODE_PRED><<<grid, 32 * MM_FIR_WARPS, 0, s>>>(P, first, count, pos);
 }
-void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my)
+void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my, int xoff)
 {
   dim3 tb(32, 8), gr((w + 2 * mx + 31) / 32, (h + 2 * my + 7) / 8);
-  k_extend_border<<<gr, tb, 0, s>>>(plane00, stride, w, h, mx, my);
+  k_extend_border<<<gr, tb, 0, s>>>(plane00, stride, w, h, mx, my, xoff);
 }
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi)

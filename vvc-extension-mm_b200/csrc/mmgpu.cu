@@ -542,11 +542,12 @@ extern "C" int mmgpu_set_ref_device(mmgpu_ctx* ctx, int slot, int poc, const int
   return publishRef(ctx, slot);
 }
 
-extern "C" int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3],
-                                      const int32_t stride[3])
+static int setRefUnpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3], const int32_t stride[3],
+                          int wrap_offset)
 {
   if (!ctx || !plane || !stride) return MMGPU_ERR_ARG;
   if (slot < 0 || slot >= ctx->cfg.max_refs) return fail(ctx, MMGPU_ERR_ARG, "ref slot out of range");
+  if (wrap_offset < 0 || wrap_offset > ctx->cfg.pic_w) return fail(ctx, MMGPU_ERR_ARG, "wrap_offset must be 0..pic_w");
   cudaSetDevice(ctx->cfg.device);
   MmRef r;
   memset(&r, 0, sizeof(r));
@@ -561,7 +562,7 @@ extern "C" int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const i
     if (rc) return rc;
     CU(cudaMemcpy2DAsync(d00, sizeof(int16_t) * pitch, plane[c], sizeof(int16_t) * stride[c], sizeof(int16_t) * w, h,
                          cudaMemcpyHostToDevice, ctx->stream));
-    mmk_extend_border(ctx->stream, d00, pitch, w, h, mx, my);
+    mmk_extend_border(ctx->stream, d00, pitch, w, h, mx, my, wrap_offset >> scaleX(c, ctx->cfg.chroma_fmt));
     ctx->launches++;
     r.plane00[c] = d00;
     r.stride[c] = pitch;
@@ -569,6 +570,18 @@ extern "C" int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const i
   CU(cudaGetLastError());
   ctx->hRefs[slot] = r;
   return publishRef(ctx, slot);
+}
+
+extern "C" int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3],
+                                      const int32_t stride[3])
+{
+  return setRefUnpadded(ctx, slot, poc, plane, stride, 0);
+}
+
+extern "C" int mmgpu_set_ref_unpadded_wrap(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3],
+                                           const int32_t stride[3], int wrap_offset)
+{
+  return setRefUnpadded(ctx, slot, poc, plane, stride, wrap_offset);
 }
 
 extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9])
