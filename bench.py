@@ -31,6 +31,10 @@ CANDS = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fir<DIST> launch of this workload, from the committed
 # `ncu --set full` capture (profiles/ncu_k_map_k_fir_r01e_summary.csv: 27.660544 MB read + 0.768 KB written).
 NCU_TRAFFIC_BYTES = 27661312
+# smsp__inst_executed.sum of one k_fir<DIST> / k_map launch of this workload (same capture): what the kernels are really
+# bound by is instruction issue (1 warp-instruction per clock per SM sub-partition), so the bench line also reports the
+# fraction of that ceiling the measured kernel times correspond to.
+NCU_INST = {"k_fir": 71340554, "k_map": 47667990}
 POOL = 32            # synthetic frames resident per GPU (references cycle through them: 270 MB > L2)
 MV_RANGE = 64
 EPIPOLE = (1.0, 0.0, 0.0)
@@ -427,6 +431,12 @@ def main():
         kmap_avg_ms = kmap_ms / max(1, k_n)
         path_ms = k_avg_ms + kmap_avg_ms
         path_achieved = (alg_bytes_rank / 1e9) / (path_ms / 1000.0) if path_ms > 0 else 0.0
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965)
+        n_smsp = 4 * torch.cuda.get_device_properties(local).multi_processor_count
+        issue = {"unit": "warp-instructions/clk/SMSP", "peak": 1.0,
+                 "k_fir": NCU_INST["k_fir"] / (k_avg_ms * 1e-3 * sm_hz * n_smsp) if k_avg_ms > 0 else None,
+                 "k_map": NCU_INST["k_map"] / (kmap_avg_ms * 1e-3 * sm_hz * n_smsp) if kmap_avg_ms > 0 else None,
+                 "note": "instruction counts from the committed ncu capture of one launch (profiles/), times measured live"}
         cpu = None
         if not args.no_cpu_baseline:
             v, dt, nblk, done = cpu_oracle_throughput(1, args.cpu_budget)
@@ -449,7 +459,7 @@ def main():
                          "traffic": NCU_TRAFFIC_BYTES, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
                          "path": {"kernels": "k_map + k_fir<DIST>", "k_map_ms": kmap_avg_ms, "ms": path_ms,
                                   "achieved": path_achieved, "frac": path_achieved / peak},
-                         "algorithmic_bytes_per_launch": alg_bytes_rank,
+                         "algorithmic_bytes_per_launch": alg_bytes_rank, "issue": issue if N == 1 else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "luma sample-candidates/s", "h2d_bytes_per_step": h2d,
