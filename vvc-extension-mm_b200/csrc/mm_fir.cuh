@@ -106,6 +106,11 @@ template <bool BI>
 __device__ __forceinline__ void mm_fir_vpass(const MmFir& f, const int (*P)[4], const MmTaps& tv, bool copy, int lo, int hi,
                                              int* pred)
 {
+  // rndRes = true: the reference stores (sum + offset) >> shift into a Pel (int16) and then clips (except in the pure copy
+  // case, filterCopy<true,true>).  The int16 store never wraps here: the first-pass rows are int16, sum |c| <= 112, so
+  // |(sum + off2) >> shift2| <= (32768 * 112 + 524800) >> 10 < 2^13 (and the copy case returns the sample itself); the
+  // copy case is folded into per-lane clip bounds.
+  const int clo = copy ? -32768 : lo, chi = copy ? 32767 : hi;
 #pragma unroll
   for (int c = 0; c < 4; ++c)
   {
@@ -120,12 +125,10 @@ __device__ __forceinline__ void mm_fir_vpass(const MmFir& f, const int (*P)[4], 
     }
     else
     {
-      o0 = (int)(int16_t)(o0 >> f.shift2); o1 = (int)(int16_t)(o1 >> f.shift2);
-      o2 = (int)(int16_t)(o2 >> f.shift2); o3 = (int)(int16_t)(o3 >> f.shift2);
-      pred[0 * 4 + c] = copy ? o0 : mm_clip(o0, lo, hi);
-      pred[1 * 4 + c] = copy ? o1 : mm_clip(o1, lo, hi);
-      pred[2 * 4 + c] = copy ? o2 : mm_clip(o2, lo, hi);
-      pred[3 * 4 + c] = copy ? o3 : mm_clip(o3, lo, hi);
+      pred[0 * 4 + c] = mm_clip(o0 >> f.shift2, clo, chi);
+      pred[1 * 4 + c] = mm_clip(o1 >> f.shift2, clo, chi);
+      pred[2 * 4 + c] = mm_clip(o2 >> f.shift2, clo, chi);
+      pred[3 * 4 + c] = mm_clip(o3 >> f.shift2, clo, chi);
     }
   }
 }
