@@ -44,8 +44,11 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   const int xP = fp.x >> 4, yP = fp.y >> 4;
   const int ax = (xP - 3) & ~3, ay = yP - 3;
   int boxType = -1, x0 = 0, y0 = 0;
+  // Full-pel warp (classic candidates at integer MVs: the bulk of an integer TZ search): both passes are
+  // filterCopy<true,true> (InterpolationFilter.cpp:392-470), the prediction is the reference block itself.
+  const bool fullPel = __all_sync(0xffffffffu, oob || ((fp.x | fp.y) & 15) == 0);
 #ifndef MM_NO_TMA
-  if (n >= 32 && ref.tma)   // warp-uniform
+  if (!fullPel && n >= 32 && ref.tma)   // warp-uniform
   {
     const int BIG = 1 << 28;
     x0 = __reduce_min_sync(0xffffffffu, oob ? BIG : ax) & ~7;   // TMA: the box must start on a 16-byte boundary
@@ -86,6 +89,14 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   {
 #pragma unroll
     for (int i = 0; i < 16; ++i) pred[i] = 0;
+  }
+  else if (fullPel)
+  {
+    const int16_t* p = ref.plane00[0] + (long)yP * ref.stride[0] + xP;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pred[r * 4 + c] = __ldg(p + (long)r * ref.stride[0] + c);
   }
 #ifndef MM_NO_TMA
   else if (boxType >= 0)
