@@ -176,8 +176,9 @@ MM_HD void mm_erp_from_sphere_arr(const MmGeom& g, float x, float y, float z, fl
   float r, th, ph;
   mm_arr_cart_to_sph(x, y, z, &r, &th, &ph);
   if (ph > 0.0f) ph = MM_FSUB(ph, MM_2PI_F);
-  *X = MM_FSUB(MM_FMUL(mm_negf(MM_FDIV(ph, MM_2PI_F)), g.picW), 0.0f);
-  *Y = MM_FSUB(MM_FMUL(MM_FDIV(th, MM_PI_F), g.picH), 0.0f);
+  // (the reference subtracts a zero sample offset here: v - 0.0f == v for every v, omitted)
+  *X = MM_FMUL(mm_negf(MM_FDIV(ph, MM_2PI_F)), g.picW);
+  *Y = MM_FMUL(MM_FDIV(th, MM_PI_F), g.picH);
 }
 
 // ---- Projection.cpp: perspective (motion plane) ----------------------------------------------------
@@ -194,7 +195,7 @@ MM_HD void mm_pers_from_sphere_arr(const MmGeom& g, float sx, float sy, float sz
 }
 MM_HD void mm_pers_to_sphere_arr(const MmGeom& g, float X, float Y, bool vip, bool pk, float* o)
 {
-  const float x = MM_FSUB(X, 0.0f), y = MM_FSUB(Y, 0.0f);
+  const float x = X, y = Y;  // X - 0.0f, Y - 0.0f in the reference: identities
   const float polarR = MM_FSQRT(MM_FADD(MM_FMUL(x, x), MM_FMUL(y, y)));
   const float polarPhi = mm_atan2f(y, x);
   float th = mm_atanf(MM_FDIV(polarR, g.focal));
