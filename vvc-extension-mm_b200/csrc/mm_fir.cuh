@@ -133,16 +133,11 @@ __device__ __forceinline__ void mm_fir_vpass(const MmFir& f, const int (*P)[4], 
   }
 }
 
-// Core.  SMEM = false: `base` points at the 32-bit word holding sample (xPos-3)&~1 of row yPos-3 in global memory (read-only
-// path, word stride `wstride`).  SMEM = true: the window is read from a staged box in shared memory whose row R starts
-// at word R*wstride + (R>>2) (mm_stage_row: the skew spreads lanes that sit 4 rows apart over the banks); `base` points
-// at the window's first word inside row 0 of the box and `row0` is the box row of the window's first row.
-// sh = 16 if xPos-3 is odd.
-__device__ __forceinline__ int mm_stage_row(int R, int pitchW) { return R * pitchW + (R >> 2); }
-
-template <bool BI, bool SMEM>
+// 4-byte gather variant (k_dmvr): `base` points at the 32-bit word holding sample (xPos-3)&~1 of row yPos-3 (read-only
+// path, word stride `wstride`); sh = 16 if xPos-3 is odd (funnel-shift realignment).
+template <bool BI>
 __device__ __forceinline__ void mm_fir_luma4x4_core(const MmFir& f, const MmTaps* taps, const uint32_t* base, int wstride,
-                                                    int row0, int sh, int xFrac, int yFrac, int lo, int hi, int* pred)
+                                                    int sh, int xFrac, int yFrac, int lo, int hi, int* pred)
 {
   const MmTaps th = taps[xFrac];
   const MmTaps tv = taps[yFrac];
@@ -151,10 +146,9 @@ __device__ __forceinline__ void mm_fir_luma4x4_core(const MmFir& f, const MmTaps
 #pragma unroll
   for (int r = 0; r < 11; ++r)
   {
-    const uint32_t* rowp = SMEM ? (base + mm_stage_row(row0 + r, wstride)) : (base + (long)r * wstride);
-    uint32_t w0, w1, w2, w3, w4, w5;
-    if (SMEM) { w0 = rowp[0]; w1 = rowp[1]; w2 = rowp[2]; w3 = rowp[3]; w4 = rowp[4]; w5 = rowp[5]; }
-    else { w0 = __ldg(rowp + 0); w1 = __ldg(rowp + 1); w2 = __ldg(rowp + 2); w3 = __ldg(rowp + 3); w4 = __ldg(rowp + 4); w5 = __ldg(rowp + 5); }
+    const uint32_t* rowp = base + (long)r * wstride;
+    uint32_t w0 = __ldg(rowp + 0), w1 = __ldg(rowp + 1), w2 = __ldg(rowp + 2), w3 = __ldg(rowp + 3), w4 = __ldg(rowp + 4),
+             w5 = __ldg(rowp + 5);
     w0 = __funnelshift_r(w0, w1, sh);
     w1 = __funnelshift_r(w1, w2, sh);
     w2 = __funnelshift_r(w2, w3, sh);
@@ -190,7 +184,7 @@ __device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* tap
 {
   const int a = xPos - 3;
   const uint32_t* base = reinterpret_cast<const uint32_t*>(ref + (long)(yPos - 3) * stride + (a & ~1));
-  mm_fir_luma4x4_core<BI, false>(f, taps, base, stride >> 1, 0, (a & 1) << 4, xFrac, yFrac, lo, hi, pred);
+  mm_fir_luma4x4_core<BI>(f, taps, base, stride >> 1, (a & 1) << 4, xFrac, yFrac, lo, hi, pred);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -210,19 +204,14 @@ __device__ __forceinline__ int mm_fir6(int v0, int v1, int v2, int v3, int v4, i
          __dp2a_lo(v4, (int)c2, __dp2a_hi(v5, (int)c2, init))))));
 }
 
-// htaps: the coefficient table; `base` = 8-byte word holding sample (xPos-3)&~3 of row yPos-3, `qstride` = row stride in
+// htaps: the coefficient table in global memory (3 KB, L1 resident); `base` = 8-byte word holding sample (xPos-3)&~3 of row yPos-3, `qstride` = row stride in
 // 8-byte words.  SMEM = false: global memory (read-only path); SMEM = true: a TMA-filled box in shared memory.
 template <bool BI, bool SMEM>
 __device__ __forceinline__ void mm_fir_luma4x4_wide_core(const MmFir& f, const uint32_t* htaps, const uint2* base, int qstride,
                                                          int a, int xFrac, int yFrac, int lo, int hi, int* pred)
 {
   const uint4* e = reinterpret_cast<const uint4*>(htaps + (((a & 3) * 16 + xFrac) * 12));
-#ifdef MM_HTAPS_SMEM
-#define MM_TLD(p) (*(p))
-#else
-#define MM_TLD(p) __ldg(p)
-#endif
-  const uint4 e0 = MM_TLD(e), e1 = MM_TLD(e + 1), e2 = MM_TLD(e + 2);   // c[j][m] = word j*3+m: e0 = c00 c01 c02 c10, e1 = c11 c12 c20 c21, e2 = c22 c30 c31 c32
+  const uint4 e0 = __ldg(e), e1 = __ldg(e + 1), e2 = __ldg(e + 2);   // c[j][m] = word j*3+m: e0 = c00 c01 c02 c10, e1 = c11 c12 c20 c21, e2 = c22 c30 c31 c32
   int P[6][4];  // vertical pairs of first-pass rows, per column
   int hprev[4];
 #pragma unroll
@@ -260,8 +249,8 @@ __device__ __forceinline__ void mm_fir_luma4x4_wide_core(const MmFir& f, const u
   }
   const uint32_t* ev = htaps + yFrac * 12;   // entry o = 0: words 0,1 = a0,a1; 3,4,5 = b0,b1,b2
   MmTaps tv;
-  tv.a0 = (int)MM_TLD(ev); tv.a1 = (int)MM_TLD(ev + 1); tv.b0 = (int)MM_TLD(ev + 3); tv.b1 = (int)MM_TLD(ev + 4);
-  tv.b2 = (int)MM_TLD(ev + 5);
+  tv.a0 = (int)__ldg(ev); tv.a1 = (int)__ldg(ev + 1); tv.b0 = (int)__ldg(ev + 3); tv.b1 = (int)__ldg(ev + 4);
+  tv.b2 = (int)__ldg(ev + 5);
   mm_fir_vpass<BI>(f, P, tv, (xFrac | yFrac) == 0, lo, hi, pred);
 }
 
@@ -313,44 +302,10 @@ __device__ __forceinline__ void mm_tma_load_2d(void* dst, const void* tmap, int 
 // -------------------------------------------------------------------------------------------------
 // Distortion pieces
 // -------------------------------------------------------------------------------------------------
-// 4x4 2-D Hadamard in place (d[r*4+c]); coefficient order/sign is irrelevant for the sum of magnitudes,
-// d[0] ends up as the DC term (sum of all differences).
-__device__ __forceinline__ void mm_had4x4(int* d)
-{
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-  {
-    const int a = d[r * 4 + 0] + d[r * 4 + 1], b = d[r * 4 + 0] - d[r * 4 + 1];
-    const int c = d[r * 4 + 2] + d[r * 4 + 3], e = d[r * 4 + 2] - d[r * 4 + 3];
-    d[r * 4 + 0] = a + c; d[r * 4 + 1] = b + e; d[r * 4 + 2] = a - c; d[r * 4 + 3] = b - e;
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-  {
-    const int a = d[0 * 4 + c] + d[1 * 4 + c], b = d[0 * 4 + c] - d[1 * 4 + c];
-    const int g = d[2 * 4 + c] + d[3 * 4 + c], e = d[2 * 4 + c] - d[3 * 4 + c];
-    d[0 * 4 + c] = a + g; d[1 * 4 + c] = b + e; d[2 * 4 + c] = a - g; d[3 * 4 + c] = b - e;
-  }
-}
-// one cross-lane butterfly stage of the tile transform: lanes `lane` and `lane^bit` hold the 16
-// coefficients of neighbouring sub-blocks; afterwards the lower lane holds sums/differences of
-// elements 0..7, the upper lane those of elements 8..15 (8 shuffles instead of 16).
-__device__ __forceinline__ void mm_had_xlane(int* d, int bit, bool upper)
-{
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-  {
-    const int send = upper ? d[i] : d[i + 8];
-    const int keep = upper ? d[i + 8] : d[i];
-    const int recv = __shfl_xor_sync(0xffffffffu, send, bit);
-    d[i] = keep + recv;
-    d[i + 8] = keep - recv;
-  }
-}
-
-// FP32 twins of the two transforms above, used by k_fir: every value is an integer below 2^24 (|coefficient| <= 128 * 1023,
-// sum of magnitudes of a tile <= 128 * sqrt(128) * 1023), so float add/sub/fma are exact, and they issue on the FP32 pipes
-// that the integer FIR leaves idle instead of the integer ALU / IMAD pipes that it saturates.
+// 4x4 2-D Hadamard in place (d[r*4+c]) and the cross-lane butterflies of larger tiles, in FP32: every value is an integer
+// below 2^24 (|coefficient| <= 128 * 1023, sum of magnitudes of a tile <= 128 * sqrt(128) * 1023), so float add/sub/fma are
+// exact, and they issue on the FP32 pipes that the integer FIR leaves idle instead of the integer ALU / IMAD pipes that
+// it loads.  Coefficient order/sign is irrelevant for the sum of magnitudes; d[0] ends up as the DC term.
 __device__ __forceinline__ void mm_had4x4_f(float* d)
 {
 #pragma unroll

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   __shared__ __align__(128) unsigned char s_box[MM_FIR_WARPS][MM_TMA_BOX_BYTES];
   __shared__ __align__(8) unsigned long long s_bar[MM_FIR_WARPS];
 #endif
-  const uint32_t* s_htaps = P.hTaps;   // 3 KB coefficient table, L1 resident: no per-CTA prologue, no barrier
+  const uint32_t* htaps = P.hTaps;   // 3 KB coefficient table, L1 resident: no per-CTA prologue, no barrier
   const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w0 >= count) return;
@@ -102,12 +102,12 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   else if (boxType >= 0)
   {
     const uint2* base = reinterpret_cast<const uint2*>(s_box[threadIdx.x >> 5]) + (ay - y0) * pitchQ + ((ax - x0) >> 2);
-    mm_fir_luma4x4_wide_core<false, true>(P.fir, s_htaps, base, pitchQ, xP - 3, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax, pred);
+    mm_fir_luma4x4_wide_core<false, true>(P.fir, htaps, base, pitchQ, xP - 3, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax, pred);
   }
 #endif
   else
   {
-    mm_fir_luma4x4_wide<false>(P.fir, s_htaps, ref.plane00[0], ref.stride[0], xP, yP, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax,
+    mm_fir_luma4x4_wide<false>(P.fir, htaps, ref.plane00[0], ref.stride[0], xP, yP, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax,
                                pred);
   }
 
