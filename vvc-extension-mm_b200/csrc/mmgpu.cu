@@ -48,7 +48,7 @@ struct MmSlot  // one in-flight mmgpu_me_batch_submit: its own device buffers, s
   size_t capDist;
   int16_t* dOrg;
   size_t capOrg;
-  cudaEvent_t copied, done;
+  cudaEvent_t copied, computed, done;
   bool init, pending;
 };
 
@@ -98,6 +98,7 @@ struct mmgpu_ctx
   bool mapPerModel;
   MmStage stage;            // staging of the synchronous entry points
   cudaStream_t copyStream;  // host->device copies of submitted batches
+  cudaStream_t readStream;  // device->host read-back of their distortions (so it does not delay the next batch's kernels)
   MmSlot slots[MM_MAX_INFLIGHT];
   // optional CUDA-event timing of the batch kernels: events t0 | k_map | t1 | k_fir | t2 per launchMe
   bool timing;
@@ -258,6 +259,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
 
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->readStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&ctx->stage.freeEv, cudaEventDisableTiming));
   ctx->hRefs.assign(cfg->max_refs, MmRef());
   ctx->ownedPlanes.assign((size_t)cfg->max_refs * 3, nullptr);
@@ -345,6 +347,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   if (ctx->stage.h) cudaFreeHost(ctx->stage.h);
   cudaEventDestroy(ctx->stage.freeEv);
   cudaStreamSynchronize(ctx->copyStream);
+  cudaStreamSynchronize(ctx->readStream);
   for (int i = 0; i < MM_MAX_INFLIGHT; ++i)
   {
     MmSlot& sl = ctx->slots[i];
@@ -353,12 +356,14 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
     if (sl.stage.h) cudaFreeHost(sl.stage.h);
     cudaEventDestroy(sl.stage.freeEv);
     cudaEventDestroy(sl.copied);
+    cudaEventDestroy(sl.computed);
     cudaEventDestroy(sl.done);
     cudaFree(sl.dMvs);
     cudaFree(sl.dDist);
     cudaFree(sl.dOrg);
   }
   cudaStreamDestroy(ctx->copyStream);
+  cudaStreamDestroy(ctx->readStream);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
   cudaFree(ctx->dJobs);
@@ -772,7 +777,10 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   }
   // candidate ranges must tile [0, n_cands): equal total + no overlap between neighbours in cand_first order
   if (candSum != n_cands) return fail(ctx, MMGPU_ERR_ARG, "candidate ranges of the blocks do not cover the mv array exactly once");
-  std::sort(order, order + n_blocks, [blocks](int32_t a, int32_t b) { return blocks[a].cand_first < blocks[b].cand_first; });
+  bool ordered = true;   // the usual case: blocks listed in candidate order -> no sort on the per-call path
+  for (int i = 1; i < n_blocks && ordered; ++i) ordered = blocks[i - 1].cand_first <= blocks[i].cand_first;
+  if (!ordered)
+    std::sort(order, order + n_blocks, [blocks](int32_t a, int32_t b) { return blocks[a].cand_first < blocks[b].cand_first; });
   long expect = 0;
   for (int i = 0; i < n_blocks; ++i)
   {
@@ -938,6 +946,7 @@ static int slotInit(mmgpu_ctx* ctx, MmSlot* sl)
   if (sl->init) return MMGPU_OK;
   CU(cudaEventCreateWithFlags(&sl->stage.freeEv, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&sl->copied, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&sl->computed, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
   sl->init = true;
   return MMGPU_OK;
@@ -969,8 +978,10 @@ extern "C" int mmgpu_me_batch_submit(mmgpu_ctx* ctx, int slot, const int16_t* or
   if ((rc = launchMe(ctx, &sl->plan, sl->dMvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max, sl->dDist, nullptr,
                      0, sl->dOrg, pitch)))
     return rc;
-  CU(cudaMemcpyAsync(dist, sl->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaEventRecord(sl->done, ctx->stream));
+  CU(cudaEventRecord(sl->computed, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->readStream, sl->computed, 0));
+  CU(cudaMemcpyAsync(dist, sl->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->readStream));
+  CU(cudaEventRecord(sl->done, ctx->readStream));
   sl->pending = true;
   return MMGPU_OK;
 }
