@@ -48,7 +48,7 @@ struct MmSlot  // one in-flight mmgpu_me_batch_submit: its own device buffers, s
   size_t capDist;
   int16_t* dOrg;
   size_t capOrg;
-  cudaEvent_t copied, computed, done;
+  cudaEvent_t copied, prepared, computed, done;
   bool init, pending;
 };
 
@@ -98,6 +98,7 @@ struct mmgpu_ctx
   bool mapPerModel;
   MmStage stage;            // staging of the synchronous entry points
   cudaStream_t copyStream;  // host->device copies of submitted batches
+  cudaStream_t prepStream;  // work list + per-candidate scalars of a submitted batch (overlaps the previous batch's k_fir)
   cudaStream_t readStream;  // device->host read-back of their distortions (so it does not delay the next batch's kernels)
   MmSlot slots[MM_MAX_INFLIGHT];
   // optional CUDA-event timing of the batch kernels: events t0 | k_map | t1 | k_fir | t2 per launchMe
@@ -260,6 +261,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&ctx->readStream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->prepStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&ctx->stage.freeEv, cudaEventDisableTiming));
   ctx->hRefs.assign(cfg->max_refs, MmRef());
   ctx->ownedPlanes.assign((size_t)cfg->max_refs * 3, nullptr);
@@ -348,6 +350,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaEventDestroy(ctx->stage.freeEv);
   cudaStreamSynchronize(ctx->copyStream);
   cudaStreamSynchronize(ctx->readStream);
+  cudaStreamSynchronize(ctx->prepStream);
   for (int i = 0; i < MM_MAX_INFLIGHT; ++i)
   {
     MmSlot& sl = ctx->slots[i];
@@ -356,6 +359,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
     if (sl.stage.h) cudaFreeHost(sl.stage.h);
     cudaEventDestroy(sl.stage.freeEv);
     cudaEventDestroy(sl.copied);
+    cudaEventDestroy(sl.prepared);
     cudaEventDestroy(sl.computed);
     cudaEventDestroy(sl.done);
     cudaFree(sl.dMvs);
@@ -364,6 +368,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   }
   cudaStreamDestroy(ctx->copyStream);
   cudaStreamDestroy(ctx->readStream);
+  cudaStreamDestroy(ctx->prepStream);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
   cudaFree(ctx->dJobs);
@@ -851,8 +856,11 @@ extern "C" uint64_t mmgpu_plan_samples(const mmgpu_plan* p) { return p ? p->samp
 
 static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int mode, int dist_kind,
                     int sub_shift, int clp_min, int clp_max, unsigned long long* d_dist, int16_t* d_dst, int dst_stride,
-                    const int16_t* d_org = nullptr, int org_stride = 0)
+                    const int16_t* d_org = nullptr, int org_stride = 0, cudaStream_t setupStream = nullptr,
+                    cudaEvent_t setupDone = nullptr)
 {
+  // setupStream != nullptr (pipelined submit): k_cand_setup runs there, behind the slot's k_build_items, so that both
+  // overlap the previous batch's k_fir; the main stream joins through setupDone before k_map.
   if (mv_prec_shift < 0 || mv_prec_shift > 4) return fail(ctx, MMGPU_ERR_ARG, "mv_prec_shift must be 0..4");
   MmParams P = baseParams(ctx);
   if (d_org) { P.org = d_org; P.orgStride = org_stride; }
@@ -869,8 +877,14 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
   P.dist = d_dist;
   P.dst = d_dst;
   P.dstStride = dst_stride;
-  mmk_cand_setup(ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot, plan->nCands, plan->dCands);
+  mmk_cand_setup(setupStream ? setupStream : ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot,
+                 plan->nCands, plan->dCands);
   ctx->launches++;
+  if (setupStream)
+  {
+    CU(cudaEventRecord(setupDone, setupStream));
+    CU(cudaStreamWaitEvent(ctx->stream, setupDone, 0));
+  }
   int rc;
   P.oobMode = (mode == MM_MODE_DIST) ? MMGPU_OOB_ME : MMGPU_OOB_PRED;
   if (mode == MM_MODE_DIST) CU(cudaMemsetAsync(d_dist, 0, sizeof(unsigned long long) * plan->nCands, ctx->stream));
@@ -946,6 +960,7 @@ static int slotInit(mmgpu_ctx* ctx, MmSlot* sl)
   if (sl->init) return MMGPU_OK;
   CU(cudaEventCreateWithFlags(&sl->stage.freeEv, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&sl->copied, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&sl->prepared, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&sl->computed, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
   sl->init = true;
@@ -973,10 +988,10 @@ extern "C" int mmgpu_me_batch_submit(mmgpu_ctx* ctx, int slot, const int16_t* or
   CU(cudaMemcpy2DAsync(sl->dOrg, 2 * (size_t)pitch, org, 2 * (size_t)org_stride, 2 * (size_t)org_w, org_h, cudaMemcpyHostToDevice,
                        ctx->copyStream));
   CU(cudaMemcpyAsync(sl->dMvs, mvs, sizeof(mmgpu_mv) * n_cands, cudaMemcpyHostToDevice, ctx->copyStream));
-  if ((rc = buildPlan(ctx, &sl->plan, n_blocks, blocks, n_cands, org_w, org_h, &sl->stage, ctx->copyStream, ctx->stream, sl->copied)))
+  if ((rc = buildPlan(ctx, &sl->plan, n_blocks, blocks, n_cands, org_w, org_h, &sl->stage, ctx->copyStream, ctx->prepStream, sl->copied)))
     return rc;
   if ((rc = launchMe(ctx, &sl->plan, sl->dMvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max, sl->dDist, nullptr,
-                     0, sl->dOrg, pitch)))
+                     0, sl->dOrg, pitch, ctx->prepStream, sl->prepared)))
     return rc;
   CU(cudaEventRecord(sl->computed, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->readStream, sl->computed, 0));
