@@ -176,8 +176,9 @@ void mmk_mpa_cache(cudaStream_t s, const MmGeom& g, int model, float2* out, uint
 void mmk_trig_tables(cudaStream_t s, const MmGeom& g, float2* th0, float2* th1, float2* ph0, float2* ph1);
 void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* itemBase, int nBlocks, MmItem* items,
                      int32_t* candBlock);
+// dist != nullptr: also zeroes the per-candidate distortion accumulators
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
-                    int mvShift, const float* rot, int nCands, MmCand* out);
+                    int mvShift, const float* rot, int nCands, MmCand* out, unsigned long long* dist);
 void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                    int model, int rotSlot, int32_t* outX, int32_t* outY);
 // positions of items [first, first+count) of P.items; model >= 0: all of them use that motion model

@@ -94,10 +94,11 @@ __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int3
 // -------------------------------------------------------------------------------------------------
 __global__ void k_cand_setup(MmGeom g, const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ candBlock,
                              const mmgpu_mv* __restrict__ mvs, int mvShift, const float* __restrict__ rot, int nCands,
-                             MmCand* __restrict__ out)
+                             MmCand* __restrict__ out, unsigned long long* __restrict__ dist)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nCands) return;
+  if (dist) dist[i] = 0ull;   // k_fir accumulates into it (saves a separate memset launch)
   const mmgpu_block b = blocks[candBlock[i]];
   const mmgpu_mv mv = mvs[i];
   MmCand c;
@@ -226,9 +227,9 @@ void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* i
   k_build_items<<<(nBlocks + 3) / 4, 128, 0, s>>>(blocks, itemBase, nBlocks, items, candBlock);
 }
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
-                    int mvShift, const float* rot, int nCands, MmCand* out)
+                    int mvShift, const float* rot, int nCands, MmCand* out, unsigned long long* dist)
 {
-  k_cand_setup<<<(nCands + MM_CS_THREADS - 1) / MM_CS_THREADS, MM_CS_THREADS, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, nCands, out);
+  k_cand_setup<<<(nCands + MM_CS_THREADS - 1) / MM_CS_THREADS, MM_CS_THREADS, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, nCands, out, dist);
 }
 void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                    int model, int rotSlot, int32_t* outX, int32_t* outY)

@@ -878,7 +878,7 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
   P.dst = d_dst;
   P.dstStride = dst_stride;
   mmk_cand_setup(setupStream ? setupStream : ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot,
-                 plan->nCands, plan->dCands);
+                 plan->nCands, plan->dCands, (mode == MM_MODE_DIST) ? d_dist : nullptr);
   ctx->launches++;
   if (setupStream)
   {
@@ -887,7 +887,6 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
   }
   int rc;
   P.oobMode = (mode == MM_MODE_DIST) ? MMGPU_OOB_ME : MMGPU_OOB_PRED;
-  if (mode == MM_MODE_DIST) CU(cudaMemsetAsync(d_dist, 0, sizeof(unsigned long long) * plan->nCands, ctx->stream));
   if ((rc = timingEvent(ctx))) return rc;
   // k_map: positions of all entries.  Work items are grouped by motion model; ctx->mapPerModel launches one
   // specialised kernel per model present, otherwise one generic launch covers all items.
