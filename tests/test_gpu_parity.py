@@ -450,6 +450,28 @@ def test_reregistered_device_plane_gets_fresh_tma_descriptor(env):
     assert np.array_equal(res[0], res[2]) and not np.array_equal(res[0], res[1])
 
 
+def test_unclipped_classic_mv_stays_inside_the_padded_plane(env):
+    """Classic candidates have no out-of-picture rule (the reference clips MVs with clipMv before xPredInterBlk); an
+    unclipped MV far outside must not make the batch kernels read outside the padded plane: the call returns, and the
+    valid candidates of the same batch are still exact."""
+    o, g, planes, ref, cur = env
+    g.set_org(cur[0])
+    blocks = np.zeros(2, dtype=mm.api.BLOCK_DTYPE)
+    blocks[0] = (64, 64, 64, 64, 0, 0, 0, 0, 3, 64, 64, 0)
+    blocks[1] = (W - 128, H - 128, 128, 128, 0, 0, 0, 3, 3, W - 128, H - 128, 0)
+    mvs = np.zeros(6, dtype=mm.api.MV_DTYPE)
+    mvs["hor"] = [5, -30000, 30000, -7, 20000, -20000]
+    mvs["ver"] = [-3, 30000, -30000, 9, -20000, 20000]
+    got = g.me_batch(blocks, mvs, mv_prec_shift=4, dist=mm.DIST_HAD)
+    for bi, ci in ((0, 0), (1, 3)):
+        b = blocks[bi]
+        org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+        exp = o.me_block(planes[0], org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), 0,
+                         np.array([[mvs["hor"][ci], mvs["ver"][ci]]]), mv_prec_shift=4, dist=mm.DIST_HAD, had_mode=ol.HAD_SIMD)
+        assert int(exp[0]) == int(got[ci])
+    g.sync()
+
+
 def test_cpp_host_adapter_matches_oracle():
     """The C++ adapter (reference-shaped argument lists) end to end: MC of a GED_CAMPOSE block and
     xPatternRefinementProjected's 9-point HAD refinement equal the oracle."""

@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(32 * MM_MAP_WARPS, MM_MAP_MINBLOCKS) k_map(con
     {
       fx = ((it.x + s.col * 4) << 4) + __float_as_int(c.p[0]);
       fy = ((it.y + s.row * 4) << 4) + __float_as_int(c.p[1]);
+      // xPredInterBlk has no zero-fill rule: the reference clips the MV beforehand (clipMv) so that the block stays inside
+      // the padded picture.  Positions of unclipped MVs are held inside the padded plane here, for memory safety only.
+      const int mg = P.tmaOffX - 16;
+      fx = min(max(fx, -mg << 4), (P.picW + mg) << 4);
+      fy = min(max(fy, -mg << 4), (P.picH + mg) << 4);
     }
     else
     {

@@ -3,6 +3,15 @@
 #include "mm_sbpos.cuh"
 #include "mm_fir.cuh"
 
+// Classic MVs come clipped from the reference (clipMv before xPredInterBlk); an unclipped one is held inside the padded
+// plane, for memory safety only (margin minus the filter reach).
+__device__ __forceinline__ void mm_classic_keep_inside(const MmParams& P, int csx, int csy, int shH, int shV, int* fx, int* fy)
+{
+  const int mgx = (P.tmaOffX >> csx) - 8, mgy = (P.tmaOffY >> csy) - 8;
+  *fx = min(max(*fx, -mgx << shH), ((P.picW >> csx) + mgx) << shH);
+  *fy = min(max(*fy, -mgy << shV), ((P.picH >> csy) + mgy) << shV);
+}
+
 // One thread per sub-block of ONE block (mmgpu_mc).  model == CLASSIC: one MV for the block (xPredInterBlk).
 __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                              int model, int rotSlot, int bi, int16_t* dst, int dstStride)
@@ -21,6 +30,7 @@ __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy
     // xPredInterBlk (InterPrediction.cpp:928-1096, no wrap / RPR): every sample uses the block MV
     fx = ((x + col * sbw) << shH) + mv.hor;
     fy = ((y + row * sbh) << shV) + mv.ver;
+    mm_classic_keep_inside(P, csx, csy, shH, shV, &fx, &fy);
   }
   else
   {
@@ -60,6 +70,7 @@ __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, i
   {
     fx = ((x + col * sbw) << shH) + mv.hor;
     fy = ((y + row * sbh) << shV) + mv.ver;
+    mm_classic_keep_inside(P, csx, csy, shH, shV, &fx, &fy);
   }
   else
   {
