@@ -1,6 +1,6 @@
 // map_host.cpp -- host build of the PRODUCT mapping code (vvc-extension-mm_b200/csrc/mm_map.cuh,
 // mm_libm.cuh) behind a tiny C interface, so the CPU test-suite can compare it with the oracle
-// without a GPU.  The sub-block enumeration mirrors mm_subblock_pos() in mm_kernels.cuh.
+// without a GPU.  The sub-block enumeration mirrors mm_subblock_pos() in mm_sbpos.cuh.
 #include <cstdint>
 #include <cstdlib>
 #include <vector>

@@ -318,7 +318,7 @@ MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int 
 // ---- one sub-block -------------------------------------------------------------------------------
 // The mapping of a sub-block is split into the part that does not depend on the candidate MV (mm_model_prepare:
 // the reference recomputes it per call, encoder-side memoisation aside -- quirk Q8 says that has no numeric effect)
-// and the per-candidate part (mm_model_apply).  k_me prepares once per warp and applies per candidate.
+// and the per-candidate part (mm_model_apply).  k_map prepares once per chunk of sub-blocks and applies per candidate.
 struct MmInv
 {
   float a, b, c, d, e;  // MPA: PX,PY | GED: r,theta,phi,sinf(theta),cosf(theta) | ROT/3DT: s0,s1,s2 | TAN: yPl,xPl

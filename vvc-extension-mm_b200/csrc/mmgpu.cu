@@ -1,4 +1,4 @@
-// mmgpu.cu -- C ABI (include/mmgpu.h) over the sm_100a kernels in mm_kernels.cuh.
+// mmgpu.cu -- C ABI (include/mmgpu.h) over the sm_100a kernels of mm_kernels_{map,fir,mc}.cu (launch wrappers: mm_common.cuh).
 // Host side is plain C++ + CUDA runtime; no torch types, no CPU fallback of the compute path.
 #include <cuda.h>          // CUtensorMap types; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
