@@ -303,32 +303,34 @@ def main():
                 freed[s % 2].record(stream)
 
     # e2e: the host-facing call with every input in pinned HOST memory -- original picture, blocks and MVs go up, the
-    # distortions come back, every step.  Two batches are kept in flight (mmgpu_me_batch_submit / _wait on two slots) so
-    # that the copies of step s+1 overlap the kernels of step s; step s's result is read before step s+2 is submitted.
-    h_dist2 = [h_dist, torch.zeros(n_cands, dtype=torch.int64).pin_memory()]
-    h_blocks2 = [h_blocks, h_blocks.clone().pin_memory()]
+    # distortions come back, every step.  NSLOT batches are kept in flight (mmgpu_me_batch_submit / _wait) so that the
+    # copies and the preparation of step s+1 overlap the kernels of step s and a short stall of the host thread does not
+    # idle the GPU; step s's result is read before step s+NSLOT is submitted.
+    NSLOT = 3
+    h_dist2 = [h_dist] + [torch.zeros(n_cands, dtype=torch.int64).pin_memory() for _ in range(NSLOT - 1)]
+    h_blocks2 = [h_blocks] + [h_blocks.clone().pin_memory() for _ in range(NSLOT - 1)]
 
     def e2e_submit(s):
         prefetch(s + 1)
         if N > 1:
             ready[s % 2].synchronize()
         _, b = step_plan(s)
-        hb = h_blocks2[s % 2].numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
+        hb = h_blocks2[s % NSLOT].numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
         hb["ref_slot"] = b["ref_slot"]
         hb["org_y"] = e2e_org_y
-        gpu.me_batch_submit(s % 2, h_org.numpy(), hb, h_mvs.numpy().view(mm.api.MV_DTYPE).reshape(-1),
-                            h_dist2[s % 2].numpy().view(np.uint64), mv_prec_shift=prec, dist=mm.DIST_HAD)
+        gpu.me_batch_submit(s % NSLOT, h_org.numpy(), hb, h_mvs.numpy().view(mm.api.MV_DTYPE).reshape(-1),
+                            h_dist2[s % NSLOT].numpy().view(np.uint64), mv_prec_shift=prec, dist=mm.DIST_HAD)
         if N > 1:
             freed[s % 2].record(stream)
 
     def e2e_step(s):
-        if s >= 2:
-            gpu.me_batch_wait(s % 2)
+        if s >= NSLOT:
+            gpu.me_batch_wait(s % NSLOT)
         e2e_submit(s)
 
     def e2e_drain(k):
-        for s in range(max(0, k - 2), k):
-            gpu.me_batch_wait(s % 2)
+        for s in range(max(0, k - NSLOT), k):
+            gpu.me_batch_wait(s % NSLOT)
 
     def barrier():
         torch.cuda.synchronize()
@@ -378,9 +380,9 @@ def main():
     launches = gpu.launch_count - launches0
     kmap_ms, k_ms, k_n = gpu.kernel_timing_read()
     gpu.kernel_timing(False)
-    for s in range(4):
+    for s in range(2 * NSLOT):
         e2e_step(s)
-    e2e_drain(4)
+    e2e_drain(2 * NSLOT)
     # self-check: the host-facing call and the device-resident call evaluate the same batch -> identical distortions;
     # with N > 1 the exchanged pictures are what their owners hold (every rank can regenerate every synthetic picture)
     for p in range(2):
