@@ -78,6 +78,11 @@ uint64_t mmgpu_launch_count(const mmgpu_ctx* ctx);
 int mmgpu_kernel_timing_enable(mmgpu_ctx* ctx, int on);
 int mmgpu_kernel_timing_read(mmgpu_ctx* ctx, double* map_ms, double* fir_ms, uint64_t* batches);
 
+/* Self-test of the one place where the reference narrows a DOUBLE libm result to float (TangentialMotionModel.cpp:27-28,
+ * 38,40): checksum of (x, float(sin((double)x)), float(cos((double)x))) over every stride-th float x with |x| <= pi/2,
+ * computed by the device code the kernels use.  Must equal the glibc sweep of oracle/tools/tan_exceptions.cpp. */
+int mmgpu_selftest_tan_sincos(mmgpu_ctx* ctx, uint32_t stride, uint64_t* checksum);
+
 /* ---- reference pictures: Picture::getRecoBuf(compID, wrapRef) after extendPicBorder (Picture.cpp:988-1092) */
 /* plane00[c] points at sample (0,0) of component c in HOST memory; the margins around it are copied too. */
 int mmgpu_set_ref(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane00[3], const int32_t stride[3]);

@@ -634,7 +634,11 @@ void orc_mc_block(OrcCtx* c, const int16_t* ref, int rs, int comp, int chroma_fm
       const int i = col * rows + row;
       const int xP = px[i] >> shH, yP = py[i] >> shV, xF = px[i] & ((1 << shH) - 1), yF = py[i] & ((1 << shV) - 1);
       int16_t* d = dst + row * sbh * ds + col * sbw;
-      if (xP < -mcw || yP < -mch || xP >= picw + mcw - sbw || yP >= pich + mch - sbh)
+      /* InterPrediction.cpp:780 / InterSearch.cpp:6332.  refBuf.width/height and subblockSize.width/height are SizeType
+         (uint32_t), so the two upper-bound comparisons are UNSIGNED: a negative position converts to a huge value and
+         counts as beyond the bound.  Net effect: the +-maxCU slack exists on the right/bottom only; any sub-block whose
+         integer position is negative is zero-filled.  (Found by decoding a real bitstream: tests/test_e2e_*.) */
+      if (xP < -mcw || yP < -mch || (uint32_t)xP >= (uint32_t)(picw + mcw - sbw) || (uint32_t)yP >= (uint32_t)(pich + mch - sbh))
       {
         for (int y = 0; y < sbh; ++y) memset(d + y * ds, 0, sbw * sizeof(int16_t));
         continue;

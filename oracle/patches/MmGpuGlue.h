@@ -1,0 +1,69 @@
+// MmGpuGlue.h -- reference-side binding of libmmgpu.so (include/mmgpu.h), added to the reference by oracle/patches/mmgpu.patch.
+// Included only by the patched translation units (InterPrediction.cpp, InterSearch.cpp, MVReprojection.cpp, Picture.cpp):
+// no reference header changes, so every other object file of the stock build is reused as is.
+//
+// MMGPU=0 in the environment switches the patched apps back to the reference's CPU code at run time.
+#pragma once
+#include "CommonDef.h"
+#include "Unit.h"
+#include "Mv.h"
+#include "Buffer.h"
+#include "Picture.h"
+#include "RdCost.h"
+#include "EpipoleList.h"
+
+namespace mmglue
+{
+bool enabled();
+
+// MVReprojection::init (MVReprojection.cpp:7-65): creates the device context (MPA caches, ERP tables on the device)
+void init(const Size& resolution, const SPS* sps, const EpipoleList* epipoleList);
+// Picture::extendPicBorder (Picture.cpp:988-1048): the reconstruction of `pic` changed -> its device copy is stale
+void invalidate(const Picture* pic);
+// make sure the (pic, wrap) variant is resident; returns its reference slot (lazy upload of the padded planes)
+int ensureRef(const Picture* pic, bool wrap);
+
+// body of InterPrediction::xPredInterBlkMM (InterPrediction.cpp:683-856)
+void predInterBlkMM(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, const Size& blockSize, const Picture* refPic,
+                    bool wrapRef, const Mv& mv, MotionModelID motionModel, bool bi, const ClpRng& clpRng, int curPOC, PelBuf& dstBuf);
+
+// ---- motion estimation: xApplyMvVA / xMVReprojectionInterpolation + m_cDistParam.distFunc (InterSearch.cpp:363-453,
+//      5287-5322, 6168-6385).  The search control flow is untouched: candidate sets the reference is about to visit are
+//      evaluated ahead in ONE mmgpu_me_batch, and the reference's own compare chain then reads the distortions back one by
+//      one through m_cDistParam.distFunc (identical decisions by construction).
+struct MeBlock
+{
+  Position blkPos;
+  Size blkSize;
+  const Pel* refLuma00;   // cStruct.pcRefBuf->buf: sample (0,0) of the reference luma plane (identifies the resident slot)
+  MotionModelID model;
+  int curPOC, refPOC;
+  ClpRng clpRng;
+};
+// after RdCost::setDistParam in the MM branches: remembers SAD/HAD, forgets the look-ahead of the previous search and
+// points dp.distFunc at the function that returns the distortion of the last meEval()
+void meSetup(DistParam& dp, bool useHadamard);
+// evaluate one candidate (look-ahead hit, or a one-candidate batch); its distortion is what dp.distFunc returns next
+void meEval(const MeBlock& b, const DistParam& dp, const Mv& mv, MvPrecision prec);
+// look-ahead: the listed MVs will (probably) be visited next
+void mePrefetch(const MeBlock& b, const DistParam& dp, const Mv* mvs, int n, MvPrecision prec);
+// dry run of one of the reference's own enumerators: while collecting, xTZSearchHelp only records the point
+void beginCollect();
+bool collecting();
+void collect(int x, int y);
+void endCollect(const MeBlock& b, const DistParam& dp);   // = mePrefetch of the collected integer MVs
+
+void printStats();
+
+// ---- debugging aid: MMGPU_DUMP=<file> (with MMGPU=0) records every xPredInterBlkMM call of the CPU path -- parameters,
+//      the reference picture (un-padded planes, once per picture) and the predicted samples -- for tests/replay_mc_dump.py,
+//      which replays the calls through the oracle (and, on a GPU box, through libmmgpu.so).
+bool dumping();
+// ME side of the dump (every MMGPU_DUMP_ME-th search; 0/unset = none): the original block once per search ('O'), then
+// every candidate the CPU path evaluates with the distortion the reference's distFunc returned ('E').
+void dumpRef(const Picture* refPic, bool wrapRef);
+void meDumpSetup(DistParam& dp, bool useHadamard);
+void meDumpCandidate(const MeBlock& b, const Mv& mv, MvPrecision prec);
+void dumpMc(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, const Size& blockSize, const Picture* refPic,
+            bool wrapRef, const Mv& mv, MotionModelID motionModel, bool bi, const ClpRng& clpRng, int curPOC, const PelBuf& dstBuf);
+}  // namespace mmglue

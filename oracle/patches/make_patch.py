@@ -1,0 +1,387 @@
+"""Regenerates oracle/patches/mmgpu.patch: copies the four touched reference units to a scratch directory, applies the
+edits below (exact-match replacements, each asserted to match once) and writes the unified diff.  The patch, not this
+script, is what oracle/vtm.mk applies; the script documents every edit and fails loudly if the reference text moves."""
+import difflib
+import os
+import shutil
+import sys
+
+SRC = "/root/reference/source"
+FILES = ["Lib/CommonLib/InterPrediction.cpp", "Lib/CommonLib/MVReprojection.cpp", "Lib/CommonLib/Picture.cpp",
+         "Lib/EncoderLib/InterSearch.cpp"]
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sub(text, old, new, count=1):
+    assert text.count(old) == count, "expected %d match(es) of %r, found %d" % (count, old[:60], text.count(old))
+    return text.replace(old, new)
+
+
+def edit_picture(t):
+    t = sub(t, '#include "CommonLib/InterpolationFilter.h"\n', '#include "CommonLib/InterpolationFilter.h"\n#include "MmGpuGlue.h"\n')
+    # the reconstruction changed and its borders were rebuilt: the device copy (if any) is stale
+    t = sub(t, "  m_extendedBorder = true;\n}\n", "  m_extendedBorder = true;\n  mmglue::invalidate( this );\n}\n")
+    return t
+
+
+def edit_mvreprojection(t):
+    t = sub(t, '#include "MVReprojection.h"\n', '#include "MVReprojection.h"\n#include "MmGpuGlue.h"\n')
+    t = sub(t, "  m_initialized = true;\n}\n", "  m_initialized = true;\n  mmglue::init( resolution, sps, epipoleList );\n}\n")
+    return t
+
+
+def edit_interprediction(t):
+    t = sub(t, '#include "debug_tools.h"\n', '#include "debug_tools.h"\n#include "MmGpuGlue.h"\n')
+    t = sub(t, """  const Position blockPos = pu.blocks[compID].pos();
+  const Size blockSize = pu.blocks[compID].size();
+#if INTERPRED_PROFILING
+  auto start_mvReprojTime = std::chrono::high_resolution_clock::now();
+#endif
+  ArrayXXFixedPtrPair cart2DProjMovedFixedSubblocks = m_mvReprojection->reprojectMotionVectorSubblocks(
+    blockPos, blockSize, mv, motionModel, compID, chFmt, pu.cs->slice->getPOC(), refPic->getPOC());
+""", """  const Position blockPos = pu.blocks[compID].pos();
+  const Size blockSize = pu.blocks[compID].size();
+  if( mmglue::enabled() && !srcPadBuf && !bilinearMC )
+  {
+    // GPU path: mapping + interpolation of the whole block in one call (libmmgpu.so, mmgpu_mc)
+    mmglue::predInterBlkMM( compID, chFmt, blockPos, blockSize, refPic, wrapRef, mv, motionModel, bi, clpRng, pu.cs->slice->getPOC(),
+                            dstPic.bufs[compID] );
+    return;
+  }
+#if INTERPRED_PROFILING
+  auto start_mvReprojTime = std::chrono::high_resolution_clock::now();
+#endif
+  ArrayXXFixedPtrPair cart2DProjMovedFixedSubblocks = m_mvReprojection->reprojectMotionVectorSubblocks(
+    blockPos, blockSize, mv, motionModel, compID, chFmt, pu.cs->slice->getPOC(), refPic->getPOC());
+""")
+    # debugging aid (MMGPU_DUMP): record the CPU path's result
+    t = sub(t, """      }
+    }
+  }
+  JVET_J0090_SET_CACHE_ENABLE(
+    (srcPadStride == 0)
+    && (bioApplied
+        == false));   // Enabled only in non-DMVR-non-BDOF process, In DMVR process, srcPadStride is always non-zero
+#if INTERPRED_PROFILING
+  auto end_interpolTime = std::chrono::high_resolution_clock::now();
+  dbg_interpolTime += std::chrono::duration<double>(end_interpolTime - start_interpolTime).count();
+  auto start_bdofPadTime""", """      }
+    }
+  }
+  if( mmglue::dumping() && !srcPadBuf && !bilinearMC )
+  {
+    mmglue::dumpMc( compID, chFmt, blockPos, blockSize, refPic, wrapRef, mv, motionModel, bi, clpRng, pu.cs->slice->getPOC(), dstBuf );
+  }
+  JVET_J0090_SET_CACHE_ENABLE(
+    (srcPadStride == 0)
+    && (bioApplied
+        == false));   // Enabled only in non-DMVR-non-BDOF process, In DMVR process, srcPadStride is always non-zero
+#if INTERPRED_PROFILING
+  auto end_interpolTime = std::chrono::high_resolution_clock::now();
+  dbg_interpolTime += std::chrono::duration<double>(end_interpolTime - start_interpolTime).count();
+  auto start_bdofPadTime""")
+    return t
+
+
+MEBLK = "mmglue::MeBlock{ %s.blkPos, %s.blkSize, %s.pcRefBuf->buf, %s.motionModel, %s.curPOC, %s.refPOC, m_lumaClpRng }"
+
+
+def meblk(s):
+    return MEBLK % ((s,) * 6)
+
+
+def edit_intersearch(t):
+    t = sub(t, '#include "EncLib.h"\n', '#include "EncLib.h"\n#include "MmGpuGlue.h"\n')
+    # --- xTZSearchHelp: during a dry run of an enumerator only the visited point is recorded
+    t = sub(t, """  Distortion  uiSad = 0;
+
+//  CHECK(!( !( rcStruct.searchRange.left > iSearchX""", """  Distortion  uiSad = 0;
+  if( mmglue::collecting() )
+  {
+    mmglue::collect( iSearchX, iSearchY );
+    return;
+  }
+
+//  CHECK(!( !( rcStruct.searchRange.left > iSearchX""")
+    # --- xTZ2PointSearch: both points ahead
+    t = sub(t, """  const int iY2 = rcStruct.iBestY + yOffset[1][rcStruct.ucPointNr];
+
+""", """  const int iY2 = rcStruct.iBestY + yOffset[1][rcStruct.ucPointNr];
+  if( mmglue::enabled() && rcStruct.motionModel != CLASSIC && !mmglue::collecting() )
+  {
+    const Mv ahead[2] = { Mv( iX1, iY1 ), Mv( iX2, iY2 ) };
+    const bool in1 = iX1 >= sr.left && iX1 <= sr.right && iY1 >= sr.top && iY1 <= sr.bottom;
+    const bool in2 = iX2 >= sr.left && iX2 <= sr.right && iY2 >= sr.top && iY2 <= sr.bottom;
+    if( in1 || in2 )
+    {
+      mmglue::mePrefetch( %s, m_cDistParam, ahead + ( in1 ? 0 : 1 ), ( in1 && in2 ) ? 2 : 1, MV_PRECISION_INT );
+    }
+  }
+
+""" % meblk("rcStruct"))
+    # --- xMotionEstimation: the reference picture must be resident before the search starts
+    t = sub(t, """    buf = refPic->getRecoBuf(COMPONENT_Y, wrap);
+  }
+
+  IntTZSearchStruct cStruct;""", """    buf = refPic->getRecoBuf(COMPONENT_Y, wrap);
+    if( mmglue::enabled() )
+    {
+      mmglue::ensureRef( refPic, wrap );
+    }
+    else if( mmglue::dumping() )
+    {
+      mmglue::dumpRef( refPic, wrap );
+    }
+  }
+
+  IntTZSearchStruct cStruct;""")
+    # --- xPatternSearch: the whole grid (bi-prediction: 81 points) in one batch
+    t = sub(t, """  const SearchRange& sr = cStruct.searchRange;
+
+  for ( int y = sr.top; y <= sr.bottom; y++ )
+  {
+    for ( int x = sr.left; x <= sr.right; x++ )
+    {
+      //  find min. distortion position
+      xApplyMvVA(cStruct, Mv(x, y), MV_PRECISION_INT);
+""", """  const SearchRange& sr = cStruct.searchRange;
+
+  if( mmglue::enabled() && cStruct.motionModel != CLASSIC )
+  {
+    mmglue::beginCollect();
+    for ( int y = sr.top; y <= sr.bottom; y++ )
+    {
+      for ( int x = sr.left; x <= sr.right; x++ )
+      {
+        mmglue::collect( x, y );
+      }
+    }
+    mmglue::endCollect( %s, m_cDistParam );
+  }
+  for ( int y = sr.top; y <= sr.bottom; y++ )
+  {
+    for ( int x = sr.left; x <= sr.right; x++ )
+    {
+      //  find min. distortion position
+      xApplyMvVA(cStruct, Mv(x, y), MV_PRECISION_INT);
+""" % meblk("cStruct"))
+    # --- xTZSearch: first search -- dry run of all diamond rounds around the start point, one batch
+    t = sub(t, """  // first search around best position up to now.
+  // The following works as a "subsampled/log" window search around the best candidate
+  for (iDist = 1; iDist <= searchRange; iDist *= 2)
+  {
+""", """  // first search around best position up to now.
+  // The following works as a "subsampled/log" window search around the best candidate
+  if( mmglue::enabled() && cStruct.motionModel != CLASSIC )
+  {
+    // look-ahead: dry run of the reference's own enumerators (xTZSearchHelp only records the points), one GPU batch
+    IntTZSearchStruct dry = cStruct;
+    mmglue::beginCollect();
+    for (iDist = 1; iDist <= searchRange; iDist *= 2)
+    {
+      if ( bFirstSearchDiamond == 1 )
+      {
+        xTZ8PointDiamondSearch ( dry, iStartX, iStartY, iDist, bFirstCornersForDiamondDist1 );
+      }
+      else
+      {
+        xTZ8PointSquareSearch  ( dry, iStartX, iStartY, iDist );
+      }
+    }
+    mmglue::endCollect( %s, m_cDistParam );
+  }
+  for (iDist = 1; iDist <= searchRange; iDist *= 2)
+  {
+""" % meblk("cStruct"))
+    # --- xTZSearch: raster searches
+    t = sub(t, """    cStruct.uiBestDistance = iWindowSize;
+    for ( iStartY = localsr.top; iStartY <= localsr.bottom; iStartY += iWindowSize )
+    {
+""", """    cStruct.uiBestDistance = iWindowSize;
+    if( mmglue::enabled() && cStruct.motionModel != CLASSIC )
+    {
+      mmglue::beginCollect();
+      for ( iStartY = localsr.top; iStartY <= localsr.bottom; iStartY += iWindowSize )
+      {
+        for ( iStartX = localsr.left; iStartX <= localsr.right; iStartX += iWindowSize )
+        {
+          mmglue::collect( iStartX, iStartY );
+        }
+      }
+      mmglue::endCollect( %s, m_cDistParam );
+    }
+    for ( iStartY = localsr.top; iStartY <= localsr.bottom; iStartY += iWindowSize )
+    {
+""" % meblk("cStruct"))
+    t = sub(t, """      cStruct.uiBestDistance = iRaster;
+      for ( iStartY = sr.top; iStartY <= sr.bottom; iStartY += iRaster )
+      {
+""", """      cStruct.uiBestDistance = iRaster;
+      if( mmglue::enabled() && cStruct.motionModel != CLASSIC )
+      {
+        mmglue::beginCollect();
+        for ( iStartY = sr.top; iStartY <= sr.bottom; iStartY += iRaster )
+        {
+          for ( iStartX = sr.left; iStartX <= sr.right; iStartX += iRaster )
+          {
+            mmglue::collect( iStartX, iStartY );
+          }
+        }
+        mmglue::endCollect( %s, m_cDistParam );
+      }
+      for ( iStartY = sr.top; iStartY <= sr.bottom; iStartY += iRaster )
+      {
+""" % meblk("cStruct"))
+    # --- xTZSearch: star refinement -- all rounds around the new start point
+    t = sub(t, """      cStruct.uiBestDistance = 0;
+      cStruct.ucPointNr = 0;
+      for (iDist = 1; iDist < searchRange + 1; iDist *= 2)
+      {
+        if ( bStarRefinementDiamond == 1 )
+        {
+          xTZ8PointDiamondSearch ( cStruct, iStartX, iStartY, iDist, bStarRefinementCornersForDiamondDist1 );
+""", """      cStruct.uiBestDistance = 0;
+      cStruct.ucPointNr = 0;
+      if( mmglue::enabled() && cStruct.motionModel != CLASSIC )
+      {
+        IntTZSearchStruct dry = cStruct;
+        mmglue::beginCollect();
+        for (iDist = 1; iDist < searchRange + 1; iDist *= 2)
+        {
+          if ( bStarRefinementDiamond == 1 )
+          {
+            xTZ8PointDiamondSearch ( dry, iStartX, iStartY, iDist, bStarRefinementCornersForDiamondDist1 );
+          }
+          else
+          {
+            xTZ8PointSquareSearch  ( dry, iStartX, iStartY, iDist );
+          }
+        }
+        mmglue::endCollect( %s, m_cDistParam );
+      }
+      for (iDist = 1; iDist < searchRange + 1; iDist *= 2)
+      {
+        if ( bStarRefinementDiamond == 1 )
+        {
+          xTZ8PointDiamondSearch ( cStruct, iStartX, iStartY, iDist, bStarRefinementCornersForDiamondDist1 );
+""" % meblk("cStruct"), count=1)
+    # --- fractional refinement: distortion set-up + the 9 points of a refinement step in one batch
+    t = sub(t, """    m_pcRdCost->setDistParam(m_cDistParam, *cStruct.pcPatternKey, m_tmpMMStorage.buf, m_tmpMMStorage.stride, m_lumaClpRng.bd, COMPONENT_Y, 0, 1, m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD());
+    xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, rcMvBaseI, MV_PRECISION_INT,
+                                 m_tmpMMStorage, cStruct.motionModel, m_lumaClpRng, cStruct.curPOC, cStruct.refPOC);
+""", """    m_pcRdCost->setDistParam(m_cDistParam, *cStruct.pcPatternKey, m_tmpMMStorage.buf, m_tmpMMStorage.stride, m_lumaClpRng.bd, COMPONENT_Y, 0, 1, m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD());
+    if( mmglue::dumping() )
+    {
+      mmglue::meDumpSetup( m_cDistParam, m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD() );
+    }
+    if( mmglue::enabled() )
+    {
+      mmglue::meSetup( m_cDistParam, m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD() );
+      mmglue::meEval( %s, m_cDistParam, rcMvBaseI, MV_PRECISION_INT );
+    }
+    else
+    xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, rcMvBaseI, MV_PRECISION_INT,
+                                 m_tmpMMStorage, cStruct.motionModel, m_lumaClpRng, cStruct.curPOC, cStruct.refPOC);
+""" % meblk("cStruct"))
+    t = sub(t, """  m_pcRdCost->setDistParam( m_cDistParam, *cStruct.pcPatternKey, m_tmpMMStorage.buf, m_tmpMMStorage.stride, m_lumaClpRng.bd, COMPONENT_Y, 0, 1, useHadamard );
+
+  // Half-pel refinement
+""", """  m_pcRdCost->setDistParam( m_cDistParam, *cStruct.pcPatternKey, m_tmpMMStorage.buf, m_tmpMMStorage.stride, m_lumaClpRng.bd, COMPONENT_Y, 0, 1, useHadamard );
+  if( mmglue::enabled() )
+  {
+    mmglue::meSetup( m_cDistParam, useHadamard );
+  }
+  else if( mmglue::dumping() )
+  {
+    mmglue::meDumpSetup( m_cDistParam, useHadamard );
+  }
+
+  // Half-pel refinement
+""")
+    t = sub(t, """  const Mv* pcMvRefine = (refinementPrecision == MV_PRECISION_HALF ? s_acMvRefineH : s_acMvRefineQ);
+  for (uint32_t i = 0; i < 9; ++i) {
+    cMvTest = cMvBase + pcMvRefine[i];
+    xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, cMvTest, refinementPrecision,
+                                 m_tmpMMStorage, cStruct.motionModel, m_lumaClpRng, cStruct.curPOC, cStruct.refPOC);
+""", """  const Mv* pcMvRefine = (refinementPrecision == MV_PRECISION_HALF ? s_acMvRefineH : s_acMvRefineQ);
+  if( mmglue::enabled() )
+  {
+    Mv ahead[9];
+    for (uint32_t i = 0; i < 9; ++i) {
+      ahead[i] = cMvBase + pcMvRefine[i];
+    }
+    mmglue::mePrefetch( %s, m_cDistParam, ahead, 9, refinementPrecision );
+  }
+  for (uint32_t i = 0; i < 9; ++i) {
+    cMvTest = cMvBase + pcMvRefine[i];
+    if( mmglue::enabled() )
+    {
+      mmglue::meEval( %s, m_cDistParam, cMvTest, refinementPrecision );
+    }
+    else
+    xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, cMvTest, refinementPrecision,
+                                 m_tmpMMStorage, cStruct.motionModel, m_lumaClpRng, cStruct.curPOC, cStruct.refPOC);
+""" % (meblk("cStruct"), meblk("cStruct")))
+    # --- prepareRdCostDistParamVA / xApplyMvVA: the MM branches
+    t = sub(t, """    m_pcRdCost->setDistParam(m_cDistParam, *rcStruct.pcPatternKey, m_tmpMMStorage.buf, m_tmpMMStorage.stride, m_lumaClpRng.bd, COMPONENT_Y, subShiftMode, step, useHadamard);
+  }
+}
+""", """    m_pcRdCost->setDistParam(m_cDistParam, *rcStruct.pcPatternKey, m_tmpMMStorage.buf, m_tmpMMStorage.stride, m_lumaClpRng.bd, COMPONENT_Y, subShiftMode, step, useHadamard);
+    if( mmglue::enabled() )
+    {
+      CHECK( step != 1, "mmglue: distortion step != 1" );
+      mmglue::meSetup( m_cDistParam, useHadamard );
+    }
+    else if( mmglue::dumping() )
+    {
+      mmglue::meDumpSetup( m_cDistParam, useHadamard );
+    }
+  }
+}
+""")
+    t = sub(t, """  else
+  {
+    xMVReprojectionInterpolation(rcStruct.blkPos, rcStruct.blkSize, *rcStruct.pcRefBuf, rMv, mvPrec, m_tmpMMStorage, rcStruct.motionModel, m_lumaClpRng, rcStruct.curPOC, rcStruct.refPOC);
+  }
+}
+""", """  else if( mmglue::enabled() )
+  {
+    mmglue::meEval( %s, m_cDistParam, rMv, mvPrec );
+  }
+  else
+  {
+    xMVReprojectionInterpolation(rcStruct.blkPos, rcStruct.blkSize, *rcStruct.pcRefBuf, rMv, mvPrec, m_tmpMMStorage, rcStruct.motionModel, m_lumaClpRng, rcStruct.curPOC, rcStruct.refPOC);
+  }
+}
+""" % meblk("rcStruct"))
+    t = sub(t, """  Mv mv(_mv);
+  // Luma interpolation filter with quarter pixel precision and MVReprojection requires MV_PRECISION_INTERNAL
+  // for COMPONENT_Y.
+""", """  Mv mv(_mv);
+  if( mmglue::dumping() )
+  {
+    mmglue::meDumpCandidate( mmglue::MeBlock{ cuPosition, cuSize, refBuf.buf, motionModel, curPOC, refPOC, clpRng }, _mv, mvPrec );
+  }
+  // Luma interpolation filter with quarter pixel precision and MVReprojection requires MV_PRECISION_INTERNAL
+  // for COMPONENT_Y.
+""")
+    return t
+
+
+EDITS = {"Lib/CommonLib/InterPrediction.cpp": edit_interprediction, "Lib/CommonLib/MVReprojection.cpp": edit_mvreprojection,
+         "Lib/CommonLib/Picture.cpp": edit_picture, "Lib/EncoderLib/InterSearch.cpp": edit_intersearch}
+
+
+def main():
+    out = []
+    for f in FILES:
+        a = open(os.path.join(SRC, f), encoding="latin-1").read()
+        b = EDITS[f](a)
+        out += difflib.unified_diff(a.splitlines(True), b.splitlines(True), "a/" + f, "b/" + f, n=3)
+    with open(os.path.join(HERE, "mmgpu.patch"), "w", encoding="latin-1") as fh:
+        fh.writelines(out)
+    print("wrote mmgpu.patch: %d lines" % len(out))
+
+
+if __name__ == "__main__":
+    main()

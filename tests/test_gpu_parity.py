@@ -655,3 +655,22 @@ def test_config3_all_five_models_4096x2048():
     finally:
         g.close()
         o.close()
+
+
+def test_tan_double_sincos_exhaustive(env):
+    """TangentialMotionModel.cpp:27-28,38,40 narrow a DOUBLE libm sin/cos to float.  The device code
+    (mm_libm.cuh: mm_sin_d2f / mm_cos_d2f) must give glibc's narrowed result for EVERY float of the domain |x| <= pi/2:
+    its checksum over all 2^31 inputs equals the host sweep of oracle/tools/tan_exceptions.cpp, committed in
+    csrc/mm_tan_exceptions.h (MM_TAN_SWEEP_CHECKSUM); a strided sweep is re-done against this box's glibc here."""
+    import os, re, subprocess
+    o, g, *_ = env
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "vvc-extension-mm_b200", "csrc", "mm_tan_exceptions.h")).read()
+    full = int(re.search(r"MM_TAN_SWEEP_CHECKSUM 0x([0-9a-f]+)ull", hdr).group(1), 16)
+    assert g.selftest_tan_sincos(1) == full
+    tool = os.path.join(root, "oracle", "_build", "tan_exceptions")
+    if not os.path.exists(tool):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "oracle", "tools", "tan_exceptions.cpp"),
+                               "-o", tool, "-lm"])
+    host = int(subprocess.check_output([tool, "sum", "97"]).decode().strip(), 16)
+    assert g.selftest_tan_sincos(97) == host

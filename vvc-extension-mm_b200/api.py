@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library():
     L.mmgpu_launch_count.argtypes = [vp]
     L.mmgpu_kernel_timing_enable.argtypes = [vp, i32]
     L.mmgpu_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64)]
+    L.mmgpu_selftest_tan_sincos.argtypes = [vp, C.c_uint32, C.POINTER(u64)]
     for f in (L.mmgpu_set_ref, L.mmgpu_set_ref_device, L.mmgpu_set_ref_unpadded):
         f.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_set_ref_unpadded_wrap.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32), i32]
@@ -206,6 +207,12 @@ class MmGpu:
     @property
     def launch_count(self):
         return int(self.L.mmgpu_launch_count(self.h))
+
+    def selftest_tan_sincos(self, stride=1):
+        """Checksum of the device's float(sin/cos((double)x)) over every stride-th float of |x| <= pi/2 (mmgpu.h)."""
+        v = C.c_uint64()
+        self._chk(self.L.mmgpu_selftest_tan_sincos(self.h, int(stride), C.byref(v)))
+        return int(v.value)
 
     def kernel_timing(self, on=True):
         self._chk(self.L.mmgpu_kernel_timing_enable(self.h, int(on)))

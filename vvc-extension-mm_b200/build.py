@@ -9,11 +9,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-HDRS = ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_sbpos.cuh", "mm_fir.cuh", "mm_htaps.h"]
+HDRS = ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_tan_exceptions.h", "mm_sbpos.cuh", "mm_fir.cuh", "mm_htaps.h"]
 # unit -> headers it depends on (besides include/mmgpu.h)
 UNITS = {
     "mmgpu.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_fir.cuh", "mm_htaps.h"],
-    "mm_kernels_map.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_sbpos.cuh"],
+    "mm_kernels_map.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_tan_exceptions.h", "mm_sbpos.cuh"],
     "mm_kernels_fir.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_fir.cuh", "mm_htaps.h"],
     "mm_kernels_mc.cu": HDRS,
 }

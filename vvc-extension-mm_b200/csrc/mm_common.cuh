@@ -161,6 +161,15 @@ __device__ __forceinline__ MmSub mm_sub_from_index(int w, int h, int s)
   return r;
 }
 
+// Zero-fill rule of xPredInterBlkMM (InterPrediction.cpp:780) and xMVReprojectionInterpolation (InterSearch.cpp:6332):
+//   xPos < -maxCU || yPos < -maxCU || xPos >= refBuf.width + maxCU - sbW || yPos >= refBuf.height + maxCU - sbH
+// refBuf.width/height and the sub-block size are unsigned (SizeType), so the two upper-bound comparisons are unsigned: a
+// negative position converts to a huge value and is "beyond" the bound -- the slack exists on the right/bottom only.
+__device__ __forceinline__ bool mm_oob(int xP, int yP, int picW, int picH, int mcw, int mch, int sbw, int sbh)
+{
+  return xP < -mcw || yP < -mch || (uint32_t)xP >= (uint32_t)(picW + mcw - sbw) || (uint32_t)yP >= (uint32_t)(picH + mch - sbh);
+}
+
 enum { MM_MODE_DIST = 0, MM_MODE_PRED = 1 };
 #define MM_POS_OOB ((int32_t)0x80000000)  // k_map -> k_fir: sub-block outside the picture, prediction := 0
 
@@ -185,6 +194,7 @@ void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy
 void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model, int2* pos);
 // FIR + distortion (or prediction write-out) of items [first, first+count)
 void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, const int2* pos);
+void mmk_tan_selftest(cudaStream_t s, uint32_t stride, unsigned long long* out);
 void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my, int xoff);
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi);

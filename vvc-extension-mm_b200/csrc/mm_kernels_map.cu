@@ -204,12 +204,46 @@ __global__ void __launch_bounds__(32 * MM_MAP_WARPS, MM_MAP_MINBLOCKS) k_map(con
         mm_subblock_prepare(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, 0, 0, 0, it.x, it.y, bw, bh, c, R, s.row, s.col, &st);
       mm_subblock_apply(P.g, model, 0, 0, 0, c, R, st, &fx, &fy);
       const int xP = fx >> 4, yP = fy >> 4;
-      if (xP < -mc || yP < -mc || xP >= P.picW + mc - 4 || yP >= P.picH + mc - 4) fx = MM_POS_OOB;
+      if (mm_oob(xP, yP, P.picW, P.picH, mc, mc, 4, 4)) fx = MM_POS_OOB;
     }
     key = make_int4(it.x, it.y, (int)it.wh, (int)it.rmr);
     keySb = it.sb;
     pos[(long)warp * 32 + lane] = make_int2(fx, fy);
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_tan_selftest: checksum of (x, float(sin((double)x)), float(cos((double)x))) over every `stride`-th float of
+// |x| <= float(pi/2) -- the same sum oracle/tools/tan_exceptions.cpp prints for glibc (MM_TAN_SWEEP_CHECKSUM for stride 1).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mm_tan_mix(uint32_t x, uint32_t s, uint32_t c)
+{
+  unsigned long long h = 0x9e3779b97f4a7c15ull * (unsigned long long)(x + 1u);
+  h ^= (unsigned long long)s * 0xc2b2ae3d27d4eb4full;
+  h = (h << 31) | (h >> 33);
+  h ^= (unsigned long long)c * 0x165667b19e3779f9ull;
+  return h * 0xff51afd7ed558ccdull;
+}
+__global__ void k_tan_selftest(uint32_t stride, unsigned long long* out)
+{
+  const unsigned long long maxBits = 0x3fc90fdbull;
+  const unsigned long long n = maxBits / stride + 1;
+  unsigned long long sum = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (unsigned long long)gridDim.x * blockDim.x)
+  {
+    const int sign = i >= n;
+    const unsigned long long m = (sign ? i - n : i) * stride;
+    if (sign && m == 0) continue;
+    const uint32_t xb = (uint32_t)m | (sign ? 0x80000000u : 0u);
+    const float x = __uint_as_float(xb);
+    sum += mm_tan_mix(xb, __float_as_uint(mm_sin_d2f(x)), __float_as_uint(mm_cos_d2f(x)));
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, sum);
+}
+void mmk_tan_selftest(cudaStream_t s, uint32_t stride, unsigned long long* out)
+{
+  k_tan_selftest<<<148 * 8, 256, 0, s>>>(stride, out);
 }
 
 #ifndef MM_CS_THREADS

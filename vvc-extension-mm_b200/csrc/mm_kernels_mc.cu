@@ -42,7 +42,7 @@ __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy
     const int picw = P.picW >> csx, pich = P.picH >> csy;
     const int mcw = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csx);
     const int mch = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csy);
-    if (xP < -mcw || yP < -mch || xP >= picw + mcw - sbw || yP >= pich + mch - sbh)
+    if (mm_oob(xP, yP, picw, pich, mcw, mch, sbw, sbh))
     {
       for (int r = 0; r < sbh; ++r)
         for (int q = 0; q < sbw; ++q) d[r * dstStride + q] = 0;
@@ -82,7 +82,7 @@ __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, i
     const int picw = P.picW >> csx, pich = P.picH >> csy;
     const int mcw = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csx);
     const int mch = (P.oobMode == MMGPU_OOB_ME) ? 0 : (P.maxCU >> csy);
-    if (xP < -mcw || yP < -mch || xP >= picw + mcw - sbw || yP >= pich + mch - sbh)
+    if (mm_oob(xP, yP, picw, pich, mcw, mch, sbw, sbh))
     {
       for (int i = 0; i < 16; ++i) out[i] = 0;
       return;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) k_dmvr(const MmParams P, const mmgpu_dmvr
   int fx, fy;
   mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, sp.model, 0, 0, 0, sp.x, sp.y, sp.w, sp.h, c, R, row, col, &fx, &fy);
   const int xP = fx >> 4, yP = fy >> 4;
-  const bool oob = (xP < -P.maxCU || yP < -P.maxCU || xP >= P.picW + P.maxCU - 4 || yP >= P.picH + P.maxCU - 4);
+  const bool oob = mm_oob(xP, yP, P.picW, P.picH, P.maxCU, P.maxCU, 4, 4);
   int pred[16];
   if (oob)
   {

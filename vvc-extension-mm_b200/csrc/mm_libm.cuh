@@ -721,3 +721,49 @@ MM_HD float mm_roundf(float x)
   const float one = MM_U2F((MM_F2U(x) & 0x80000000u) | 0x3f800000u);
   return (mm_fabsf(d) >= 0.5f) ? MM_FADD(t, one) : t;
 }
+
+// ------------------------------------------------------------------------------------------
+// float(sin((double)x)), float(cos((double)x)) for |x| <= pi/2 -- the two block constants of
+// TangentialMotionModel.cpp:27-28,38,40, where the unqualified sin/cos bind to the DOUBLE libm
+// overloads.  Host: glibc.  Device: CUDA's double sin/cos (<= 2 ulp) agree with glibc's
+// (<= 1 ulp) after narrowing unless the double result lies within a few ulp of a float rounding
+// breakpoint; exactly those inputs -- found by sweeping all 2^31 floats of the domain on the host
+// (oracle/tools/tan_exceptions.cpp, guard 8 ulp) -- are answered from a table.  The GPU test
+// test_tan_double_sincos_exhaustive re-checks the whole domain against the sweep's checksum.
+// ------------------------------------------------------------------------------------------
+#include "mm_tan_exceptions.h"
+#if defined(__CUDA_ARCH__)
+struct MmTanExc { uint32_t x, r; };
+__device__ __forceinline__ bool mm_d2f_risky(double d)
+{
+  // would a value 4 ulp(double) below / above narrow to a different float?
+  const long long b = __double_as_longlong(d);
+  return __double2float_rn(__longlong_as_double(b - 4)) != __double2float_rn(__longlong_as_double(b + 4));
+}
+static __device__ __noinline__ float mm_tan_exc_lookup(const MmTanExc* t, int n, float x, float fallback)
+{
+  const uint32_t xb = __float_as_uint(x);
+  for (int i = 0; i < n; ++i)
+    if (t[i].x == xb) return __uint_as_float(t[i].r);
+  return fallback;
+}
+__device__ __forceinline__ float mm_sin_d2f(float x)
+{
+  const MmTanExc exc[MM_TAN_EXC_SIN_N] = MM_TAN_EXC_SIN_INIT;
+  const double d = sin((double)x);
+  const float f = __double2float_rn(d);
+  if (d != 0.0 && mm_d2f_risky(d)) return mm_tan_exc_lookup(exc, MM_TAN_EXC_SIN_N, x, f);
+  return f;
+}
+__device__ __forceinline__ float mm_cos_d2f(float x)
+{
+  const MmTanExc exc[MM_TAN_EXC_COS_N] = MM_TAN_EXC_COS_INIT;
+  const double d = cos((double)x);
+  const float f = __double2float_rn(d);
+  if (d != 0.0 && mm_d2f_risky(d)) return mm_tan_exc_lookup(exc, MM_TAN_EXC_COS_N, x, f);
+  return f;
+}
+#else
+static inline float mm_sin_d2f(float x) { return (float)sin((double)x); }
+static inline float mm_cos_d2f(float x) { return (float)cos((double)x); }
+#endif

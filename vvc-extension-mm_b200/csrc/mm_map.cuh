@@ -291,10 +291,10 @@ MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int 
     mm_sc_cart_to_sph(cc, sc);
     const float epsC = MM_D2F(MM_DSUB(0x1.921fb54442d18p+0, (double)sc[1]));
     c->p[0] = sc[2];
-    // unqualified sin()/cos() on a float bind to the double libm overloads in the reference (R4);
-    // float(double sin) differs between correct libms only with probability ~2^-28 per value.
-    c->p[1] = MM_D2F(sin((double)epsC));
-    c->p[2] = MM_D2F(cos((double)epsC));
+    // unqualified sin()/cos() on a float bind to the double libm overloads in the reference (R4): narrowed glibc
+    // results, reproduced exactly on the device (mm_libm.cuh: mm_sin_d2f / mm_cos_d2f)
+    c->p[1] = mm_sin_d2f(epsC);
+    c->p[2] = mm_cos_d2f(epsC);
     c->p[3] = MM_FMUL(mvY, g.angRes);
     c->p[4] = MM_FMUL(mvX, g.angRes);
   }

@@ -642,6 +642,21 @@ static int checkBlockShape(mmgpu_ctx* ctx, int comp, int fmt, int x, int y, int 
   return MMGPU_OK;
 }
 
+extern "C" int mmgpu_selftest_tan_sincos(mmgpu_ctx* ctx, uint32_t stride, uint64_t* checksum)
+{
+  if (!ctx || !checksum || stride == 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  int rc = ensureCap(ctx, &ctx->dDist, &ctx->capDist, 1);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->dDist, 0, sizeof(unsigned long long), ctx->stream));
+  mmk_tan_selftest(ctx->stream, stride, ctx->dDist);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(checksum, ctx->dDist, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
 // ---- a1 ------------------------------------------------------------------------------------------
 extern "C" int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
                                int rot_slot, int32_t* out_x, int32_t* out_y)
