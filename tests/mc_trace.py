@@ -34,8 +34,41 @@ def read_trace(path):
             dst = np.frombuffer(data, dtype=np.int16, count=m["w"] * m["h"], offset=off).reshape(m["h"], m["w"]).copy()
             off += 2 * m["w"] * m["h"]
             yield ("M", m, dst)
+        elif tag == ord("O"):
+            v = struct.unpack_from("<8i3f4i", data, off)
+            off += 8 * 4 + 12 + 16
+            keys = ("x", "y", "w", "h", "ref_poc", "wrap", "model", "cur_poc")
+            m = dict(zip(keys, v[:8]))
+            m["epipole"] = v[8:11]
+            m["had"], m["sub_shift"], m["clp_min"], m["clp_max"] = v[11:15]
+            org = np.frombuffer(data, dtype=np.int16, count=m["w"] * m["h"], offset=off).reshape(m["h"], m["w"]).copy()
+            off += 2 * m["w"] * m["h"]
+            yield ("O", m, org)
+        elif tag == ord("E"):
+            hor, ver, shift = struct.unpack_from("<3i", data, off)
+            (dist,) = struct.unpack_from("<Q", data, off + 12)
+            off += 20
+            yield ("E", hor, ver, shift, dist)
         else:
             raise ValueError("bad record tag %r at %d" % (tag, off - 4))
+
+
+def searches(path):
+    """Groups the ME records: yields (header dict, org block, [(hor, ver, shift, dist), ...]) per dumped search, and the
+    reference pictures seen so far as a dict {(poc, wrap): [planes]} (shared, updated while iterating)."""
+    refs = {}
+    cur = None
+    for rec in read_trace(path):
+        if rec[0] == "R":
+            refs[(rec[1], rec[2])] = rec[3]
+        elif rec[0] == "O":
+            if cur:
+                yield cur + (refs,)
+            cur = (rec[1], rec[2], [])
+        elif rec[0] == "E" and cur:
+            cur[2].append(rec[1:])
+    if cur:
+        yield cur + (refs,)
 
 
 def pad_planes(planes, margin, fmt, wrap_offset=0):
@@ -65,6 +98,8 @@ def replay_oracle(path, pic_w, pic_h, margin=288, max_cu=128, limit=None, verbos
             _, poc, wrap, planes = rec
             refs[(poc, wrap)] = pad_planes(planes, margin, 1, pic_w if wrap else 0)
             continue
+        if rec[0] != "M":
+            continue
         _, m, dst = rec
         if m["model"] == ol.GED_CAMPOSE and m["epipole"] != last_e:
             o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(m["epipole"]))
@@ -84,8 +119,42 @@ def replay_oracle(path, pic_w, pic_h, margin=288, max_cu=128, limit=None, verbos
     return n, bad, first
 
 
+def replay_me_oracle(path, pic_w, pic_h, margin=288, verbose=False):
+    """Distortions of every dumped ME candidate through the oracle; returns (searches, candidates, mismatches)."""
+    o = ol.Oracle(pic_w, pic_h)
+    padded = {}
+    ns = nc = bad = 0
+    last_e = None
+    for hdr, org, cands, refs in searches(path):
+        key = (hdr["ref_poc"], hdr["wrap"])
+        if key not in padded or padded[key][0] is not refs[key]:
+            padded[key] = (refs[key], pad_planes(refs[key], margin, 1, pic_w if hdr["wrap"] else 0))
+        pl = padded[key][1][0]
+        if hdr["model"] == ol.GED_CAMPOSE and hdr["epipole"] != last_e:
+            o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(hdr["epipole"]))
+            last_e = hdr["epipole"]
+        ns += 1
+        by_shift = {}
+        for hor, ver, shift, dist in cands:
+            by_shift.setdefault(shift, []).append((hor, ver, dist))
+        for shift, lst in by_shift.items():
+            mvs = np.array([(a, b) for a, b, _ in lst], dtype=np.int32)
+            exp = np.array([d for _, _, d in lst], dtype=np.uint64)
+            got = o.me_block(pl, org, None, (hdr["x"], hdr["y"]), (hdr["w"], hdr["h"]), hdr["model"], mvs, mv_prec_shift=shift,
+                             dist=ol.DIST_HAD if hdr["had"] else ol.DIST_SAD, sub_shift=hdr["sub_shift"], had_mode=ol.HAD_SIMD,
+                             clp=(hdr["clp_min"], hdr["clp_max"]))
+            nc += len(lst)
+            nb = int((got != exp).sum())
+            bad += nb
+            if nb and verbose:
+                i = int(np.nonzero(got != exp)[0][0])
+                print("ME MISMATCH", hdr, "mv", mvs[i], "shift", shift, "ref", int(exp[i]), "oracle", int(got[i]))
+    return ns, nc, bad
+
+
 if __name__ == "__main__":
     import sys
+    print("ME searches, candidates, mismatches:", replay_me_oracle(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), verbose=True))
     n, bad, first = replay_oracle(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), verbose=True)
     print("calls", n, "mismatches", bad)
     if first:
