@@ -655,7 +655,10 @@ void orc_mc_block_classic(const int16_t* ref, int rs, int comp, int chroma_fmt, 
    * xFrac = mv.hor & mask, yFrac likewise, refBuf offset = mv >> shift; filterHor/filterVer as for MM. */
   const int csx = scale_x(comp, chroma_fmt), csy = scale_y(comp, chroma_fmt);
   const int shH = 4 + csx, shV = 4 + csy;
-  const int xF = mv_hor & ((1 << shH) - 1), yF = mv_ver & ((1 << shV) - 1);
+  /* :960-971: luma phase = mv & 15; chroma phase = mv * (1 << (1 - scale)) & 31 -- the chroma table always has 32 phases,
+   * so for an un-subsampled direction (4:4:4, 4:2:2 vertical) the 1/16 fraction is doubled */
+  const int xF = (comp == 0) ? (mv_hor & 15) : ((mv_hor * (1 << (1 - csx))) & 31);
+  const int yF = (comp == 0) ? (mv_ver & 15) : ((mv_ver * (1 << (1 - csy))) & 31);
   const int xI = mv_hor >> shH, yI = mv_ver >> shV;
   const int is_luma = comp == 0, rnd = !bi, taps = is_luma ? 8 : 4;
   const int16_t* p = ref + (long)(pos_y + yI) * rs + (pos_x + xI);

@@ -5,7 +5,7 @@ compiled unchanged against the Eigen stand-in, oracle/vtm.mk) on a synthetic ERP
 families active, and by the MMGPU_DUMP mode of the patched app running the reference's CPU path (tests/golden/make_e2e_golden.py):
 
   CPU tests   the oracle reproduces what the reference computed IN SITU: 12 485 xPredInterBlkMM calls (all models, Y/Cb/Cr)
-              and 36 100 motion-search candidates (SAD + Hadamard through the reference's SIMD distFunc) of a real encode.
+              and 22 587 motion-search candidates (SAD + Hadamard through the reference's SIMD distFunc) of a real encode.
   GPU tests   libmmgpu.so reproduces the same through the C ABI; the patched DecoderApp (GPU MC) decodes the stock bitstream
               with 0 MD5 errors and byte-identical YUV; the patched EncoderApp (GPU MC + GPU candidate evaluation, the
               reference's own search control flow) emits a byte-identical bitstream.
@@ -89,7 +89,7 @@ def test_oracle_equals_reference_encoder_me_in_situ(trace):
             assert np.array_equal(got, dist[sel]), h
             n += int(sel.sum())
             had += int(sel.sum()) if h["had"] else 0
-    assert n > 36000 and had > 1000
+    assert n > 20000 and had > 1000
 
 
 # ---- GPU ----------------------------------------------------------------------------------------------------------------
@@ -138,7 +138,7 @@ def test_gpu_equals_reference_encoder_me_in_situ(trace, gpu_small):
                              sub_shift=h["sub_shift"], clp=(h["clp_min"], h["clp_max"]))
             assert np.array_equal(got, dist[sel]), h
             n += int(sel.sum())
-    assert n > 36000
+    assert n > 20000
 
 
 def _apps():

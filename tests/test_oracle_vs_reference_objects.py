@@ -100,3 +100,32 @@ def test_dmvr_cost_equals_reference_objects(level):
             got = ol.lib().orc_dmvr_cost(a.ctypes.data, w, b.ctypes.data, w, w, h, 1 if level else 0)
             assert exp == got, (w, h, rep, level)
     rl.init(-1)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_classic_chroma_phase_equals_reference_filters(fmt):
+    """xPredInterBlk (InterPrediction.cpp:960-1096): chroma phase = mv * (1 << (1 - scale)) & 31, integer offset = mv >> (4 + scale);
+    the expectation is built from the reference's own filterHor/filterVer objects with that formula (4:2:0, 4:2:2, 4:4:4)."""
+    rl.init(-1)
+    rng = np.random.default_rng(70 + fmt)
+    csx = 1 if fmt in (1, 2) else 0
+    csy = 1 if fmt == 1 else 0
+    ref = rng.integers(0, 1024, size=(96, 128)).astype(np.int16)
+    x0, y0, w, h = 40, 32, 8, 8
+    for mv in [(0, 0), (5, 0), (0, 7), (13, 9), (-21, 30), (31, -17), (16, 16), (8, 24)]:
+        xF = (mv[0] * (1 << (1 - csx))) & 31
+        yF = (mv[1] * (1 << (1 - csy))) & 31
+        xI, yI = mv[0] >> (4 + csx), mv[1] >> (4 + csy)
+        px, py = x0 + xI, y0 + yI
+        if yF == 0:
+            exp = rl.filter_hor(1, ref, px, py, w, h, xF, 1)
+        elif xF == 0:
+            exp = rl.filter_ver(1, ref, px, py, w, h, yF, 1, 1)
+        else:
+            tmp = np.zeros((h + 3, 128), dtype=np.int16)
+            tmp[:, :w] = rl.filter_hor(1, ref, px, py - 1, w, h + 3, xF, 0)
+            exp = rl.filter_ver(1, tmp, 0, 1, w, h, yF, 0, 1)
+        dst = np.zeros((h, w), dtype=np.int16)
+        ol.lib().orc_mc_block_classic(ref.ctypes.data, ref.shape[1], 1, fmt, x0, y0, w, h, mv[0], mv[1], 0, 10, 0, 1023,
+                                      dst.ctypes.data, w)
+        assert np.array_equal(dst, exp), (fmt, mv)

@@ -12,6 +12,18 @@ __device__ __forceinline__ void mm_classic_keep_inside(const MmParams& P, int cs
   *fy = min(max(*fy, -mgy << shV), ((P.picH >> csy) + mgy) << shV);
 }
 
+// xPredInterBlk (InterPrediction.cpp:968-971): chroma phase = mv * (1 << (1 - scale)) & 31 -- the chroma filter table always has
+// 32 phases, so the 1/16 fraction of an un-subsampled direction (4:4:4, 4:2:2 vertical) is doubled.  xPredInterBlkMM passes
+// its raw fraction (InterPrediction.cpp:730-733), so this applies to the classic model only.
+__device__ __forceinline__ void mm_classic_chroma_phase(int model, int comp, int csx, int csy, int* xF, int* yF)
+{
+  if (model == MM_CLASSIC && comp != 0)
+  {
+    *xF <<= (1 - csx);
+    *yF <<= (1 - csy);
+  }
+}
+
 // One thread per sub-block of ONE block (mmgpu_mc).  model == CLASSIC: one MV for the block (xPredInterBlk).
 __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                              int model, int rotSlot, int bi, int16_t* dst, int dstStride)
@@ -49,7 +61,9 @@ __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy
       return;
     }
   }
-  const int xP = fx >> shH, yP = fy >> shV, xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  const int xP = fx >> shH, yP = fy >> shV;
+  int xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  mm_classic_chroma_phase(model, comp, csx, csy, &xF, &yF);
   if (comp == 0)
     mm_fir_generic<8>(P.fir, ref.plane00[0], ref.stride[0], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, d, dstStride);
   else
@@ -88,7 +102,9 @@ __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, i
       return;
     }
   }
-  const int xP = fx >> shH, yP = fy >> shV, xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  const int xP = fx >> shH, yP = fy >> shV;
+  int xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
+  mm_classic_chroma_phase(model, comp, csx, csy, &xF, &yF);
   if (comp == 0)
     mm_fir_generic<8>(P.fir, ref.plane00[0], ref.stride[0], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
   else

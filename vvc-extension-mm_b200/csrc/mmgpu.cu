@@ -26,6 +26,8 @@ struct mmgpu_plan
   int32_t* dItemBase;
   int2* dPos;  // 1/16-pel position of every (candidate, sub-block) entry: k_map -> k_fir
   int modelFirst[MM_NUM_MODELS], modelCount[MM_NUM_MODELS];  // work items of each motion model (contiguous)
+  int orgMaxX, orgMaxY;   // max(org_x + w), max(org_y + h) over the blocks: checked against the org plane at launch
+  int maxCandCount;       // largest cand_count of a block (mmgpu_mc_batch_device wants exactly one MV per block)
   size_t capBlocks, capItems, capCands, capCandParams, capItemBase, capPos;
 };
 
@@ -109,7 +111,7 @@ struct mmgpu_ctx
   uint64_t evAccumN;
 };
 
-static std::string g_createErr;
+static thread_local std::string g_createErr;   // error text of the last failed mmgpu_create of this thread
 
 static int fail(mmgpu_ctx* c, int code, const std::string& msg)
 {
@@ -154,6 +156,7 @@ static MmParams baseParams(mmgpu_ctx* ctx)
   return P;
 }
 
+extern "C" void mmgpu_destroy(mmgpu_ctx* ctx);
 extern "C" const char* mmgpu_last_error(const mmgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
 
 extern "C" void mmgpu_rodrigues(const float e[3], float R[9])
@@ -201,6 +204,20 @@ extern "C" float mmgpu_fixed_to_float(int32_t fixed, int32_t precision)
   return (float)(fixed >> precision) + (float)(fixed & ((1 << precision) - 1)) / (float)(1 << precision);
 }
 
+// inside mmgpu_create a failing CUDA call must not leak the half-built context, and its message must be readable through
+// mmgpu_last_error(NULL)
+#define CUC(call)                                                                                          \
+  do                                                                                                       \
+  {                                                                                                        \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+    {                                                                                                      \
+      const std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+      cudaGetLastError();                                                                                  \
+      mmgpu_destroy(ctx);                                                                                  \
+      return fail(nullptr, MMGPU_ERR_CUDA, m_);                                                            \
+    }                                                                                                      \
+  } while (0)
 extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
 {
   mmgpu_ctx* ctx = nullptr;
@@ -209,6 +226,15 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     return fail(nullptr, MMGPU_ERR_ARG, "picture size must be a positive multiple of 8");
   if (cfg->bit_depth < 8 || cfg->bit_depth > 10) return fail(nullptr, MMGPU_ERR_ARG, "bit_depth must be 8..10");
   if (cfg->max_refs <= 0 || cfg->max_refs > 1024) return fail(nullptr, MMGPU_ERR_ARG, "max_refs out of range");
+  if (cfg->chroma_fmt < 0 || cfg->chroma_fmt > 3) return fail(nullptr, MMGPU_ERR_ARG, "chroma_fmt must be 0..3 (400, 420, 422, 444)");
+  if (!pow2(cfg->max_cu) || cfg->max_cu < 16 || cfg->max_cu > 128) return fail(nullptr, MMGPU_ERR_ARG, "max_cu must be 16, 32, 64 or 128");
+  // memory safety of the kernels: the PRED zero-fill rule lets a position reach picW + max_cu, the 8-tap window adds 4+4 and
+  // the wide row loads up to 12 more samples; classic MVs are held inside margin - 16.  8-byte row loads and the TMA
+  // descriptors need plane (0,0) = base + margin on a 4-sample boundary for luma and chroma alike.
+  if (cfg->margin < cfg->max_cu + 16 || (cfg->margin & 7))
+    return fail(nullptr, MMGPU_ERR_ARG, "margin must be a multiple of 8 and >= max_cu + 16 (the reference uses 2 * (max_cu + 16))");
+  if (cfg->ged_flavor != 0 && cfg->ged_flavor != 1) return fail(nullptr, MMGPU_ERR_ARG, "ged_flavor must be 0 or 1");
+  if (cfg->had_mode > MMGPU_HAD_SIMD) return fail(nullptr, MMGPU_ERR_ARG, "bad had_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -258,16 +284,16 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
   f.off1l = 32;
   f.cpShift = hr;
 
-  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&ctx->readStream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&ctx->prepStream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&ctx->stage.freeEv, cudaEventDisableTiming));
+  CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&ctx->readStream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&ctx->prepStream, cudaStreamNonBlocking));
+  CUC(cudaEventCreateWithFlags(&ctx->stage.freeEv, cudaEventDisableTiming));
   ctx->hRefs.assign(cfg->max_refs, MmRef());
   ctx->ownedPlanes.assign((size_t)cfg->max_refs * 3, nullptr);
-  CU(cudaMalloc(&ctx->dRefs, sizeof(MmRef) * cfg->max_refs));
-  CU(cudaMemset(ctx->dRefs, 0, sizeof(MmRef) * cfg->max_refs));
-  CU(cudaMalloc(&ctx->dRot, sizeof(float) * 9 * (MM_ROT_USER0 + MM_MAX_ROT)));
+  CUC(cudaMalloc(&ctx->dRefs, sizeof(MmRef) * cfg->max_refs));
+  CUC(cudaMemset(ctx->dRefs, 0, sizeof(MmRef) * cfg->max_refs));
+  CUC(cudaMalloc(&ctx->dRot, sizeof(float) * 9 * (MM_ROT_USER0 + MM_MAX_ROT)));
   {
     std::vector<float> rot(9 * (MM_ROT_USER0 + MM_MAX_ROT));
     const float ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1}, e0[3] = {0, 0, 0};
@@ -275,20 +301,20 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     mmgpu_rodrigues(ey, &rot[9]);
     mmgpu_rodrigues(ez, &rot[18]);
     for (int s = 0; s < MM_MAX_ROT; ++s) mmgpu_rodrigues(e0, &rot[9 * (MM_ROT_USER0 + s)]);  // EpipoleList.h:15-17
-    CU(cudaMemcpy(ctx->dRot, rot.data(), rot.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(ctx->dRot, rot.data(), rot.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   const int n4 = g.rows4 * g.cols4;
   for (int m = 0; m < 3; ++m)
   {
-    CU(cudaMalloc(&ctx->dMpa[m], sizeof(float2) * n4));
-    CU(cudaMalloc(&ctx->dMpaVip[m], n4));
+    CUC(cudaMalloc(&ctx->dMpa[m], sizeof(float2) * n4));
+    CUC(cudaMalloc(&ctx->dMpaVip[m], n4));
     mmk_mpa_cache(ctx->stream, g, m + 1, ctx->dMpa[m], ctx->dMpaVip[m]);
     ctx->launches++;
   }
   for (int v = 0; v < 2; ++v)
   {
-    CU(cudaMalloc(&ctx->dThTab[v], sizeof(float2) * g.rows4));
-    CU(cudaMalloc(&ctx->dPhTab[v], sizeof(float2) * g.cols4));
+    CUC(cudaMalloc(&ctx->dThTab[v], sizeof(float2) * g.rows4));
+    CUC(cudaMalloc(&ctx->dPhTab[v], sizeof(float2) * g.cols4));
   }
   {
     cudaDriverEntryPointQueryResult qres;
@@ -297,19 +323,19 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
         qres != cudaDriverEntryPointSuccess)
       ctx->encodeTiled = nullptr;   // no descriptors: k_fir gathers from global memory
     cudaGetLastError();
-    CU(cudaMalloc(&ctx->dTmaps, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
-    CU(cudaMemset(ctx->dTmaps, 0, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
+    CUC(cudaMalloc(&ctx->dTmaps, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
+    CUC(cudaMemset(ctx->dTmaps, 0, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
   }
   {
     std::vector<uint32_t> ht(MM_HTAPS_WORDS);
     mm_build_htaps(ht.data(), h_lumaFilter);
-    CU(cudaMalloc(&ctx->dHTaps, sizeof(uint32_t) * MM_HTAPS_WORDS));
-    CU(cudaMemcpy(ctx->dHTaps, ht.data(), sizeof(uint32_t) * MM_HTAPS_WORDS, cudaMemcpyHostToDevice));
+    CUC(cudaMalloc(&ctx->dHTaps, sizeof(uint32_t) * MM_HTAPS_WORDS));
+    CUC(cudaMemcpy(ctx->dHTaps, ht.data(), sizeof(uint32_t) * MM_HTAPS_WORDS, cudaMemcpyHostToDevice));
   }
   mmk_trig_tables(ctx->stream, g, ctx->dThTab[0], ctx->dThTab[1], ctx->dPhTab[0], ctx->dPhTab[1]);
   ctx->launches++;
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(ctx->stream));
+  CUC(cudaGetLastError());
+  CUC(cudaStreamSynchronize(ctx->stream));
   *out = ctx;
   return MMGPU_OK;
 }
@@ -333,7 +359,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto p : ctx->ownedPlanes) cudaFree(p);
   cudaFree(ctx->dRefs);
   cudaFree(ctx->dRot);
@@ -347,10 +373,10 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dDist);
   cudaFree(ctx->dTmp);
   if (ctx->stage.h) cudaFreeHost(ctx->stage.h);
-  cudaEventDestroy(ctx->stage.freeEv);
-  cudaStreamSynchronize(ctx->copyStream);
-  cudaStreamSynchronize(ctx->readStream);
-  cudaStreamSynchronize(ctx->prepStream);
+  if (ctx->stage.freeEv) cudaEventDestroy(ctx->stage.freeEv);
+  if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
+  if (ctx->readStream) cudaStreamSynchronize(ctx->readStream);
+  if (ctx->prepStream) cudaStreamSynchronize(ctx->prepStream);
   for (int i = 0; i < MM_MAX_INFLIGHT; ++i)
   {
     MmSlot& sl = ctx->slots[i];
@@ -366,15 +392,16 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
     cudaFree(sl.dDist);
     cudaFree(sl.dOrg);
   }
-  cudaStreamDestroy(ctx->copyStream);
-  cudaStreamDestroy(ctx->readStream);
-  cudaStreamDestroy(ctx->prepStream);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  if (ctx->readStream) cudaStreamDestroy(ctx->readStream);
+  if (ctx->prepStream) cudaStreamDestroy(ctx->prepStream);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
   cudaFree(ctx->dJobs);
   for (int c = 0; c < 3; ++c) cudaFree(ctx->dPic[c]);
   for (auto e : ctx->evPool) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   delete ctx;
 }
 
@@ -491,7 +518,9 @@ static int makeTmaps(mmgpu_ctx* ctx, int slot, MmRef* r)
                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return MMGPU_OK;   // not encodable: gather path
   }
-  CU(cudaMemcpy(ctx->dTmaps + (size_t)slot * MM_TMA_TYPES, maps, sizeof(maps), cudaMemcpyHostToDevice));
+  // ordered behind the kernels already queued on the context's stream (a batch in flight keeps the descriptors it was
+  // launched with); `maps` is pageable memory: the call returns once it has been staged
+  CU(cudaMemcpyAsync(ctx->dTmaps + (size_t)slot * MM_TMA_TYPES, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
   r->tma = 1;
   return MMGPU_OK;
 }
@@ -500,8 +529,9 @@ static int publishRef(mmgpu_ctx* ctx, int slot)
 {
   int rc = makeTmaps(ctx, slot, &ctx->hRefs[slot]);
   if (rc) return rc;
+  // stream-ordered like the descriptors; hRefs[slot] is pageable memory (staged before the call returns), so the
+  // registration does not stall the host behind the kernels of the previous frame
   CU(cudaMemcpyAsync(ctx->dRefs + slot, &ctx->hRefs[slot], sizeof(MmRef), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));  // hRefs may change right after
   return MMGPU_OK;
 }
 
@@ -664,6 +694,7 @@ extern "C" int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, 
   if (!ctx || !out_x || !out_y) return MMGPU_ERR_ARG;
   if (model <= MMGPU_CLASSIC || model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "reproject: model must be a non-classic motion model");
   if (comp < 0 || comp > 2 || rot_slot < 0 || rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad comp/rot_slot");
+  if (comp != 0 && chroma_fmt != ctx->cfg.chroma_fmt) return fail(ctx, MMGPU_ERR_ARG, "chroma_fmt differs from the context's");
   int rc = checkBlockShape(ctx, comp, chroma_fmt, x, y, w, h);
   if (rc) return rc;
   cudaSetDevice(ctx->cfg.device);
@@ -690,6 +721,7 @@ extern "C" int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, 
   if (!ctx || !dst) return MMGPU_ERR_ARG;
   if (model < MMGPU_CLASSIC || model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "bad model");
   if (comp < 0 || comp > 2 || rot_slot < 0 || rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad comp/rot_slot");
+  if (comp != 0 && chroma_fmt != ctx->cfg.chroma_fmt) return fail(ctx, MMGPU_ERR_ARG, "chroma_fmt differs from the context's");
   if (ref_slot < 0 || ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[ref_slot].plane00[comp])
     return fail(ctx, MMGPU_ERR_STATE, "reference slot not set");
   int rc = checkBlockShape(ctx, comp, chroma_fmt, x, y, w, h);
@@ -774,6 +806,7 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   long modelItems[MM_NUM_MODELS] = {0};
   uint64_t samples = 0;
   long candSum = 0;
+  int orgMaxX = 0, orgMaxY = 0, maxCand = 0;
   for (int bi = 0; bi < n_blocks; ++bi)
   {
     const mmgpu_block& b = blocks[bi];
@@ -785,8 +818,12 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
     if (b.cand_count < 0 || b.cand_first < 0 || (long)b.cand_first + b.cand_count > n_cands)
       return fail(ctx, MMGPU_ERR_ARG, "candidate range outside the mv array");
     if (b.org_x < 0 || b.org_y < 0 || b.org_x > 0xffff || b.org_y > 0xffff) return fail(ctx, MMGPU_ERR_ARG, "org_x / org_y must be in 0..65535");
-    if (needOrg && ((b.org_x & 3) || b.org_x + b.w > orgW || b.org_y + b.h > orgH))
-      return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane (or org_x not a multiple of 4)");
+    if (b.org_x & 3) return fail(ctx, MMGPU_ERR_ARG, "org_x must be a multiple of 4 (8-byte loads of the original block)");
+    if (needOrg && (b.org_x + b.w > orgW || b.org_y + b.h > orgH))
+      return fail(ctx, MMGPU_ERR_ARG, "org block outside the org plane");
+    orgMaxX = std::max(orgMaxX, b.org_x + b.w);
+    orgMaxY = std::max(orgMaxY, b.org_y + b.h);
+    maxCand = std::max(maxCand, b.cand_count);
     const int n = (b.w >> 2) * (b.h >> 2);
     const int nItems = (n >= 32) ? b.cand_count * (n >> 5) : (b.cand_count + (32 / n) - 1) / (32 / n);
     itemBase[bi] = nItems;
@@ -845,6 +882,9 @@ static int buildPlan(mmgpu_ctx* ctx, mmgpu_plan* p, int n_blocks, const mmgpu_bl
   p->nCands = n_cands;
   p->nItems = (int)total;
   p->samples = samples;
+  p->orgMaxX = orgMaxX;
+  p->orgMaxY = orgMaxY;
+  p->maxCandCount = maxCand;
   return MMGPU_OK;
 }
 
@@ -934,6 +974,8 @@ extern "C" int mmgpu_me_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, con
   if (!ctx->dOrg) return fail(ctx, MMGPU_ERR_STATE, "mmgpu_set_org* has not been called");
   if (dist_kind != MMGPU_DIST_SAD && dist_kind != MMGPU_DIST_HAD) return fail(ctx, MMGPU_ERR_ARG, "bad dist_kind");
   if (sub_shift < 0 || sub_shift > 2 || (dist_kind == MMGPU_DIST_HAD && sub_shift != 0)) return fail(ctx, MMGPU_ERR_ARG, "bad sub_shift");
+  if (plan->orgMaxX > ctx->orgW || plan->orgMaxY > ctx->orgH)
+    return fail(ctx, MMGPU_ERR_ARG, "a block of the plan lies outside the current org plane (mmgpu_set_org*)");
   cudaSetDevice(ctx->cfg.device);
   return launchMe(ctx, plan, d_mvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max,
                   reinterpret_cast<unsigned long long*>(d_dist), nullptr, 0);
@@ -944,6 +986,8 @@ extern "C" int mmgpu_mc_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, con
 {
   if (!ctx || !plan || !d_mvs || !d_dst) return MMGPU_ERR_ARG;
   if (((uintptr_t)d_dst & 7) || (dst_stride & 3)) return fail(ctx, MMGPU_ERR_ARG, "dst must be 8-byte aligned, stride a multiple of 4");
+  if (plan->maxCandCount != 1)
+    return fail(ctx, MMGPU_ERR_ARG, "mmgpu_mc_batch_device wants exactly one MV per block (every candidate writes the block's destination)");
   cudaSetDevice(ctx->cfg.device);
   return launchMe(ctx, plan, d_mvs, mv_prec_shift, MM_MODE_PRED, 0, 0, clp_min, clp_max, nullptr, d_dst, dst_stride);
 }
@@ -1002,11 +1046,21 @@ extern "C" int mmgpu_me_batch_submit(mmgpu_ctx* ctx, int slot, const int16_t* or
   CU(cudaMemcpy2DAsync(sl->dOrg, 2 * (size_t)pitch, org, 2 * (size_t)org_stride, 2 * (size_t)org_w, org_h, cudaMemcpyHostToDevice,
                        ctx->copyStream));
   CU(cudaMemcpyAsync(sl->dMvs, mvs, sizeof(mmgpu_mv) * n_cands, cudaMemcpyHostToDevice, ctx->copyStream));
-  if ((rc = buildPlan(ctx, &sl->plan, n_blocks, blocks, n_cands, org_w, org_h, &sl->stage, ctx->copyStream, ctx->prepStream, sl->copied)))
+  rc = buildPlan(ctx, &sl->plan, n_blocks, blocks, n_cands, org_w, org_h, &sl->stage, ctx->copyStream, ctx->prepStream, sl->copied);
+  if (!rc)
+    rc = launchMe(ctx, &sl->plan, sl->dMvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max, sl->dDist, nullptr, 0,
+                  sl->dOrg, pitch, ctx->prepStream, sl->prepared);
+  if (rc)
+  {
+    // copies of this batch may already be queued: drain them so that the caller's buffers are free again
+    const std::string msg = ctx->err;
+    cudaStreamSynchronize(ctx->copyStream);
+    cudaStreamSynchronize(ctx->prepStream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    ctx->err = msg;
     return rc;
-  if ((rc = launchMe(ctx, &sl->plan, sl->dMvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max, sl->dDist, nullptr,
-                     0, sl->dOrg, pitch, ctx->prepStream, sl->prepared)))
-    return rc;
+  }
   CU(cudaEventRecord(sl->computed, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->readStream, sl->computed, 0));
   CU(cudaMemcpyAsync(dist, sl->dDist, sizeof(uint64_t) * n_cands, cudaMemcpyDeviceToHost, ctx->readStream));
