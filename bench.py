@@ -28,13 +28,9 @@ sys.path.insert(0, ROOT)
 
 W, H, CTU = 2048, 1024, 128
 CANDS = 16
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fir<DIST> launch of this workload, from the committed
-# `ncu --set full` capture (profiles/ncu_k_map_k_fir_r01h_summary.csv: 27.660800 MB read + 0 B written).
-NCU_TRAFFIC_BYTES = 27660800
-# smsp__inst_executed.sum of one k_fir<DIST> / k_map launch of this workload (same capture): what the kernels are really
-# bound by is instruction issue (1 warp-instruction per clock per SM sub-partition), so the bench line also reports the
-# fraction of that ceiling the measured kernel times correspond to.
-NCU_INST = {"k_fir": 70810370, "k_map": 41275039}
+# DRAM bytes and executed warp-instructions of one k_map / k_fir<DIST> launch of this workload come from the committed ncu
+# capture (profiles/ncu_counts.json, written by tools/ncu_counts.py) and are used only while the kernel sources are the ones
+# that capture was taken with (SHA-256 of csrc/ in the file); otherwise the line carries null for them.
 POOL = 32            # synthetic frames resident per GPU (references cycle through them: 270 MB > L2)
 MV_RANGE = 64
 EPIPOLE = (1.0, 0.0, 0.0)
@@ -89,75 +85,152 @@ class ClockSampler:
                 "samples": len(rows), "samples_under_load": len(busy)}
 
 
-def cpu_oracle_throughput(n_threads, budget_s, seed=1):
-    """Reference CPU arm / cpu_baseline: the oracle's xMVReprojectionInterpolation + xGetHADs on the same workload."""
+def cpu_workload(seed=1):
+    """The frame batch of one step on the host: oracle context, padded reference, original, blocks, MVs."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     from vvc_extension_mm_b200 import workload as wl
-    from concurrent.futures import ThreadPoolExecutor
-    o = ol.Oracle(W, H)
-    o.set_rotation(ol.GED_CAMPOSE, ol.Oracle.rodrigues(list(EPIPOLE)))
     ref = wl.pad_frame(wl.synth_frame(W, H, seed), 288, 1)
     cur = wl.synth_frame(W, H, seed + 1, shift=(3.0, 1.0))
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=seed, cands_per_block=CANDS, mv_range=MV_RANGE, models=models())
+    return ol, ref, cur, blocks, mvs, prec
+
+
+def oracle_distortions(ref, org, blocks, mvs, prec, n_threads, epipole=EPIPOLE):
+    """Distortions of a whole batch through the CPU oracle (the checker), multi-threaded over blocks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from concurrent.futures import ThreadPoolExecutor
+    R = ol.Oracle.rodrigues(list(epipole))
+    out = np.zeros(len(mvs), dtype=np.uint64)
+    tls = threading.local()
 
     class P:
         pass
     pl = P()
-    pl.origin, pl.stride = ref[0].origin, ref[0].stride
-    blocks, mvs, prec = wl.frame_batch(W, H, seed=seed, cands_per_block=CANDS, mv_range=MV_RANGE, models=models())
+    pl.origin, pl.stride = ref.origin, ref.stride
 
     def run_block(b):
-        sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
-        org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+        if not hasattr(tls, "o"):
+            tls.o = ol.Oracle(W, H)
+            tls.o.set_rotation(ol.GED_CAMPOSE, R)
+        sl = slice(int(b["cand_first"]), int(b["cand_first"]) + int(b["cand_count"]))
+        o_y, o_x = int(b["org_y"]), int(b["org_x"])
+        blk = org[o_y:o_y + int(b["h"]), o_x:o_x + int(b["w"])]
         m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
-        o.me_block(pl, org, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
-                   mv_prec_shift=prec, dist=ol.DIST_HAD, had_mode=ol.HAD_SIMD)
-        return int(b["w"]) * int(b["h"]) * int(b["cand_count"])
+        out[sl] = tls.o.me_block(pl, blk, None, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), int(b["model"]), m,
+                                 mv_prec_shift=prec, dist=ol.DIST_HAD, had_mode=ol.HAD_SIMD)
 
-    # bounded sample: whole blocks of the frame, in order, until the time budget is used (ctypes releases the GIL)
-    t0 = time.perf_counter()
-    done = 0
-    nblk = 0
-    chunk = 64 * n_threads
     with ThreadPoolExecutor(max_workers=n_threads) as ex:
-        i = 0
-        while time.perf_counter() - t0 < budget_s:
-            part = [blocks[(i + k) % len(blocks)] for k in range(chunk)]
-            done += sum(ex.map(run_block, part))
-            nblk += chunk
-            i += chunk
+        list(ex.map(run_block, blocks))
+    return out
+
+
+_REFBENCH = os.path.join(ROOT, "oracle", "_ref", "librefbench.so")
+
+
+def cpu_reference_throughput(n_threads, budget_s, seed=1):
+    """CPU arm: the reference's per-candidate loop xMVReprojectionInterpolation + distFunc on the same frame batch.
+    oracle/_ref/librefbench.so (kind "reference": the reference's own compiled InterpolationFilter / RdCost AVX2 code for
+    the interpolation and the Hadamard SATD, driven per 4x4 like InterSearch.cpp:6330-6380; the float mapping is the C
+    restatement because Eigen is absent) when it was built, else the pure oracle port (kind "port").
+    Returns (sample-candidates/s, kind, description of the sample)."""
+    import ctypes as C
+    ol, ref, cur, blocks, mvs, prec = cpu_workload(seed)
+    org = np.ascontiguousarray(cur[0])
+    if os.path.exists(_REFBENCH):
+        L = C.CDLL(_REFBENCH)
+        L.refbench_run.restype = C.c_double
+        L.refbench_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        cfg = ol.OrcCfg(W, H, 1, 128, 1.0, 1, 10)
+        R = ol.Oracle.rodrigues(list(EPIPOLE))
+        b = np.ascontiguousarray(blocks)
+        m = np.ascontiguousarray(mvs)
+        stats = np.zeros(5)
+        v = L.refbench_run(C.byref(cfg), R.ctypes.data, ref[0].origin, ref[0].stride, org.ctypes.data, org.strides[0] // 2,
+                           b.ctypes.data, len(b), m.ctypes.data, prec, 1, n_threads, float(budget_s), None, stats.ctypes.data)
+        tot = max(1e-9, stats[2] + stats[3] + stats[4])
+        desc = ("%d whole blocks of the same frame batch in %.1f s on %d thread(s); reference's compiled AVX2 filterHor/filterVer + "
+                "setDistParam/distFunc per candidate, C restatement of the Eigen mapping (time split: mapping %.0f%%, interpolation "
+                "%.0f%%, distortion %.0f%%)" % (int(stats[1]), stats[0], n_threads, 100 * stats[2] / tot, 100 * stats[3] / tot,
+                                                  100 * stats[4] / tot))
+        return float(v), "reference", desc, float(stats[0])
+    t0 = time.perf_counter()
+    done = nblk = 0
+    step = 64 * n_threads
+    i = 0
+    while time.perf_counter() - t0 < budget_s:
+        part = blocks[[(i + k) % len(blocks) for k in range(step)]].copy()
+        first = 0
+        for q in part:
+            first += int(q["cand_count"])
+        oracle_distortions(ref[0], org, part, mvs, prec, n_threads)
+        done += int((part["w"].astype(np.int64) * part["h"] * part["cand_count"]).sum())
+        nblk += step
+        i += step
     dt = time.perf_counter() - t0
-    return done / dt, dt, nblk, done
+    return done / dt, "port", "%d whole blocks of the same frame batch in %.1f s, oracle port, %d thread(s)" % (nblk, dt, n_threads), dt
+
+
+def bench_config(N, blocks_per_rank=None, cands_per_rank=None, samples=None, parallelism="1 gpu"):
+    """config keys shared by both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "frames_per_step": N, "blocks_per_rank": blocks_per_rank, "candidates_per_rank": cands_per_rank,
+            "sample_candidates_per_step": samples,
+            "l2": "references cycle through %d resident frames (%.0f MB of luma planes > 126 MB L2)" % (POOL, POOL * 8.4),
+            "parallelism": parallelism}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference itself cannot be built on
-    this image (Eigen 3.3.7 is fetched from the network at build time), so this times the oracle port with every
-    host thread it can use; rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path on all host threads; rank 0 only."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     vals = []
+    kind, desc = "port", ""
     for s in range(args.warmup + args.steps):
-        v, dt, nblk, done = cpu_oracle_throughput(cores, per_step, seed=1 + s)
+        v, kind, desc, dt = cpu_reference_throughput(cores, per_step, seed=1 + (s % 4))
         if s >= args.warmup:
-            vals.append((v, dt, done))
-    tot_s = sum(d for _, d, _ in vals)
-    tot_n = sum(n for _, _, n in vals)
-    value = tot_n / tot_s
+            vals.append((v, dt))
+    tot_s = sum(d for _, d in vals)
+    value = sum(v * d for v, d in vals) / max(1e-9, tot_s)
+    from vvc_extension_mm_b200 import workload as wl
+    blocks, mvs, _ = wl.frame_batch(W, H, seed=1, cands_per_block=CANDS, mv_range=MV_RANGE, models=models())
+    samples = float((blocks["w"].astype(np.int64) * blocks["h"] * blocks["cand_count"]).sum())
     line = {
         "impl": "reference", "metric": "multi-model MC+SATD luma samples/sec at 2048x1024 ERP", "value": value,
         "unit": "luma sample-candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference path (reference not buildable: Eigen absent)"},
-        "cpu_baseline": {"value": value, "unit": "luma sample-candidates/s", "cores": cores, "kind": "port",
-                         "sample": "%.1f s of whole blocks of the frame batch per step, %d threads" % (per_step, cores)},
+        "config": bench_config(1, int(len(blocks)), int(len(mvs)), samples),
+        "cpu_baseline": {"value": value, "unit": "luma sample-candidates/s", "cores": cores, "kind": kind,
+                         "sample": "per step: " + desc},
         "e2e": {"value": value, "unit": "luma sample-candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_source_hash():
+    import hashlib
+    d = os.path.join(ROOT, "vvc-extension-mm_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def ncu_counts():
+    """Instruction / DRAM-byte counts of one k_map and one k_fir launch of this workload from the committed ncu capture,
+    valid only for the kernel sources they were captured with."""
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "ncu_counts.json")))
+        return c if c.get("csrc_sha256") == kernel_source_hash() and "MMGPU_LIB" not in os.environ else None
+    except Exception:
+        return None
 
 
 def main():
@@ -168,6 +241,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure")
+    ap.add_argument("--no-parity-check", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -403,18 +478,38 @@ def main():
     gpu.me_batch_wait(0)
     if not np.array_equal(chk_dev, h_dist2[0].numpy().view(np.uint64)):
         raise SystemExit("bench self-check failed: e2e distortions differ from the device-resident path")
+    # parity of the TIMED batch: every distortion of step 0 (this rank's blocks of all N frames) against the CPU oracle
+    parity = None
+    if not args.no_parity_check:
+        exp = np.zeros(n_cands, dtype=np.uint64)
+        for f in range(N):
+            sel = (blocks["org_y"] // H) == f
+            if not sel.any():
+                continue
+            bf = blocks[sel].copy()
+            bf["org_y"] -= f * H
+            fr = (0 * N + f) % POOL
+            planes = geo if fr == 0 else wl.pad_frame(wl.synth_frame(W, H, seed=100 + fr, shift=(0.37 * fr, 0.11 * fr)), 288, 1)
+            exp += oracle_distortions(planes[0], pool_org_h[(f + 1) % POOL].numpy(), bf, mvs, prec, os.cpu_count() or 1)
+        bad = int((exp != chk_dev).sum())
+        parity = {"distortions_checked": int(n_cands), "mismatches": bad, "checker": "CPU oracle (oracle/mm_oracle.c), step 0 of the timed batch"}
+        if bad:
+            raise SystemExit("bench parity check failed on rank %d: %d of %d distortions differ from the oracle" % (rank, bad, n_cands))
     barrier()
     e2e_dev_ms, e2e_wall_ms = timed(e2e_step, args.steps, lambda s: None, e2e_drain)
+    # sustained leg: back-to-back device-resident steps for about args.sustain seconds (clock samples fall inside it)
+    sus_steps = max(args.steps, int(args.sustain * 1000.0 / max(1e-3, dev_ms / args.steps)))
+    sus_ms, _ = timed(device_step, sus_steps, lambda s: None)
     clocks = sampler.stop()
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
 
-    t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms, kmap_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms, kmap_ms, sus_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, k_ms, kmap_ms = float(tmax[0]), float(tmax[1]), float(tmax[4]), float(tmax[5])
+        dev_ms, e2e_ms, k_ms, kmap_ms, sus_ms = float(tmax[0]), float(tmax[1]), float(tmax[4]), float(tmax[5]), float(tmax[6])
         samples_all, bytes_all = float(tsum[2]), float(tsum[3])
     else:
         samples_all, bytes_all = float(samples_rank), float(alg_bytes_rank)
@@ -435,38 +530,41 @@ def main():
         path_achieved = (alg_bytes_rank / 1e9) / (path_ms / 1000.0) if path_ms > 0 else 0.0
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965)
         n_smsp = 4 * torch.cuda.get_device_properties(local).multi_processor_count
-        issue = {"unit": "warp-instructions/clk/SMSP", "peak": 1.0,
-                 "k_fir": NCU_INST["k_fir"] / (k_avg_ms * 1e-3 * sm_hz * n_smsp) if k_avg_ms > 0 else None,
-                 "k_map": NCU_INST["k_map"] / (kmap_avg_ms * 1e-3 * sm_hz * n_smsp) if kmap_avg_ms > 0 else None,
-                 "note": "instruction counts from the committed ncu capture of one launch (profiles/), times measured live"}
+        counts = ncu_counts() if N == 1 else None
+        issue = None
+        if counts and k_avg_ms > 0 and kmap_avg_ms > 0:
+            issue = {"unit": "warp-instructions/clk/SMSP", "peak": 1.0,
+                     "k_fir": counts["k_fir"]["inst_executed"] / (k_avg_ms * 1e-3 * sm_hz * n_smsp),
+                     "k_map": counts["k_map"]["inst_executed"] / (kmap_avg_ms * 1e-3 * sm_hz * n_smsp),
+                     "note": "instruction counts from the committed ncu capture of one launch (%s), times measured live" % counts.get("source")}
         cpu = None
-        if not args.no_cpu_baseline:
-            v, dt, nblk, done = cpu_oracle_throughput(1, args.cpu_budget)
-            cpu = {"value": v, "unit": "luma sample-candidates/s", "cores": 1, "kind": "port",
-                   "sample": "%d whole blocks (%.2e sample-candidates) of the same frame batch, %.1f s, oracle port, 1 thread" % (nblk, done, dt)}
+        if not args.no_cpu_baseline and N == 1:
+            v, kind, desc, dt = cpu_reference_throughput(1, args.cpu_budget)
+            cpu = {"value": v, "unit": "luma sample-candidates/s", "cores": 1, "kind": kind, "sample": desc}
         h2d = int(h_org.numel() * 2 + h_blocks.numel() * 4 + h_mvs.numel() * 4)
         line = {
             "metric": "multi-model MC+SATD luma samples/sec at 2048x1024 ERP", "value": value,
             "unit": "luma sample-candidates/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": N, "blocks_per_rank": int(len(blocks)),
-                       "candidates_per_rank": int(n_cands), "sample_candidates_per_step": samples_all,
-                       "l2": "references cycle through %d resident frames (%.0f MB of luma planes > 126 MB L2)" % (POOL, POOL * 8.4),
-                       "parallelism": ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each, one owner rank each) reach "
-                                       "every GPU %s, prefetched one step ahead on a second stream"
-                                       % (N, N, pic_bytes / 1e6, "by copy-engine pulls from symmetric (peer) memory over NVLink"
-                                          if exchange.mode == "p2p" else "by one ncclAllGather")) if N > 1 else "1 gpu"},
+            "config": bench_config(N, int(len(blocks)), int(n_cands), samples_all,
+                                   ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each, one owner rank each) reach "
+                                    "every GPU %s, prefetched one step ahead on a second stream"
+                                    % (N, N, pic_bytes / 1e6, "by copy-engine pulls from symmetric (peer) memory over NVLink"
+                                       if exchange.mode == "p2p" else "by one ncclAllGather")) if N > 1 else "1 gpu"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
+                         "traffic": counts["k_fir"]["dram_bytes"] if counts else None, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
                          "path": {"kernels": "k_map + k_fir<DIST>", "k_map_ms": kmap_avg_ms, "ms": path_ms,
                                   "achieved": path_achieved, "frac": path_achieved / peak},
-                         "algorithmic_bytes_per_launch": alg_bytes_rank, "issue": issue if N == 1 else None,
+                         "algorithmic_bytes_per_launch": alg_bytes_rank, "issue": issue,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "luma sample-candidates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(h_dist.numel() * 8), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "parity": parity,
+            "sustained": {"seconds": sus_ms / 1000.0, "steps": sus_steps, "ms_per_step": sus_ms / sus_steps,
+                          "value": samples_all * sus_steps / (sus_ms / 1000.0)},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -184,6 +184,17 @@ int mmgpu_me_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv
 /* number of luma sample-candidates (sum over blocks of w*h*cand_count) a plan evaluates */
 uint64_t mmgpu_plan_samples(const mmgpu_plan* plan);
 
+/* The same candidate set against SEVERAL reference pictures (the reference loops iRefIdxTemp over the same block and search
+ * pattern, InterSearch.cpp:2695-...; the positions of MPA / ROT / TAN / 3DT do not depend on the reference picture, those of
+ * GEODESIC_CAMPOSE only through the epipole of the (current, reference) POC pair): the float mapping (k_map) runs once per
+ * distinct rotation slot, the interpolation + distortion (k_fir) once per reference.  ref_slots[r] replaces every block's
+ * ref_slot, rot_slots[r] every block's rot_slot (NULL: keep the blocks' own); d_dist holds n_refs * n_cands distortions,
+ * reference-major.  Device pointers for d_mvs / d_dist, host pointers for the slot lists; asynchronous like
+ * mmgpu_me_batch_device. */
+int mmgpu_me_batch_device_multiref(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int dist_kind,
+                                   int sub_shift, int clp_min, int clp_max, int n_refs, const int32_t* ref_slots,
+                                   const int32_t* rot_slots, uint64_t* d_dist);
+
 /* MC of a whole batch (one MV per block: the first candidate), predictions written into a device picture
  * buffer at (x,y): final-MC / merge-candidate shape of the path (EncCu.cpp:2375-2600). */
 int mmgpu_mc_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift, int clp_min,

@@ -59,6 +59,16 @@ int main()
     bad += e[4] != pk(c[3], c[4], c[5], c[6]);
     bad += e[5] != pk(c[7], 0, 0, 0);
   }
+  for (int o = 0; o < 4; ++o)      // the shifted base words k_fir derives at run time == the table words
+    for (int ph = 0; ph < 16; ++ph)
+      for (int j = 0; j < 4; ++j)
+      {
+        uint32_t w[3];
+        mm_htaps_shift(t[ph * 12 + 0], t[ph * 12 + 1], o + (j & 1), w);
+        const uint32_t* c = t + ((o * 16 + ph) * 4 + j) * 3;
+        bad += (w[0] != c[0]) + (w[1] != c[1]) + (w[2] != c[2]);
+        ++n;
+      }
   printf("htaps: %ld cases, %ld mismatches\n", n, bad);
   return bad ? 1 : 0;
 }

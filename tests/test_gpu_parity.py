@@ -674,3 +674,33 @@ def test_tan_double_sincos_exhaustive(env):
                                "-o", tool, "-lm"])
     host = int(subprocess.check_output([tool, "sum", "97"]).decode().strip(), 16)
     assert g.selftest_tan_sincos(97) == host
+
+
+def test_multi_reference_batch_equals_single_reference_calls(env):
+    """mmgpu_me_batch_device_multiref: one float mapping (per distinct GEODESIC_CAMPOSE rotation), one interpolation +
+    distortion pass per reference picture == the plain call repeated with the blocks' ref_slot / rot_slot rewritten."""
+    import torch
+    o, g, planes, ref, cur = env
+    refs = []
+    for f in range(3):
+        pp = wl.pad_frame(wl.synth_frame(W, H, seed=40 + f, shift=(0.5 * f, 0.25 * f)), 288, 1)
+        g.set_ref(1 + f, 10 + f, [p.origin for p in pp], [p.stride for p in pp])
+        refs.append(pp)
+    g.set_rotation(1, mm.rodrigues([0.1, 0.9, -0.2]))
+    g.set_org(cur[0])
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=9, cands_per_block=5, mv_range=32, models=(1, 2, 3, 4, 5, 6, 10), ctu_rows=[1, 5])
+    plan = g.plan(blocks, len(mvs))
+    dm = torch.from_numpy(mvs.view(np.int32).reshape(-1, 2).copy()).cuda()
+    ref_slots, rot_slots = [1, 2, 3, 0], [0, 1, 0, 1]
+    dd = torch.zeros(len(ref_slots) * len(mvs), dtype=torch.int64, device="cuda")
+    for dist in (mm.DIST_SAD, mm.DIST_HAD):
+        g.me_batch_device_multiref(plan, dm.data_ptr(), dd.data_ptr(), ref_slots, rot_slots, mv_prec_shift=prec, dist=dist)
+        g.sync()
+        got = dd.cpu().numpy().view(np.uint64).reshape(len(ref_slots), len(mvs))
+        for r, (rs, ro) in enumerate(zip(ref_slots, rot_slots)):
+            b = blocks.copy()
+            b["ref_slot"] = rs
+            b["rot_slot"] = ro
+            exp = g.me_batch(b, mvs, mv_prec_shift=prec, dist=dist)
+            assert np.array_equal(got[r], exp), (dist, r)
+    assert len({tuple(x) for x in got}) == len(ref_slots)   # the four references really give different distortions

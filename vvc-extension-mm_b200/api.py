@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref",
 ]
 
 
@@ -99,6 +99,7 @@ def load_library():
     L.mmgpu_plan_create.argtypes = [vp, i32, vp, i32, C.POINTER(vp)]
     L.mmgpu_plan_destroy.argtypes = [vp]
     L.mmgpu_me_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.mmgpu_me_batch_device_multiref.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.mmgpu_plan_samples.restype = u64
     L.mmgpu_plan_samples.argtypes = [vp]
     L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
@@ -338,6 +339,14 @@ class MmGpu:
     def me_batch_device(self, plan, d_mvs, d_dist, mv_prec_shift=4, dist=DIST_SAD, sub_shift=0, clp=(0, 1023)):
         self._chk(self.L.mmgpu_me_batch_device(self.h, plan.h, _ptr(d_mvs), mv_prec_shift, dist, sub_shift, clp[0],
                                                clp[1], _ptr(d_dist)))
+
+    def me_batch_device_multiref(self, plan, d_mvs, d_dist, ref_slots, rot_slots=None, mv_prec_shift=4, dist=DIST_SAD, sub_shift=0,
+                                 clp=(0, 1023)):
+        """One mapping, len(ref_slots) interpolation + distortion passes; d_dist: len(ref_slots) * n_cands uint64, reference-major."""
+        rs = (C.c_int32 * len(ref_slots))(*[int(v) for v in ref_slots])
+        ro = (C.c_int32 * len(ref_slots))(*[int(v) for v in rot_slots]) if rot_slots is not None else None
+        self._chk(self.L.mmgpu_me_batch_device_multiref(self.h, plan.h, _ptr(d_mvs), mv_prec_shift, dist, sub_shift, clp[0], clp[1],
+                                                        len(ref_slots), rs, ro, _ptr(d_dist)))
 
     def mc_batch_device(self, plan, d_mvs, d_dst, dst_stride, mv_prec_shift=4, clp=(0, 1023)):
         self._chk(self.L.mmgpu_mc_batch_device(self.h, plan.h, _ptr(d_mvs), mv_prec_shift, clp[0], clp[1], _ptr(d_dst),

@@ -89,6 +89,8 @@ struct MmParams
   int32_t clpMin, clpMax;
   int32_t picW, picH, maxCU;
   int32_t oobMode;
+  int32_t refOverride;       // >= 0: every item reads this reference slot (multi-reference batches), else the item's own
+  int32_t rotOverride;       // >= 0: every GEODESIC_CAMPOSE block uses this rotation slot
   unsigned long long* dist;
   int16_t* dst;
   int32_t dstStride;
@@ -187,7 +189,7 @@ void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* i
                      int32_t* candBlock);
 // dist != nullptr: also zeroes the per-candidate distortion accumulators
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
-                    int mvShift, const float* rot, int nCands, MmCand* out, unsigned long long* dist);
+                    int mvShift, const float* rot, int rotOverride, int nCands, MmCand* out, unsigned long long* dist);
 void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                    int model, int rotSlot, int32_t* outX, int32_t* outY);
 // positions of items [first, first+count) of P.items; model >= 0: all of them use that motion model

@@ -196,6 +196,7 @@ __device__ __forceinline__ void mm_fir_luma4x4(const MmFir& f, const MmTaps* tap
 // Entry o = 0 also holds the vertical pass' words: j=0 -> (a0,a1,0), j=1 -> (b0,b1,b2) of MmTaps.
 // -------------------------------------------------------------------------------------------------
 #include "mm_htaps.h"
+__device__ __forceinline__ uint32_t mm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ int mm_fir6(int v0, int v1, int v2, int v3, int v4, int v5, uint32_t c0, uint32_t c1, uint32_t c2,
                                        int init)
@@ -204,32 +205,47 @@ __device__ __forceinline__ int mm_fir6(int v0, int v1, int v2, int v3, int v4, i
          __dp2a_lo(v4, (int)c2, __dp2a_hi(v5, (int)c2, init))))));
 }
 
-// htaps: the coefficient table in global memory (3 KB, L1 resident); `base` = 8-byte word holding sample (xPos-3)&~3 of row yPos-3, `qstride` = row stride in
-// 8-byte words.  SMEM = false: global memory (read-only path); SMEM = true: a TMA-filled box in shared memory.
+// cx, cy: the base words (C0, C1) of the horizontal / vertical phase (compact 128-byte table behind the alignment-folded one:
+// one 8-byte load per lane each); the six alignment-folded words of the lane are funnel shifts of cx (mm_htaps.h:
+// mm_htaps_shift; even outputs sh = o, odd outputs sh = o + 1).  `base` = 8-byte word holding sample (xPos-3)&~3 of row
+// yPos-3, `qstride` = row stride in 8-byte words.  SMEM = false: global memory (read-only path); SMEM = true: a TMA-filled
+// box in shared memory.  Samples 12,13 of the aligned row are touched only for alignments 2 and 3: the fourth load of a row
+// is predicated on that.
 template <bool BI, bool SMEM>
-__device__ __forceinline__ void mm_fir_luma4x4_wide_core(const MmFir& f, const uint32_t* htaps, const uint2* base, int qstride,
+__device__ __forceinline__ void mm_fir_luma4x4_wide_core(const MmFir& f, uint2 cx, uint2 cy, const uint2* base, int qstride,
                                                          int a, int xFrac, int yFrac, int lo, int hi, int* pred)
 {
-  const uint4* e = reinterpret_cast<const uint4*>(htaps + (((a & 3) * 16 + xFrac) * 12));
-  const uint4 e0 = __ldg(e), e1 = __ldg(e + 1), e2 = __ldg(e + 2);   // c[j][m] = word j*3+m: e0 = c00 c01 c02 c10, e1 = c11 c12 c20 c21, e2 = c22 c30 c31 c32
+  const unsigned she = 8u * (unsigned)(a & 3), sho = she + 8u;
+  const uint32_t e0 = __funnelshift_lc(0u, cx.x, she), e1 = __funnelshift_lc(cx.x, cx.y, she), e2 = __funnelshift_lc(cx.y, 0u, she);
+  const uint32_t o0 = __funnelshift_lc(0u, cx.x, sho), o1 = __funnelshift_lc(cx.x, cx.y, sho), o2 = __funnelshift_lc(cx.y, 0u, sho);
+  const int needTail = (a & 3) >= 2;
   int P[6][4];  // vertical pairs of first-pass rows, per column
   int hprev[4];
 #pragma unroll
   for (int r = 0; r < 11; ++r)
   {
     const uint2* rowp = SMEM ? (base + r * qstride) : (base + (long)r * qstride);
-    uint2 q0, q1, q2, q3;
+    uint2 q0, q1, q2;
+    uint32_t q3 = 0;
 #ifdef MM_ABL_NOLOAD   // ablation build only (tools/): no reference loads
-    q0 = make_uint2(r + a, yFrac); q1 = make_uint2(a, r ^ xFrac); q2 = q0; q3 = q1;
+    q0 = make_uint2(r + a, yFrac); q1 = make_uint2(a, r ^ xFrac); q2 = q0; q3 = q1.x;
     (void)rowp;
 #else
-    if (SMEM) { q0 = rowp[0]; q1 = rowp[1]; q2 = rowp[2]; q3.x = reinterpret_cast<const uint32_t*>(rowp + 3)[0]; q3.y = 0; }
-    else { q0 = __ldg(rowp + 0); q1 = __ldg(rowp + 1); q2 = __ldg(rowp + 2); q3 = __ldg(rowp + 3); }
+    if (SMEM)
+    {
+      q0 = rowp[0]; q1 = rowp[1]; q2 = rowp[2];
+      asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p ld.shared.b32 %0, [%1];\n}" : "+r"(q3) : "r"(mm_smem_u32(rowp + 3)), "r"(needTail));
+    }
+    else
+    {
+      q0 = __ldg(rowp + 0); q1 = __ldg(rowp + 1); q2 = __ldg(rowp + 2);
+      asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %2, 0;\n@p ld.global.nc.b32 %0, [%1];\n}" : "+r"(q3) : "l"(rowp + 3), "r"(needTail));
+    }
 #endif
-    int h0 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0.x, e0.y, e0.z, f.off1);
-    int h1 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0.w, e1.x, e1.y, f.off1);
-    int h2 = mm_fir6((int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, (int)q3.x, e1.z, e1.w, e2.x, f.off1);
-    int h3 = mm_fir6((int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, (int)q3.x, e2.y, e2.z, e2.w, f.off1);
+    int h0 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, e0, e1, e2, f.off1);
+    int h1 = mm_fir6((int)q0.x, (int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, o0, o1, o2, f.off1);
+    int h2 = mm_fir6((int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, (int)q3, e0, e1, e2, f.off1);
+    int h3 = mm_fir6((int)q0.y, (int)q1.x, (int)q1.y, (int)q2.x, (int)q2.y, (int)q3, o0, o1, o2, f.off1);
     h0 >>= f.shift1; h1 >>= f.shift1; h2 >>= f.shift1; h3 >>= f.shift1;
     if (r & 1)
     {
@@ -247,28 +263,26 @@ __device__ __forceinline__ void mm_fir_luma4x4_wide_core(const MmFir& f, const u
       hprev[0] = h0; hprev[1] = h1; hprev[2] = h2; hprev[3] = h3;
     }
   }
-  const uint32_t* ev = htaps + yFrac * 12;   // entry o = 0: words 0,1 = a0,a1; 3,4,5 = b0,b1,b2
-  MmTaps tv;
-  tv.a0 = (int)__ldg(ev); tv.a1 = (int)__ldg(ev + 1); tv.b0 = (int)__ldg(ev + 3); tv.b1 = (int)__ldg(ev + 4);
-  tv.b2 = (int)__ldg(ev + 5);
+  MmTaps tv;   // vertical pass: (a0, a1) = the base words, (b0, b1, b2) = the same moved up by one byte
+  tv.a0 = (int)cy.x; tv.a1 = (int)cy.y;
+  tv.b0 = (int)__funnelshift_lc(0u, cy.x, 8u); tv.b1 = (int)__funnelshift_lc(cy.x, cy.y, 8u); tv.b2 = (int)__funnelshift_lc(cy.y, 0u, 8u);
   mm_fir_vpass<BI>(f, P, tv, (xFrac | yFrac) == 0, lo, hi, pred);
 }
 
 // ref plane 8-byte aligned with a stride that is a multiple of 4 samples
 template <bool BI>
-__device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, const uint32_t* htaps, const int16_t* __restrict__ ref,
+__device__ __forceinline__ void mm_fir_luma4x4_wide(const MmFir& f, uint2 cx, uint2 cy, const int16_t* __restrict__ ref,
                                                     int stride, int xPos, int yPos, int xFrac, int yFrac, int lo, int hi,
                                                     int* pred)
 {
   const int a = xPos - 3;
   const uint2* base = reinterpret_cast<const uint2*>(ref + (long)(yPos - 3) * stride + (a & ~3));
-  mm_fir_luma4x4_wide_core<BI, false>(f, htaps, base, stride >> 2, a, xFrac, yFrac, lo, hi, pred);
+  mm_fir_luma4x4_wide_core<BI, false>(f, cx, cy, base, stride >> 2, a, xFrac, yFrac, lo, hi, pred);
 }
 
 // -------------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives (sm_100a) used by k_fir to stage a box of the reference plane in shared memory
 // -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mm_mbar_init(unsigned long long* bar, int count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mm_smem_u32(bar)), "r"(count));

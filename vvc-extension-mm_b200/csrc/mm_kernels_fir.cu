@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   __shared__ __align__(128) unsigned char s_box[MM_FIR_WARPS][MM_TMA_BOX_BYTES];
   __shared__ __align__(8) unsigned long long s_bar[MM_FIR_WARPS];
 #endif
-  const uint32_t* htaps = P.hTaps;   // 3 KB coefficient table, L1 resident: no per-CTA prologue, no barrier
+  const uint2* btaps = reinterpret_cast<const uint2*>(P.hTaps + MM_HTAPS_WORDS);   // (C0, C1) of the 16 phases: one 128-byte line
   const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w0 >= count) return;
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   else { cand = it.cand + lane / n; sb = lane % n; }
   const bool valid = cand < it.candEnd;
   const MmSub s = mm_sub_from_index(bw, bh, sb);
-  const MmRef ref = P.refs[it.rmr & 0xffff];
+  const int refSlot = (P.refOverride >= 0) ? P.refOverride : (int)(it.rmr & 0xffff);
+  const MmRef ref = P.refs[refSlot];
   const int16_t* orgp = P.org + (long)((int)(it.orgxy >> 16) + s.row * 4) * P.orgStride + ((int)(it.orgxy & 0xffff) + s.col * 4);
 
   // Reference samples.  The 32 windows of a warp (11 rows x 14 samples each, neighbours overlapping by 2/3) lie inside a
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
     {
       mm_mbar_init(bar, 1);
       mm_mbar_expect_tx(bar, (uint32_t)(bxw * bxh * 2));
-      const char* tmap = reinterpret_cast<const char*>(P.tmaps) + ((size_t)(it.rmr & 0xffff) * MM_TMA_TYPES + boxType) * 128;
+      const char* tmap = reinterpret_cast<const char*>(P.tmaps) + ((size_t)refSlot * MM_TMA_TYPES + boxType) * 128;
       mm_tma_load_2d(s_box[threadIdx.x >> 5], tmap, x0 + P.tmaOffX, y0 + P.tmaOffY, bar);
     }
     __syncwarp();
@@ -102,13 +103,14 @@ __global__ void __launch_bounds__(32 * MM_FIR_WARPS, MM_FIR_MINBLOCKS) k_fir(con
   else if (boxType >= 0)
   {
     const uint2* base = reinterpret_cast<const uint2*>(s_box[threadIdx.x >> 5]) + (ay - y0) * pitchQ + ((ax - x0) >> 2);
-    mm_fir_luma4x4_wide_core<false, true>(P.fir, htaps, base, pitchQ, xP - 3, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax, pred);
+    mm_fir_luma4x4_wide_core<false, true>(P.fir, __ldg(btaps + (fp.x & 15)), __ldg(btaps + (fp.y & 15)), base, pitchQ, xP - 3, fp.x & 15,
+                                          fp.y & 15, P.clpMin, P.clpMax, pred);
   }
 #endif
   else
   {
-    mm_fir_luma4x4_wide<false>(P.fir, htaps, ref.plane00[0], ref.stride[0], xP, yP, fp.x & 15, fp.y & 15, P.clpMin, P.clpMax,
-                               pred);
+    mm_fir_luma4x4_wide<false>(P.fir, __ldg(btaps + (fp.x & 15)), __ldg(btaps + (fp.y & 15)), ref.plane00[0], ref.stride[0], xP, yP,
+                               fp.x & 15, fp.y & 15, P.clpMin, P.clpMax, pred);
   }
 
   if (MODE == MM_MODE_PRED)

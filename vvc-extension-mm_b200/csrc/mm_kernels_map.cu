@@ -93,8 +93,8 @@ __global__ void k_build_items(const mmgpu_block* __restrict__ blocks, const int3
 // k_cand_setup: one thread per candidate MV
 // -------------------------------------------------------------------------------------------------
 __global__ void k_cand_setup(MmGeom g, const mmgpu_block* __restrict__ blocks, const int32_t* __restrict__ candBlock,
-                             const mmgpu_mv* __restrict__ mvs, int mvShift, const float* __restrict__ rot, int nCands,
-                             MmCand* __restrict__ out, unsigned long long* __restrict__ dist)
+                             const mmgpu_mv* __restrict__ mvs, int mvShift, const float* __restrict__ rot, int rotOverride,
+                             int nCands, MmCand* __restrict__ out, unsigned long long* __restrict__ dist)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nCands) return;
@@ -113,7 +113,7 @@ __global__ void k_cand_setup(MmGeom g, const mmgpu_block* __restrict__ blocks, c
   }
   else
   {
-    mm_cand_setup(g, b.model, true, b.x, b.y, b.w, b.h, mh, mvv, mm_rot_ptr(rot, b.model, b.rot_slot), &c);
+    mm_cand_setup(g, b.model, true, b.x, b.y, b.w, b.h, mh, mvv, mm_rot_ptr(rot, b.model, rotOverride >= 0 ? rotOverride : b.rot_slot), &c);
   }
   out[i] = c;
 }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(32 * MM_MAP_WARPS, MM_MAP_MINBLOCKS) k_map(con
       n = (bw >> 2) * (bh >> 2);
       s = mm_sub_from_index(bw, bh, (n >= 32) ? it.sb + lane : lane % n);
       model = (MODEL >= 0) ? MODEL : (int)((it.rmr >> 16) & 0xff);
-      R = mm_rot_ptr(P.rot, model, (int)(it.rmr >> 24));
+      R = mm_rot_ptr(P.rot, model, (P.rotOverride >= 0) ? P.rotOverride : (int)(it.rmr >> 24));
     }
     const int cand = (n >= 32) ? it.cand : it.cand + lane / n;
     const int candc = (cand < it.candEnd) ? cand : it.cand;  // lanes past the last candidate redo a valid one, result unused
@@ -266,9 +266,10 @@ void mmk_build_items(cudaStream_t s, const mmgpu_block* blocks, const int32_t* i
   k_build_items<<<(nBlocks + 3) / 4, 128, 0, s>>>(blocks, itemBase, nBlocks, items, candBlock);
 }
 void mmk_cand_setup(cudaStream_t s, const MmGeom& g, const mmgpu_block* blocks, const int32_t* candBlock, const mmgpu_mv* mvs,
-                    int mvShift, const float* rot, int nCands, MmCand* out, unsigned long long* dist)
+                    int mvShift, const float* rot, int rotOverride, int nCands, MmCand* out, unsigned long long* dist)
 {
-  k_cand_setup<<<(nCands + MM_CS_THREADS - 1) / MM_CS_THREADS, MM_CS_THREADS, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, nCands, out, dist);
+  k_cand_setup<<<(nCands + MM_CS_THREADS - 1) / MM_CS_THREADS, MM_CS_THREADS, 0, s>>>(g, blocks, candBlock, mvs, mvShift, rot, rotOverride, nCands,
+                                                                                      out, dist);
 }
 void mmk_reproject(cudaStream_t s, const MmParams& P, int comp, int csx, int csy, int x, int y, int w, int h, mmgpu_mv mv,
                    int model, int rotSlot, int32_t* outX, int32_t* outY)

@@ -153,6 +153,8 @@ static MmParams baseParams(mmgpu_ctx* ctx)
   P.maxCU = ctx->cfg.max_cu;
   P.clpMin = 0;
   P.clpMax = (1 << ctx->cfg.bit_depth) - 1;
+  P.refOverride = -1;
+  P.rotOverride = -1;
   return P;
 }
 
@@ -327,10 +329,15 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     CUC(cudaMemset(ctx->dTmaps, 0, sizeof(CUtensorMap) * (size_t)cfg->max_refs * MM_TMA_TYPES));
   }
   {
-    std::vector<uint32_t> ht(MM_HTAPS_WORDS);
+    std::vector<uint32_t> ht(MM_HTAPS_WORDS + MM_HTAPS_BASE_WORDS);
     mm_build_htaps(ht.data(), h_lumaFilter);
-    CUC(cudaMalloc(&ctx->dHTaps, sizeof(uint32_t) * MM_HTAPS_WORDS));
-    CUC(cudaMemcpy(ctx->dHTaps, ht.data(), sizeof(uint32_t) * MM_HTAPS_WORDS, cudaMemcpyHostToDevice));
+    for (int ph = 0; ph < 16; ++ph)   // entry o = 0, j = 0 holds the un-shifted words (C0, C1, 0)
+    {
+      ht[MM_HTAPS_WORDS + 2 * ph] = ht[ph * 12];
+      ht[MM_HTAPS_WORDS + 2 * ph + 1] = ht[ph * 12 + 1];
+    }
+    CUC(cudaMalloc(&ctx->dHTaps, sizeof(uint32_t) * ht.size()));
+    CUC(cudaMemcpy(ctx->dHTaps, ht.data(), sizeof(uint32_t) * ht.size(), cudaMemcpyHostToDevice));
   }
   mmk_trig_tables(ctx->stream, g, ctx->dThTab[0], ctx->dThTab[1], ctx->dPhTab[0], ctx->dPhTab[1]);
   ctx->launches++;
@@ -932,7 +939,7 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
   P.dist = d_dist;
   P.dst = d_dst;
   P.dstStride = dst_stride;
-  mmk_cand_setup(setupStream ? setupStream : ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot,
+  mmk_cand_setup(setupStream ? setupStream : ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot, -1,
                  plan->nCands, plan->dCands, (mode == MM_MODE_DIST) ? d_dist : nullptr);
   ctx->launches++;
   if (setupStream)
@@ -979,6 +986,61 @@ extern "C" int mmgpu_me_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, con
   cudaSetDevice(ctx->cfg.device);
   return launchMe(ctx, plan, d_mvs, mv_prec_shift, MM_MODE_DIST, dist_kind, sub_shift, clp_min, clp_max,
                   reinterpret_cast<unsigned long long*>(d_dist), nullptr, 0);
+}
+
+extern "C" int mmgpu_me_batch_device_multiref(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift,
+                                              int dist_kind, int sub_shift, int clp_min, int clp_max, int n_refs,
+                                              const int32_t* ref_slots, const int32_t* rot_slots, uint64_t* d_dist)
+{
+  if (!ctx || !plan || !d_mvs || !d_dist || !ref_slots || n_refs <= 0) return MMGPU_ERR_ARG;
+  if (!ctx->dOrg) return fail(ctx, MMGPU_ERR_STATE, "mmgpu_set_org* has not been called");
+  if (dist_kind != MMGPU_DIST_SAD && dist_kind != MMGPU_DIST_HAD) return fail(ctx, MMGPU_ERR_ARG, "bad dist_kind");
+  if (sub_shift < 0 || sub_shift > 2 || (dist_kind == MMGPU_DIST_HAD && sub_shift != 0)) return fail(ctx, MMGPU_ERR_ARG, "bad sub_shift");
+  if (mv_prec_shift < 0 || mv_prec_shift > 4) return fail(ctx, MMGPU_ERR_ARG, "mv_prec_shift must be 0..4");
+  if (plan->orgMaxX > ctx->orgW || plan->orgMaxY > ctx->orgH)
+    return fail(ctx, MMGPU_ERR_ARG, "a block of the plan lies outside the current org plane (mmgpu_set_org*)");
+  for (int r = 0; r < n_refs; ++r)
+  {
+    if (ref_slots[r] < 0 || ref_slots[r] >= ctx->cfg.max_refs || !ctx->hRefs[ref_slots[r]].plane00[0])
+      return fail(ctx, MMGPU_ERR_STATE, "multiref: unset reference slot");
+    if (rot_slots && (rot_slots[r] < 0 || rot_slots[r] >= MM_MAX_ROT)) return fail(ctx, MMGPU_ERR_ARG, "multiref: bad rot_slot");
+  }
+  cudaSetDevice(ctx->cfg.device);
+  unsigned long long* dist = reinterpret_cast<unsigned long long*>(d_dist);
+  CU(cudaMemsetAsync(dist, 0, sizeof(unsigned long long) * (size_t)n_refs * plan->nCands, ctx->stream));
+  MmParams P = baseParams(ctx);
+  P.blocks = plan->dBlocks; P.items = plan->dItems; P.nItems = plan->nItems; P.mvs = d_mvs; P.mvShift = mv_prec_shift;
+  P.cands = plan->dCands; P.clpMin = clp_min; P.clpMax = clp_max; P.distKind = dist_kind; P.subShift = sub_shift;
+  P.oobMode = MMGPU_OOB_ME;
+  // the mapping depends on the reference only through the rotation slot of GEODESIC_CAMPOSE blocks: one k_cand_setup + k_map
+  // per distinct rotation slot, one k_fir per reference
+  const bool campose = plan->modelCount[MMGPU_GEODESIC_CAMPOSE] > 0 && rot_slots != nullptr;
+  std::vector<char> done((size_t)n_refs, 0);
+  int rc;
+  for (int r = 0; r < n_refs; ++r)
+  {
+    if (done[r]) continue;
+    const int rot = rot_slots ? rot_slots[r] : -1;
+    mmk_cand_setup(ctx->stream, ctx->g, plan->dBlocks, plan->dCandBlock, d_mvs, mv_prec_shift, ctx->dRot, rot, plan->nCands, plan->dCands, nullptr);
+    ctx->launches++;
+    P.rotOverride = rot;
+    if ((rc = timingEvent(ctx))) return rc;
+    mmk_map(ctx->stream, P, 0, plan->nItems, -1, plan->dPos);
+    ctx->launches++;
+    if ((rc = timingEvent(ctx))) return rc;
+    for (int q = r; q < n_refs; ++q)
+    {
+      if (done[q] || (campose && rot_slots[q] != rot)) continue;
+      P.refOverride = ref_slots[q];
+      P.dist = dist + (size_t)q * plan->nCands;
+      mmk_fir(ctx->stream, P, 0, plan->nItems, MM_MODE_DIST, plan->dPos);
+      ctx->launches++;
+      done[q] = 1;
+    }
+    if ((rc = timingEvent(ctx))) return rc;
+  }
+  CU(cudaGetLastError());
+  return MMGPU_OK;
 }
 
 extern "C" int mmgpu_mc_batch_device(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mvs, int mv_prec_shift,
