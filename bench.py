@@ -284,7 +284,11 @@ def main():
         origins = [pic.data_ptr() + int(offs[c]) + 2 * (p.my * p.stride + p.mx) for c, p in enumerate(geo)]
         gpu.set_ref_device(slot, poc, origins, [p.stride for p in geo], keep=pic)
 
-    pool_ref, pool_org_h = [], []
+    # un-padded form of a picture (what crosses NVLink at N > 1: the margins are rebuilt on arrival by k_extend_border)
+    uw = [(p.w, p.h) for p in geo]
+    uoffs = np.concatenate([[0], np.cumsum([(2 * w_ * h_ + 255) // 256 * 256 for w_, h_ in uw])]).astype(np.int64)
+    upic_bytes = int(uoffs[-1])
+    pool_ref, pool_org_h, pool_unp = [], [], []
     for f in range(POOL):
         planes = geo if f == 0 else wl.pad_frame(wl.synth_frame(W, H, seed=100 + f, shift=(0.37 * f, 0.11 * f)), 288, 1)
         pic = new_picture()
@@ -292,14 +296,18 @@ def main():
             pic[int(offs[c]):int(offs[c]) + plane_bytes[c]].copy_(torch.from_numpy(p.buf.view(np.uint8).reshape(-1)))
         pool_ref.append(pic)
         register(f, pic, f)
+        if N > 1:
+            up = torch.empty(upic_bytes, dtype=torch.uint8, device=dev)
+            for c, p in enumerate(planes):
+                inner = np.ascontiguousarray(p.inner)
+                up[int(uoffs[c]):int(uoffs[c]) + inner.nbytes].copy_(torch.from_numpy(inner.view(np.uint8).reshape(-1)))
+            pool_unp.append(up)
         pool_org_h.append(torch.from_numpy(wl.synth_plane(W, H, 5000 + f, shift=(0.37 * f + 2.5, 0.11 * f + 1.0))).pin_memory())
     pool_org_d = [t.to(dev) for t in pool_org_h]
-    # landing buffers: parity p holds the N pictures of a step back to back (filled by ONE all-gather: rank f
-    # contributes the picture it owns, i.e. N simultaneous broadcasts over NVLink/NVSwitch)
-    comm = [torch.empty(N * pic_bytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
-    for p, big in enumerate(comm):
-        for f in range(N):
-            register(POOL + p * N + f, big[f * pic_bytes:(f + 1) * pic_bytes], f)
+    # landing buffers: parity p holds the N UN-PADDED pictures of a step back to back (filled by ONE all-gather: rank f
+    # contributes the picture it owns, i.e. N simultaneous broadcasts over NVLink/NVSwitch); each is then copied into the
+    # padded planes of its reference slot and its borders are extended on the device (mmgpu_set_ref_unpadded_device)
+    comm = [torch.empty(N * upic_bytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
 
     # ---- batch: this rank's CTU rows of the N frames of a step ------------------------------------------------
     rows = wl.shard_ctu_rows(H // CTU, rank, N)
@@ -350,7 +358,7 @@ def main():
             plans[key] = (gpu.plan(b, n_cands), b)
         return plans[key]
 
-    exchange = shard.PictureExchange(pic_bytes, dev) if N > 1 else None
+    exchange = shard.PictureExchange(upic_bytes, dev) if N > 1 else None
 
     def prefetch(s):
         """Rank f owns frame f of step s: it copies its picture into the landing buffer and NCCL-broadcasts it.
@@ -360,7 +368,11 @@ def main():
         p = s % 2
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(freed[p])
-            exchange.allgather(comm[p], pool_ref[(s * N + rank) % POOL])
+            exchange.allgather(comm[p], pool_unp[(s * N + rank) % POOL])
+            for f in range(N):
+                base = comm[p].data_ptr() + f * upic_bytes
+                gpu.set_ref_unpadded_device(POOL + p * N + f, f, [base + int(uoffs[c]) for c in range(3)], [w_ for w_, _ in uw],
+                                            stream=comm_stream.cuda_stream, keep=comm[p])
             ready[p].record(comm_stream)
 
     def load_orgs(s, tgt, src_pool):
@@ -466,7 +478,7 @@ def main():
     if N > 1:
         barrier()
         for f in range(N):
-            if not torch.equal(comm[0][f * pic_bytes:(f + 1) * pic_bytes], pool_ref[f % POOL]):
+            if not torch.equal(comm[0][f * upic_bytes:(f + 1) * upic_bytes], pool_unp[f % POOL]):
                 raise SystemExit("bench self-check failed: picture %d arrived corrupted on rank %d (%s)" % (f, rank, exchange.mode))
     device_step(0)
     barrier()
@@ -548,9 +560,9 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
             "config": bench_config(N, int(len(blocks)), int(n_cands), samples_all,
-                                   ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each, one owner rank each) reach "
-                                    "every GPU %s, prefetched one step ahead on a second stream"
-                                    % (N, N, pic_bytes / 1e6, "by copy-engine pulls from symmetric (peer) memory over NVLink"
+                                   ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each un-padded, one owner rank each; "
+                                    "margins rebuilt on arrival) reach every GPU %s, prefetched one step ahead on a second stream"
+                                    % (N, N, upic_bytes / 1e6, "by copy-engine pulls from symmetric (peer) memory over NVLink"
                                        if exchange.mode == "p2p" else "by one ncclAllGather")) if N > 1 else "1 gpu"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": counts["k_fir"]["dram_bytes"] if counts else None, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,

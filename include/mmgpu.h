@@ -98,6 +98,13 @@ int mmgpu_set_ref_unpadded(mmgpu_ctx* ctx, int slot, int poc, const int16_t* con
 int mmgpu_set_ref_unpadded_wrap(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const plane[3], const int32_t stride[3],
                                 int wrap_offset);
 
+/* un-padded planes that already live in DEVICE memory (e.g. the landing buffer of an NCCL all-gather: only the picture
+ * itself crosses NVLink, the margins are rebuilt on arrival): device-to-device copy into the slot's own padded planes +
+ * border extension, enqueued on `stream` (a cudaStream_t; NULL = the context's stream).  wrap_offset as above (0 = replicate).
+ * The caller orders `stream` against the batches that read the slot (events), as with any double-buffered reference. */
+int mmgpu_set_ref_unpadded_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const d_plane[3], const int32_t stride[3],
+                                  int wrap_offset, void* stream);
+
 /* ---- geodesic epipole: GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46) ------------ */
 void mmgpu_rodrigues(const float epipole[3], float R[9]);          /* host helper, row-major R */
 float mmgpu_fixed_to_float(int32_t fixed, int32_t precision);     /* Coordinate.cpp:75-77 (EPIPOLE_PRECISION_FIXED=24) */
@@ -162,6 +169,12 @@ int mmgpu_set_org_device(mmgpu_ctx* ctx, const int16_t* org, int stride, int w, 
  * (RdCost.cpp:225-311).  All pointers HOST memory; the call returns when dist[] is filled. */
 int mmgpu_me_batch(mmgpu_ctx* ctx, int n_blocks, const mmgpu_block* blocks, int n_cands, const mmgpu_mv* mvs,
                    int mv_prec_shift, int dist_kind, int sub_shift, int clp_min, int clp_max, uint64_t* dist);
+
+/* Out-of-picture rule of the candidate evaluation (mmgpu_me_batch*, _submit, _device, _multiref): MMGPU_OOB_ME (default,
+ * xMVReprojectionInterpolation, InterSearch.cpp:6329-6332) for the motion search; MMGPU_OOB_PRED (xPredInterBlkMM,
+ * InterPrediction.cpp:776-780) for distortions of decided MVs -- merge-candidate SATD pre-selection (EncCu.cpp:2375-2600) and
+ * xGetInterPredictionError (InterSearch.cpp:855-868), whose predictions come from motionCompensation. */
+int mmgpu_set_dist_oob_mode(mmgpu_ctx* ctx, int oob_mode);
 
 /* Pipelined form of the same call for callers that have the next batch ready while this one runs (frame-level
  * look-ahead ME): submit copies org/blocks/mvs on a copy stream into buffers owned by `slot` (0..3) and queues the

@@ -704,3 +704,33 @@ def test_multi_reference_batch_equals_single_reference_calls(env):
             exp = g.me_batch(b, mvs, mv_prec_shift=prec, dist=dist)
             assert np.array_equal(got[r], exp), (dist, r)
     assert len({tuple(x) for x in got}) == len(ref_slots)   # the four references really give different distortions
+
+
+def test_merge_satd_uses_the_prediction_oob_rule(env):
+    """merge-candidate SATD / xGetInterPredictionError evaluate predictions of motionCompensation, i.e. with
+    xPredInterBlkMM's out-of-picture rule (InterPrediction.cpp:776-780), not the search's: mmgpu_set_dist_oob_mode(PRED)
+    + the batch call == HAD(org, oracle MC with the PRED rule); near the picture border the two rules differ."""
+    o, g, planes, ref, cur = env
+    g.set_org(cur[0])
+    rng = np.random.default_rng(5)
+    blocks = np.zeros(24, dtype=mm.api.BLOCK_DTYPE)
+    mvs = np.zeros(24, dtype=mm.api.MV_DTYPE)
+    shapes = [(16, 16), (32, 8), (8, 32), (64, 64)]
+    for i in range(24):
+        w, h = shapes[i % 4]
+        x = (W - w) if i % 3 == 0 else int(rng.integers(0, (W - w) // 4)) * 4      # right border: the +maxCU slack matters
+        y = (H - h) if i % 3 == 1 else int(rng.integers(0, (H - h) // 4)) * 4      # bottom border
+        blocks[i] = (x, y, w, h, [1, 2, 3, 4, 5, 6, 10][i % 7], 0, 0, i, 1, x, y, 0)
+        mvs[i] = (int(rng.integers(0, 900)), int(rng.integers(0, 700)))
+    try:
+        g.set_dist_oob_mode(mm.OOB_PRED)
+        got = g.me_batch(blocks, mvs, mv_prec_shift=0, dist=mm.DIST_HAD)
+    finally:
+        g.set_dist_oob_mode(mm.OOB_ME)
+    me = g.me_batch(blocks, mvs, mv_prec_shift=0, dist=mm.DIST_HAD)
+    for i, b in enumerate(blocks):
+        pred = o.mc_block(planes[0], 0, 1, (int(b["x"]), int(b["y"])), (int(b["w"]), int(b["h"])), (int(mvs["hor"][i]), int(mvs["ver"][i])),
+                          int(b["model"]), oob=ol.OOB_PRED)
+        org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+        assert int(got[i]) == ol.had(np.ascontiguousarray(org), pred, ol.HAD_SIMD), i
+    assert (got != me).any()

@@ -51,7 +51,8 @@ def main():
     blocks, mvs, prec = wl.frame_batch(W, H, seed=1, cands_per_block=16, mv_range=64, models=(1, 2, 3, 10, 6))
     rng = np.random.default_rng(0)
     pick = rng.permutation(len(blocks))[:nb]
-    tot = {"tile": 0, "row16": 0}
+    tot = {"tile": 0, "row16": 0, "row16p32": 0}
+    big = {"tile": 0, "row16": 0, "row16p32": 0}; nbig = 0
     items = boxed = 0
     ideal = 0
     for bi in pick:
@@ -94,19 +95,32 @@ def main():
                     maps["row16"] = inv
                 else:
                     maps["row16"] = np.arange(32)
+                if lth == 1 and cols >= 16:
+                    maps["row16p32"] = maps["row16"]
+                else:
+                    maps["row16p32"] = np.arange(32)
                 for name, perm in maps.items():
-                    b8 = np.where(oob, -1, base8)[perm]
+                    if name == "row16p32" and lth == 1 and cols >= 16 and wb <= 128:
+                        pq = 32
+                        b8x = (ay - y0) * pq + (ax - x0) // 4
+                    else:
+                        pq = pitchQ
+                        b8x = base8
+                    pitch_used = pq
+                    b8 = np.where(oob, -1, b8x)[perm]
                     tl = (tail & ~oob)[perm]
                     wf = 0
                     for r in range(11):
                         for k in range(3):
-                            wf += wavefronts64(np.where(b8 >= 0, b8 + r * pitchQ + k, -1))
-                        wf += wavefronts32(np.where(tl, (b8 + r * pitchQ + 3) * 2, -1))
+                            wf += wavefronts64(np.where(b8 >= 0, b8 + r * pitch_used + k, -1))
+                        wf += wavefronts32(np.where(tl, (b8 + r * pitch_used + 3) * 2, -1))
                     tot[name] += wf
+                    if lth == 1 and cols >= 16: big[name] += wf
+                if lth == 1 and cols >= 16: nbig += 1
                 ideal += 11 * 7
     print("items %d, boxed %d (%.1f%%)" % (items, boxed, 100.0 * boxed / max(1, items)))
     for k, v in tot.items():
-        print("%-6s wavefronts per boxed item: %.1f (ideal %.1f)" % (k, v / max(1, boxed), ideal / max(1, boxed)))
+        print("%-9s wavefronts per boxed item: %.1f (ideal %.1f); items of >=16-column 2-row-tile chunks (%d): %.1f" % (k, v / max(1, boxed), ideal / max(1, boxed), nbig, big[k] / max(1, nbig)))
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
     for f in (L.mmgpu_set_ref, L.mmgpu_set_ref_device, L.mmgpu_set_ref_unpadded):
         f.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_set_ref_unpadded_wrap.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32), i32]
+    L.mmgpu_set_ref_unpadded_device.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32), i32, vp]
     L.mmgpu_rodrigues.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mmgpu_fixed_to_float.restype = C.c_float
     L.mmgpu_fixed_to_float.argtypes = [C.c_int32, C.c_int32]
@@ -99,6 +100,7 @@ def load_library():
     L.mmgpu_plan_create.argtypes = [vp, i32, vp, i32, C.POINTER(vp)]
     L.mmgpu_plan_destroy.argtypes = [vp]
     L.mmgpu_me_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.mmgpu_set_dist_oob_mode.argtypes = [vp, i32]
     L.mmgpu_me_batch_device_multiref.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.mmgpu_plan_samples.restype = u64
     L.mmgpu_plan_samples.argtypes = [vp]
@@ -251,6 +253,13 @@ class MmGpu:
         p, s = self._planes([a.ctypes.data for a in planes], [a.strides[0] // 2 for a in planes])
         self._chk(self.L.mmgpu_set_ref_unpadded_wrap(self.h, slot, poc, p, s, int(wrap_offset)))
 
+    def set_ref_unpadded_device(self, slot, poc, ptrs, strides, wrap_offset=0, stream=None, keep=None):
+        """Un-padded planes already in device memory (ptrs: device addresses): D2D copy + border extension on `stream`
+        (a raw cudaStream_t value; None = the context's stream)."""
+        p, s = self._planes(list(ptrs), list(strides))
+        self._keep[("refu", slot)] = keep
+        self._chk(self.L.mmgpu_set_ref_unpadded_device(self.h, slot, poc, p, s, int(wrap_offset), C.c_void_p(stream) if stream else None))
+
     def set_rotation(self, rot_slot, R):
         r = (C.c_float * 9)(*[float(v) for v in R])
         self._chk(self.L.mmgpu_set_rotation(self.h, rot_slot, r))
@@ -289,6 +298,10 @@ class MmGpu:
     def set_org_device(self, ptr, stride, w, h, keep=None):
         self._keep["org"] = keep
         self._chk(self.L.mmgpu_set_org_device(self.h, ptr, stride, w, h))
+
+    def set_dist_oob_mode(self, oob):
+        """OOB_ME (motion search, default) or OOB_PRED (distortions of decided MVs: merge SATD, xGetInterPredictionError)."""
+        self._chk(self.L.mmgpu_set_dist_oob_mode(self.h, int(oob)))
 
     def me_batch(self, blocks, mvs, mv_prec_shift=4, dist=DIST_SAD, sub_shift=0, clp=(0, 1023), out=None):
         """blocks: numpy array of BLOCK_DTYPE; mvs: numpy array of MV_DTYPE -> uint64 distortions."""

@@ -98,6 +98,7 @@ struct mmgpu_ctx
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
   bool mapPerModel;
+  int distOob;              // OOB rule of the DIST batches (mmgpu_set_dist_oob_mode)
   MmStage stage;            // staging of the synchronous entry points
   cudaStream_t copyStream;  // host->device copies of submitted batches
   cudaStream_t prepStream;  // work list + per-candidate scalars of a submitted batch (overlaps the previous batch's k_fir)
@@ -258,6 +259,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     ctx->cfg.libm_fma = (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
   }
   ctx->launches = 0;
+  ctx->distOob = MMGPU_OOB_ME;
   ctx->timing = false;
   memset(&ctx->stage, 0, sizeof(ctx->stage));
   memset(ctx->slots, 0, sizeof(ctx->slots));
@@ -631,6 +633,44 @@ extern "C" int mmgpu_set_ref_unpadded_wrap(mmgpu_ctx* ctx, int slot, int poc, co
   return setRefUnpadded(ctx, slot, poc, plane, stride, wrap_offset);
 }
 
+extern "C" int mmgpu_set_ref_unpadded_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const d_plane[3],
+                                             const int32_t stride[3], int wrap_offset, void* stream)
+{
+  if (!ctx || !d_plane || !stride) return MMGPU_ERR_ARG;
+  if (slot < 0 || slot >= ctx->cfg.max_refs) return fail(ctx, MMGPU_ERR_ARG, "ref slot out of range");
+  if (wrap_offset < 0 || wrap_offset > ctx->cfg.pic_w) return fail(ctx, MMGPU_ERR_ARG, "wrap_offset must be 0..pic_w");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  MmRef r;
+  memset(&r, 0, sizeof(r));
+  r.poc = poc;
+  bool fresh = false;   // first use of the slot: its planes are allocated and the device tables have to learn them
+  for (int c = 0; c < numComps(ctx); ++c)
+  {
+    if (!d_plane[c]) return fail(ctx, MMGPU_ERR_ARG, "null plane");
+    int w, h, mx, my, pitch;
+    int16_t* d00;
+    compDims(ctx, c, &w, &h, &mx, &my);
+    if (!ctx->ownedPlanes[(size_t)slot * 3 + c]) fresh = true;
+    int rc = ensureOwnedPlane(ctx, slot, c, &d00, &pitch);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(d00, sizeof(int16_t) * pitch, d_plane[c], sizeof(int16_t) * stride[c], sizeof(int16_t) * w, h,
+                         cudaMemcpyDeviceToDevice, st));
+    mmk_extend_border(st, d00, pitch, w, h, mx, my, wrap_offset >> scaleX(c, ctx->cfg.chroma_fmt));
+    ctx->launches++;
+    r.plane00[c] = d00;
+    r.stride[c] = pitch;
+  }
+  CU(cudaGetLastError());
+  if (fresh || ctx->hRefs[slot].plane00[0] != r.plane00[0])
+  {
+    ctx->hRefs[slot] = r;
+    return publishRef(ctx, slot);   // descriptor / table upload on the context's stream (addresses never change afterwards)
+  }
+  ctx->hRefs[slot].poc = poc;
+  return MMGPU_OK;
+}
+
 extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9])
 {
   if (!ctx || !R) return MMGPU_ERR_ARG;
@@ -948,7 +988,7 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
     CU(cudaStreamWaitEvent(ctx->stream, setupDone, 0));
   }
   int rc;
-  P.oobMode = (mode == MM_MODE_DIST) ? MMGPU_OOB_ME : MMGPU_OOB_PRED;
+  P.oobMode = (mode == MM_MODE_DIST) ? ctx->distOob : MMGPU_OOB_PRED;
   if ((rc = timingEvent(ctx))) return rc;
   // k_map: positions of all entries.  Work items are grouped by motion model; ctx->mapPerModel launches one
   // specialised kernel per model present, otherwise one generic launch covers all items.
@@ -971,6 +1011,14 @@ static int launchMe(mmgpu_ctx* ctx, const mmgpu_plan* plan, const mmgpu_mv* d_mv
   ctx->launches++;
   if ((rc = timingEvent(ctx))) return rc;
   CU(cudaGetLastError());
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_set_dist_oob_mode(mmgpu_ctx* ctx, int oob_mode)
+{
+  if (!ctx) return MMGPU_ERR_ARG;
+  if (oob_mode != MMGPU_OOB_ME && oob_mode != MMGPU_OOB_PRED) return fail(ctx, MMGPU_ERR_ARG, "bad oob_mode");
+  ctx->distOob = oob_mode;
   return MMGPU_OK;
 }
 
@@ -1011,7 +1059,7 @@ extern "C" int mmgpu_me_batch_device_multiref(mmgpu_ctx* ctx, const mmgpu_plan* 
   MmParams P = baseParams(ctx);
   P.blocks = plan->dBlocks; P.items = plan->dItems; P.nItems = plan->nItems; P.mvs = d_mvs; P.mvShift = mv_prec_shift;
   P.cands = plan->dCands; P.clpMin = clp_min; P.clpMax = clp_max; P.distKind = dist_kind; P.subShift = sub_shift;
-  P.oobMode = MMGPU_OOB_ME;
+  P.oobMode = ctx->distOob;
   // the mapping depends on the reference only through the rotation slot of GEODESIC_CAMPOSE blocks: one k_cand_setup + k_map
   // per distinct rotation slot, one k_fir per reference
   const bool campose = plan->modelCount[MMGPU_GEODESIC_CAMPOSE] > 0 && rot_slots != nullptr;
