@@ -307,7 +307,19 @@ def main():
     # landing buffers: parity p holds the N UN-PADDED pictures of a step back to back (filled by ONE all-gather: rank f
     # contributes the picture it owns, i.e. N simultaneous broadcasts over NVLink/NVSwitch); each is then copied into the
     # padded planes of its reference slot and its borders are extended on the device (mmgpu_set_ref_unpadded_device)
-    comm = [torch.empty(N * upic_bytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
+    # MMGPU_EXCHANGE_PADDED=1: round-1 form for comparison -- the padded pictures themselves are all-gathered straight into
+    # the registered reference slots (twice the NVLink bytes, no padding kernel)
+    padded_x = os.environ.get("MMGPU_EXCHANGE_PADDED", "0") == "1"
+    xbytes = pic_bytes if padded_x else upic_bytes
+    comm = [torch.zeros(N * xbytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
+    for p, big in enumerate(comm):     # allocate + publish the planes of every landing slot once (addresses stay fixed)
+        for f in range(N):
+            if padded_x:
+                register(POOL + p * N + f, big[f * pic_bytes:(f + 1) * pic_bytes], f)
+            else:
+                base = big.data_ptr() + f * upic_bytes
+                gpu.set_ref_unpadded_device(POOL + p * N + f, f, [base + int(uoffs[c]) for c in range(3)], [w_ for w_, _ in uw], keep=big)
+    gpu.sync()
 
     # ---- batch: this rank's CTU rows of the N frames of a step ------------------------------------------------
     rows = wl.shard_ctu_rows(H // CTU, rank, N)
@@ -358,7 +370,7 @@ def main():
             plans[key] = (gpu.plan(b, n_cands), b)
         return plans[key]
 
-    exchange = shard.PictureExchange(upic_bytes, dev) if N > 1 else None
+    exchange = shard.PictureExchange(xbytes, dev) if N > 1 else None
 
     def prefetch(s):
         """Rank f owns frame f of step s: it copies its picture into the landing buffer and NCCL-broadcasts it.
@@ -368,11 +380,11 @@ def main():
         p = s % 2
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(freed[p])
-            exchange.allgather(comm[p], pool_unp[(s * N + rank) % POOL])
-            for f in range(N):
-                base = comm[p].data_ptr() + f * upic_bytes
-                gpu.set_ref_unpadded_device(POOL + p * N + f, f, [base + int(uoffs[c]) for c in range(3)], [w_ for w_, _ in uw],
-                                            stream=comm_stream.cuda_stream, keep=comm[p])
+            exchange.allgather(comm[p], (pool_ref if padded_x else pool_unp)[(s * N + rank) % POOL])
+            if not padded_x:
+              gpu.set_refs_unpadded_device([POOL + p * N + f for f in range(N)], list(range(N)),
+                                           [[comm[p].data_ptr() + f * upic_bytes + int(uoffs[c]) for c in range(3)] for f in range(N)],
+                                           [[w_ for w_, _ in uw]] * N, stream=comm_stream.cuda_stream, keep=comm[p])
             ready[p].record(comm_stream)
 
     def load_orgs(s, tgt, src_pool):
@@ -478,7 +490,7 @@ def main():
     if N > 1:
         barrier()
         for f in range(N):
-            if not torch.equal(comm[0][f * upic_bytes:(f + 1) * upic_bytes], pool_unp[f % POOL]):
+            if not torch.equal(comm[0][f * xbytes:(f + 1) * xbytes], (pool_ref if padded_x else pool_unp)[f % POOL]):
                 raise SystemExit("bench self-check failed: picture %d arrived corrupted on rank %d (%s)" % (f, rank, exchange.mode))
     device_step(0)
     barrier()
@@ -511,6 +523,10 @@ def main():
     e2e_dev_ms, e2e_wall_ms = timed(e2e_step, args.steps, lambda s: None, e2e_drain)
     # sustained leg: back-to-back device-resident steps for about args.sustain seconds (clock samples fall inside it)
     sus_steps = max(args.steps, int(args.sustain * 1000.0 / max(1e-3, dev_ms / args.steps)))
+    if dist is not None:      # every rank must run the same number of steps (each step holds a collective)
+        n_sus = torch.tensor([sus_steps], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_sus, op=dist.ReduceOp.MIN)
+        sus_steps = int(n_sus.item())
     sus_ms, _ = timed(device_step, sus_steps, lambda s: None)
     clocks = sampler.stop()
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
@@ -560,9 +576,9 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
             "config": bench_config(N, int(len(blocks)), int(n_cands), samples_all,
-                                   ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each un-padded, one owner rank each; "
-                                    "margins rebuilt on arrival) reach every GPU %s, prefetched one step ahead on a second stream"
-                                    % (N, N, upic_bytes / 1e6, "by copy-engine pulls from symmetric (peer) memory over NVLink"
+                                   ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each%s, one owner rank each) reach every GPU %s, "
+                                    "prefetched one step ahead on a second stream"
+                                    % (N, N, xbytes / 1e6, " with margins" if padded_x else " un-padded; margins rebuilt on arrival by one k_pad_planes launch", "by copy-engine pulls from symmetric (peer) memory over NVLink"
                                        if exchange.mode == "p2p" else "by one ncclAllGather")) if N > 1 else "1 gpu"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": counts["k_fir"]["dram_bytes"] if counts else None, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,

@@ -105,6 +105,11 @@ int mmgpu_set_ref_unpadded_wrap(mmgpu_ctx* ctx, int slot, int poc, const int16_t
 int mmgpu_set_ref_unpadded_device(mmgpu_ctx* ctx, int slot, int poc, const int16_t* const d_plane[3], const int32_t stride[3],
                                   int wrap_offset, void* stream);
 
+/* the same for n pictures at once (n * components <= 24): ONE kernel launch copies and extends all planes -- the per-step
+ * form of the multi-GPU picture exchange.  d_plane[i*3 + c], stride[i*3 + c]. */
+int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs, const int16_t* const* d_plane,
+                                   const int32_t* stride, int wrap_offset, void* stream);
+
 /* ---- geodesic epipole: GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46) ------------ */
 void mmgpu_rodrigues(const float epipole[3], float R[9]);          /* host helper, row-major R */
 float mmgpu_fixed_to_float(int32_t fixed, int32_t precision);     /* Coordinate.cpp:75-77 (EPIPOLE_PRECISION_FIXED=24) */
@@ -114,6 +119,16 @@ int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9]);
 /* out_x/out_y: (h/sbH)*(w/sbW) ints, column-major like the reference's ArrayXXi (idx = col*rows + row). */
 int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
                     int rot_slot, int32_t* out_x, int32_t* out_y);
+
+/* ---- 8f-1: MVReprojection::motionVectorInDesiredMotionModel (MVReprojection.cpp:168-217; callers UnitTools.cpp:2272,2302,
+ *      2932,...): the MV that, in motion model `model_desired`, moves sample `pos` like `mv_orig` does in `model_orig` (MM-MVP
+ *      candidate conversion).  A scalar per-candidate computation inside merge / AMVP list construction: evaluated on the HOST
+ *      with the same restated float code the kernels use (no launch, no copy).  shift_hor / shift_ver: MV fraction bits
+ *      (MV_FRACTIONAL_BITS_INTERNAL [+ chroma scale]); rot_slot_*: rotation slots of the (cur, ref) POC pairs for
+ *      GEODESIC_CAMPOSE (equal slots == equal epipoles); cand / cur: position and size of the candidate's and the current block. */
+int mmgpu_mvp_convert(mmgpu_ctx* ctx, int pos_x, int pos_y, mmgpu_mv mv_orig, int model_orig, int model_desired, int shift_hor,
+                      int shift_ver, int rot_slot_orig, int rot_slot_desired, int cand_x, int cand_y, int cand_w, int cand_h,
+                      int cur_x, int cur_y, int cur_w, int cur_h, mmgpu_mv* out);
 
 /* ---- a5/a6/a8: InterPrediction::xPredInterBlkMM (InterPrediction.cpp:683-856), xPredInterBlk (:928-1096),
  *      InterSearch::xMVReprojectionInterpolation (InterSearch.cpp:6277-6385) --------------------------- */
@@ -137,6 +152,11 @@ typedef struct {
 /* dst[c]: HOST planes of the (un-padded) picture being reconstructed; every job writes its block at (x,y). */
 int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max, int16_t* const dst[3],
                   const int32_t dst_stride[3]);
+
+/* same with the destination planes in DEVICE memory (a reconstruction that stays on the GPU: no picture crosses PCIe);
+ * asynchronous on mmgpu_stream().  d_dst[c] 2-byte aligned device planes of the un-padded picture. */
+int mmgpu_mc_jobs_device(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max, int16_t* const d_dst[3],
+                         const int32_t dst_stride[3]);
 
 /* ---- a13: InterPrediction::xWeightedAverage -> PelBuf::addAvg (Buffer.cpp:551-587) ------------------ */
 int mmgpu_add_avg(mmgpu_ctx* ctx, const int16_t* src0, int s0_stride, const int16_t* src1, int s1_stride, int16_t* dst,

@@ -52,6 +52,7 @@ struct State
   std::vector<mmgpu_mv> mvScratch;
   std::vector<uint64_t> distScratch;
   // statistics
+  uint64_t nMcClassic = 0;
   uint64_t nMc = 0, nMeBatches = 0, nMeCands = 0, nMeHits = 0, nMeSingles = 0, nUploads = 0;
 };
 State g;
@@ -106,6 +107,11 @@ struct AtExit { ~AtExit() { if (g.ctx) { printStats(); mmgpu_destroy(g.ctx); g.c
 }  // namespace
 
 bool enabled() { return g_enabled; }
+bool classicOnGpu()
+{
+  static const bool on = !(getenv("MMGPU_CLASSIC") && getenv("MMGPU_CLASSIC")[0] == '0');
+  return on;
+}
 
 void init(const Size& resolution, const SPS* sps, const EpipoleList* epipoleList)
 {
@@ -183,6 +189,16 @@ void predInterBlkMM(ComponentID compID, ChromaFormat chFmt, const Position& bloc
   chk(mmgpu_mc(g.ctx, slot, (int)compID, (int)chFmt, blockPos.x, blockPos.y, (int)blockSize.width, (int)blockSize.height, m,
                (int)motionModel, rot, bi ? 1 : 0, clpRng.min, clpRng.max, MMGPU_OOB_PRED, dstBuf.buf, (int)dstBuf.stride), "mc");
   g.nMc++;
+}
+
+void predInterBlkClassic(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, int width, int height, const Picture* refPic,
+                         bool wrapRef, const Mv& mv, bool bi, const ClpRng& clpRng, PelBuf& dstBuf)
+{
+  const int slot = ensureRef(refPic, wrapRef);
+  const mmgpu_mv m = {mv.hor, mv.ver};
+  chk(mmgpu_mc(g.ctx, slot, (int)compID, (int)chFmt, blockPos.x, blockPos.y, width, height, m, MMGPU_CLASSIC, 0, bi ? 1 : 0, clpRng.min,
+               clpRng.max, MMGPU_OOB_PRED, dstBuf.buf, (int)dstBuf.stride), "mc (classic)");
+  g.nMcClassic++;
 }
 
 // ---- ME -----------------------------------------------------------------------------------------------------------------
@@ -402,6 +418,7 @@ void dumpMc(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, co
 
 void printStats()
 {
+  fprintf(stderr, "[mmgpu] classic MC calls %llu\n", (unsigned long long)g.nMcClassic);
   fprintf(stderr, "[mmgpu] MC calls %llu | ME batches %llu, candidates %llu (%.1f per batch), look-ahead hits %llu, single evaluations %llu | "
                   "reference uploads %llu | kernels launched %llu\n",
           (unsigned long long)g.nMc, (unsigned long long)g.nMeBatches, (unsigned long long)g.nMeCands,

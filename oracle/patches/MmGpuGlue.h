@@ -15,6 +15,7 @@
 namespace mmglue
 {
 bool enabled();
+bool classicOnGpu();   // MMGPU_CLASSIC=0 keeps the classic translational MC on the reference's code
 
 // MVReprojection::init (MVReprojection.cpp:7-65): creates the device context (MPA caches, ERP tables on the device)
 void init(const Size& resolution, const SPS* sps, const EpipoleList* epipoleList);
@@ -26,6 +27,11 @@ int ensureRef(const Picture* pic, bool wrap);
 // body of InterPrediction::xPredInterBlkMM (InterPrediction.cpp:683-856)
 void predInterBlkMM(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, const Size& blockSize, const Picture* refPic,
                     bool wrapRef, const Mv& mv, MotionModelID motionModel, bool bi, const ClpRng& clpRng, int curPOC, PelBuf& dstBuf);
+
+// plain case of InterPrediction::xPredInterBlk (InterPrediction.cpp:928-1096: classic translational MC of one component; no
+// RPR / BDOF border / DMVR padding / IBC / alternative half-pel filter -- those stay on the reference's code)
+void predInterBlkClassic(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, int width, int height, const Picture* refPic,
+                         bool wrapRef, const Mv& mv, bool bi, const ClpRng& clpRng, PelBuf& dstBuf);
 
 // ---- motion estimation: xApplyMvVA / xMVReprojectionInterpolation + m_cDistParam.distFunc (InterSearch.cpp:363-453,
 //      5287-5322, 6168-6385).  The search control flow is untouched: candidate sets the reference is about to visit are

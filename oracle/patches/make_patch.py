@@ -54,6 +54,27 @@ def edit_interprediction(t):
   ArrayXXFixedPtrPair cart2DProjMovedFixedSubblocks = m_mvReprojection->reprojectMotionVectorSubblocks(
     blockPos, blockSize, mv, motionModel, compID, chFmt, pu.cs->slice->getPOC(), refPic->getPOC());
 """)
+    # classic translational MC (plain case) on the device as well
+    t = sub(t, """    PelBuf & dstBuf = dstPic.bufs[compID];
+    unsigned width  = dstBuf.width;
+    unsigned height = dstBuf.height;
+
+    CPelBuf refBuf;
+    {
+      Position offset = pu.blocks[compID].pos().offset(mv.getHor() >> shiftHor, mv.getVer() >> shiftVer);""", """    PelBuf & dstBuf = dstPic.bufs[compID];
+    unsigned width  = dstBuf.width;
+    unsigned height = dstBuf.height;
+    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && !useAltHpelIf
+        && width >= 4 && height >= 4 && ( width & ( width - 1 ) ) == 0 && ( height & ( height - 1 ) ) == 0
+        && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
+    {
+      mmglue::predInterBlkClassic( compID, chFmt, pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, bi, clpRng, dstBuf );
+      return;
+    }
+
+    CPelBuf refBuf;
+    {
+      Position offset = pu.blocks[compID].pos().offset(mv.getHor() >> shiftHor, mv.getVer() >> shiftVer);""")
     # debugging aid (MMGPU_DUMP): record the CPU path's result
     t = sub(t, """      }
     }

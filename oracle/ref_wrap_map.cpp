@@ -20,9 +20,9 @@ TCoord LookupTable::inverseLookup(TCoord) const { abort(); }
 ArrayXXTCoordPtr LookupTable::inverseLookup(ArrayXXTCoordPtr) const { abort(); }
 void ReprojectionLUT::fill() {}  // two 2786x2728 tables the path never reads
 Array2TCoord ReprojectionLUT::operator()(const Array2TCoord&) const { abort(); }
-static Array3TCoord g_epipole(0, 0, 0);
+static Array3TCoord g_epipole(0, 0, 0), g_epipole2(0, 0, 0);   // the second one answers for current POC 7 (MM-MVP tests)
 void EpipoleList::addEpipole(const Array3TCoord&, const int, const int, bool) {}
-Array3TCoord EpipoleList::findEpipole(int, int) const { return g_epipole; }
+Array3TCoord EpipoleList::findEpipole(int curPOC, int) const { return curPOC == 7 ? g_epipole2 : g_epipole; }
 
 // MVReprojection::init needs an SPS (Slice.cpp and half of CommonLib): set the same members directly.
 struct RefMap : public MVReprojection
@@ -45,6 +45,7 @@ struct RefMap : public MVReprojection
       mm->fillCache({m_cart2DProj[0], m_cart2DProj[1]});
       m_motionModels[id] = mm;
     }
+    m_motionModels[CLASSIC] = new TranslationalMotionModel();      // :16-18
     m_motionModels[TANGENTIAL] = new TangentialMotionModel(proj, ang);
     m_motionModels[THREE_D_TRANSLATIONAL] = new ThreeDTranslationalMotionModel(proj);
     m_motionModels[ROTATIONAL] = new RotationalMotionModel(proj, ang);
@@ -62,7 +63,18 @@ struct RefMap : public MVReprojection
 };
 
 extern "C" void* refmap_create(int w, int h, float off, int gedFlavor) { return new RefMap(w, h, off, gedFlavor); }
-extern "C" void refmap_set_epipole(float x, float y, float z) { g_epipole = Array3TCoord(x, y, z); }
+extern "C" void refmap_set_epipole(float x, float y, float z) { g_epipole = Array3TCoord(x, y, z); g_epipole2 = g_epipole; }
+extern "C" void refmap_set_epipole2(float x, float y, float z) { g_epipole2 = Array3TCoord(x, y, z); }
+// MVReprojection::motionVectorInDesiredMotionModel (MVReprojection.cpp:168-217)
+extern "C" void refmap_mvp(void* h, int px, int py, int mvh, int mvv, int modelOrig, int modelDes, int shiftHor, int shiftVer, int curPOCOrig,
+                           int curPOCDes, int candX, int candY, int candW, int candH, int curX, int curY, int curW, int curH, int* out)
+{
+  RefMap* r = (RefMap*)h;
+  const Mv m = r->motionVectorInDesiredMotionModel(Position(px, py), Mv(mvh, mvv), MotionModelID(modelOrig), MotionModelID(modelDes), shiftHor,
+                                                    shiftVer, curPOCOrig, 0, curPOCDes, 0, Position(candX, candY), Size(candW, candH),
+                                                    Position(curX, curY), Size(curW, curH));
+  out[0] = m.hor; out[1] = m.ver;
+}
 // GeodesicMotionModel::setEpipole -> rotation matrix (row-major), through a throw-away model instance
 extern "C" void refmap_rodrigues(void* h, float x, float y, float z, float* R)
 {

@@ -6,6 +6,7 @@
 #include <vector>
 #include <cmath>
 #include "../../vvc-extension-mm_b200/csrc/mm_map.cuh"
+#include "../../vvc-extension-mm_b200/csrc/mm_mvp.cuh"
 
 struct HostCtx
 {
@@ -82,4 +83,14 @@ extern "C" void mmhost_reproject(void* h, int comp, int csx, int csy, int x, int
       mm_to_fixed(g, X, Y, MX, MY, isLuma ? 0 : csx, isLuma ? 0 : csy, &fx, &fy);
       outX[i] = fx; outY[i] = fy;
     }
+}
+
+// MM-MVP conversion (mm_mvp.cuh) on the host
+extern "C" void mmhost_mvp(void* h, int posX, int posY, int mvHor, int mvVer, int modelOrig, int modelDes, int shiftHor, int shiftVer,
+                           const float* Rorig, const float* Rdes, int sameRot, int candX, int candY, int candW, int candH, int curX,
+                           int curY, int curW, int curH, int32_t* out)
+{
+  HostCtx* c = (HostCtx*)h;
+  mm_mvp_convert(c->g, posX, posY, mvHor, mvVer, modelOrig, modelDes, shiftHor, shiftVer, Rorig, Rdes, sameRot != 0, candX, candY, candW,
+                 candH, curX, curY, curW, curH, &out[0], &out[1]);
 }

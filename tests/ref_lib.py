@@ -87,6 +87,8 @@ def maplib():
         L.refmap_rodrigues.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.refmap_reproject.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_void_p]
         L.refmap_mpa_cache.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refmap_set_epipole2.argtypes = [C.c_float] * 3
+        L.refmap_mvp.argtypes = [C.c_void_p] + [C.c_int] * 18 + [C.c_void_p]
         _map = L
     return _map
 
@@ -115,6 +117,16 @@ class RefMap:
         self.L.refmap_reproject(self.h_, pos[0], pos[1], size[0], size[1], mv[0], mv[1], model, comp, chroma_fmt, cur_poc, ref_poc,
                                 ox.ctypes.data, oy.ctypes.data)
         return ox, oy
+
+    def set_epipole2(self, e):
+        """epipole of the (curPOC 7, *) pairs"""
+        self.L.refmap_set_epipole2(float(e[0]), float(e[1]), float(e[2]))
+
+    def mvp(self, pos, mv, model_orig, model_des, cand, cur, shift=(4, 4), poc_orig=0, poc_des=0):
+        out = np.zeros(2, dtype=np.int32)
+        self.L.refmap_mvp(self.h_, pos[0], pos[1], mv[0], mv[1], model_orig, model_des, shift[0], shift[1], poc_orig, poc_des,
+                          cand[0], cand[1], cand[2], cand[3], cur[0], cur[1], cur[2], cur[3], out.ctypes.data)
+        return int(out[0]), int(out[1])
 
     def mpa_cache(self, model):
         n = (self.w // 4) * (self.h // 4)

@@ -619,6 +619,23 @@ def test_decoder_shape_full_picture_md5(env):
         assert hashlib.md5(got[c].tobytes()).hexdigest() == hashlib.md5(exp[c].tobytes()).hexdigest(), \
             ("plane", c, int((got[c] != exp[c]).sum()))
     assert len(jobs) > 5000
+    # the same reconstruction with the picture resident on the device (mmgpu_mc_jobs_device), and a partial job list on top
+    # of a host picture that must keep the samples the jobs do not cover
+    import torch
+    dev = [torch.full((H, W), -1, dtype=torch.int16, device="cuda"), torch.full((H // 2, W // 2), -1, dtype=torch.int16, device="cuda"),
+           torch.full((H // 2, W // 2), -1, dtype=torch.int16, device="cuda")]
+    g.mc_jobs_device(np.array(jobs, dtype=mm.JOB_DTYPE), [t.data_ptr() for t in dev], [W, W // 2, W // 2])
+    g.sync()
+    for c in range(3):
+        assert np.array_equal(dev[c].cpu().numpy(), exp[c]), c
+    part_jobs = np.array(jobs[:300], dtype=mm.JOB_DTYPE)
+    keep = [np.full((H, W), 77, np.int16), np.full((H // 2, W // 2), 78, np.int16), np.full((H // 2, W // 2), 79, np.int16)]
+    g.mc_jobs(part_jobs, keep)
+    for c in range(3):
+        covered = np.zeros(keep[c].shape, dtype=bool)
+        for j in part_jobs[part_jobs["comp"] == c]:
+            covered[j["y"]:j["y"] + j["h"], j["x"]:j["x"] + j["w"]] = True
+        assert np.array_equal(keep[c][covered], exp[c][covered]) and (keep[c][~covered] == 77 + c).all(), c
 
 
 def test_config3_all_five_models_4096x2048():
@@ -734,3 +751,70 @@ def test_merge_satd_uses_the_prediction_oob_rule(env):
         org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
         assert int(got[i]) == ol.had(np.ascontiguousarray(org), pred, ol.HAD_SIMD), i
     assert (got != me).any()
+
+
+def test_device_side_unpadded_registration_single_and_batched(env):
+    """mmgpu_set_ref_unpadded_device / mmgpu_set_refs_unpadded_device (the multi-GPU exchange moves un-padded pictures and
+    rebuilds the margins on arrival): distortions against the device-padded slot == against the host-padded slot, for the
+    replicated and the wrapped border, one picture per call and two pictures in one launch."""
+    import torch
+    o, g, planes, ref, cur = env
+    g.set_org(cur[0])
+    blocks, mvs, prec = wl.frame_batch(W, H, seed=21, cands_per_block=3, mv_range=48, models=(0, 1, 4, 6, 10), ctu_rows=[0, 7])
+    blocks["ref_slot"] = 0
+    exp = g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD)
+    un = [torch.from_numpy(np.ascontiguousarray(p.inner)).cuda() for p in ref]
+    b1 = blocks.copy(); b1["ref_slot"] = 1
+    b2 = blocks.copy(); b2["ref_slot"] = 2
+    g.set_ref_unpadded_device(1, 5, [t.data_ptr() for t in un], [t.shape[1] for t in un], keep=un)
+    assert np.array_equal(g.me_batch(b1, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)
+    other = [torch.from_numpy(np.ascontiguousarray(p.inner)).cuda() for p in wl.pad_frame(wl.synth_frame(W, H, seed=77), 288, 1)]
+    g.set_refs_unpadded_device([2, 1], [6, 7], [[t.data_ptr() for t in un], [t.data_ptr() for t in other]],
+                               [[t.shape[1] for t in un]] * 2, keep=(un, other))
+    assert np.array_equal(g.me_batch(b2, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)
+    assert not np.array_equal(g.me_batch(b1, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)      # slot 1 now holds the other picture
+    # wrapped border: batched device padding == host-side extendWrapBorder of the oracle
+    wr = []
+    for p in ref:
+        q = ol.PaddedPlane(p.w, p.h, p.mx, p.my)
+        q.inner[:] = p.inner
+        q.extend_wrap(W if p.w == W else W // 2)
+        wr.append(q)
+    g.set_ref(3, 9, [q.origin for q in wr], [q.stride for q in wr])
+    b3 = blocks.copy(); b3["ref_slot"] = 3
+    expw = g.me_batch(b3, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD)
+    g.set_refs_unpadded_device([2], [8], [[t.data_ptr() for t in un]], [[t.shape[1] for t in un]], wrap_offset=W, keep=un)
+    assert np.array_equal(g.me_batch(b2, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), expw)
+    g.set_ref(0, 0, [p.origin for p in ref], [p.stride for p in ref])
+
+
+def test_mvp_convert_through_the_abi_equals_reference_source(env):
+    """mmgpu_mvp_convert (8f-1, evaluated on the host inside the C-ABI library) == the reference's own
+    MVReprojection::motionVectorInDesiredMotionModel (oracle/_ref/libvtmmap.so) for all model pairs."""
+    import ref_lib as rl
+    if not rl.map_available():
+        pytest.skip("oracle/_ref/libvtmmap.so not built")
+    o, g, *_ = env
+    r = rl.RefMap(W, H, 1.0, 1)
+    e2 = [0.1, 0.9, -0.2]
+    r.set_epipole(EPIPOLE)
+    r.set_epipole2(e2)
+    g.set_rotation(0, mm.rodrigues(EPIPOLE))
+    g.set_rotation(1, mm.rodrigues(e2))
+    rng = np.random.default_rng(81)
+    n = 0
+    for mo in range(11):
+        for md in range(11):
+            for k in range(12):
+                cw, chh, uw, uh = [int(2 ** rng.integers(2, 8)) for _ in range(4)]
+                cx, cy = int(rng.integers(0, (W - cw) // 4 + 1)) * 4, int(rng.integers(0, (H - chh) // 4 + 1)) * 4
+                ux, uy = int(rng.integers(0, (W - uw) // 4 + 1)) * 4, int(rng.integers(0, (H - uh) // 4 + 1)) * 4
+                pos = (ux + int(rng.integers(0, uw)), uy + int(rng.integers(0, uh)))
+                mv = (int(rng.integers(-600, 600)), int(rng.integers(-300, 300)))
+                po, pd = (7 if k % 2 else 0), (7 if k % 4 < 2 else 0)
+                exp = r.mvp(pos, mv, mo, md, (cx, cy, cw, chh), (ux, uy, uw, uh), (4, 4), po, pd)
+                got = g.mvp_convert(pos, mv, mo, md, (cx, cy, cw, chh), (ux, uy, uw, uh), (4, 4), (1 if po == 7 else 0, 1 if pd == 7 else 0))
+                assert got == exp, (mo, md, pos, mv, exp, got)
+                n += 1
+    assert n == 11 * 11 * 12
+    g.set_rotation(1, mm.rodrigues([0.1, 0.9, -0.2]))

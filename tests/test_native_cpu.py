@@ -183,3 +183,96 @@ def test_dmvr_decide_host_equals_oracle():
             assert a == b, (c, w, h, a, b)
             n += 1
     assert n == 12000
+
+
+def test_search_enumerators_of_the_adapter_equal_oracle_restatement():
+    """host/mm_gpu_adapter.h's tzDiamondRound / tz2Point / tzRaster list the points of one call of
+    xTZ8PointDiamondSearch / xTZ2PointSearch / the raster scan in the reference's visiting order (tests/oracle_tz.py), for
+    every distance 1..64, with and without corner points, start points inside / at / beyond the search-range border."""
+    import oracle_tz as tz
+    exe = os.path.join(BUILD, "tz_check")
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(NATIVE, "tz_check.cpp")
+    hdr = os.path.join(ROOT, "vvc-extension-mm_b200", "host", "mm_gpu_adapter.h")
+    if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(exe):
+        subprocess.check_call(["g++", "-O1", "-std=c++11", src, "-o", exe])
+    rng = np.random.default_rng(14)
+    cases, exp = [], []
+    for _ in range(3000):
+        sr = (-int(rng.integers(0, 70)), int(rng.integers(0, 70)), -int(rng.integers(0, 70)), int(rng.integers(0, 70)))
+        pts = []
+        visit = lambda x, y, nr, d: pts.extend((x, y, nr, d))  # noqa: E731
+        kind = "DDDPR"[int(rng.integers(0, 5))]
+        sx, sy = int(rng.integers(sr[0] - 3, sr[1] + 4)), int(rng.integers(sr[2] - 3, sr[3] + 4))
+        if kind == "D":
+            dist, corners = int(2 ** rng.integers(0, 7)), int(rng.integers(0, 2))
+            tz.diamond(sr, sx, sy, dist, bool(corners), visit)
+            cases.append("D %d %d %d %d %d %d %d %d" % (sr + (sx, sy, dist, corners)))
+        elif kind == "P":
+            nr = int(rng.integers(0, 9))
+            tz.two_point(sr, sx, sy, nr, visit)
+            cases.append("P %d %d %d %d %d %d %d" % (sr + (sx, sy, nr)))
+        else:
+            step = int(rng.integers(1, 9))
+            tz.raster(sr, step, visit)
+            cases.append("R %d %d %d %d %d" % (sr + (step,)))
+        exp.append(pts)
+    out = subprocess.run([exe], input="\n".join(cases) + "\n", capture_output=True, text=True)
+    assert out.returncode == 0
+    got = [[int(v) for v in line.split()] for line in out.stdout.split("\n")[:len(cases)]]
+    assert got == exp
+
+
+def test_mvp_conversion_host_build_equals_reference_source():
+    """mm_mvp.cuh (MM-MVP conversion, the code behind mmgpu_mvp_convert) compiled for the host == the REFERENCE's
+    own MVReprojection::motionVectorInDesiredMotionModel (oracle/_ref/libvtmmap.so: MVReprojection.cpp + MotionModels/*.cpp
+    compiled unchanged), for every ordered pair of the 11 motion models, random positions / blocks / MVs, luma and chroma MV
+    precisions, zero MVs, poles, the ERP seam, and two different epipoles for GEODESIC_CAMPOSE."""
+    import ref_lib as rl
+    if not rl.map_available():
+        pytest.skip("oracle/_ref/libvtmmap.so not built (reference sources absent)")
+    import vvc_extension_mm_b200 as mm
+    so = _build("map_host.cpp", os.path.join(BUILD, "libmaphost.so"), ["-fPIC", "-shared"])
+    Hn = C.CDLL(so)
+    Hn.mmhost_create.restype = C.c_void_p
+    Hn.mmhost_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+    Hn.mmhost_mvp.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
+    for (W, Hh, flavor) in ((2048, 1024, 1), (1280, 640, 0)):
+        r = rl.RefMap(W, Hh, 1.0, flavor)
+        e1, e2 = [0.3, -0.5, 0.81], [0.1, 0.9, -0.2]
+        r.set_epipole(e1)
+        r.set_epipole2(e2)
+        R = {7: mm.rodrigues([1, 0, 0]), 8: mm.rodrigues([0, 1, 0]), 9: mm.rodrigues([0, 0, 1])}
+        R1, R2 = mm.rodrigues(e1), mm.rodrigues(e2)
+        h = Hn.mmhost_create(W, Hh, 1.0, flavor, 1)
+        rng = np.random.default_rng(W)
+        n = bad = nz = 0
+        for mo in range(11):
+            for md in range(11):
+                for k in range(40):
+                    cw, chh = [int(2 ** rng.integers(2, 8)) for _ in range(2)]
+                    uw, uh = [int(2 ** rng.integers(2, 8)) for _ in range(2)]
+                    cx, cy = int(rng.integers(0, (W - cw) // 4 + 1)) * 4, int(rng.integers(0, (Hh - chh) // 4 + 1)) * 4
+                    ux, uy = int(rng.integers(0, (W - uw) // 4 + 1)) * 4, int(rng.integers(0, (Hh - uh) // 4 + 1)) * 4
+                    if k % 7 == 0: uy = 0                      # pole
+                    if k % 11 == 0: ux = W - uw                # ERP seam
+                    pos = (ux + int(rng.integers(0, uw)), uy + int(rng.integers(0, uh)))
+                    mv = (int(rng.integers(-600, 600)), int(rng.integers(-300, 300)))
+                    if k % 13 == 0: mv = (0, 0)
+                    if k % 17 == 0: mv = (mv[0], 0)
+                    shift = (4, 4) if k % 3 else (5, 5)
+                    po, pd = (7 if k % 2 else 0), (7 if k % 4 < 2 else 0)        # which epipole each side uses
+                    exp = r.mvp(pos, mv, mo, md, (cx, cy, cw, chh), (ux, uy, uw, uh), shift, po, pd)
+                    Ro = R.get(mo, R2 if po == 7 else R1)
+                    Rd = R.get(md, R2 if pd == 7 else R1)
+                    out = np.zeros(2, dtype=np.int32)
+                    Hn.mmhost_mvp(h, pos[0], pos[1], mv[0], mv[1], mo, md, shift[0], shift[1], Ro.ctypes.data, Rd.ctypes.data,
+                                  int(po == pd), cx, cy, cw, chh, ux, uy, uw, uh, out.ctypes.data)
+                    n += 1
+                    nz += int(exp != (0, 0))
+                    if (int(out[0]), int(out[1])) != exp:
+                        bad += 1
+                        if bad < 5:
+                            print("MVP mismatch", W, mo, md, pos, mv, shift, (cx, cy, cw, chh), (ux, uy, uw, uh), exp, out)
+        assert bad == 0, (bad, n)
+        assert nz > n // 2

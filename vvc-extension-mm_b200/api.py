@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode", "mmgpu_mc_jobs_device", "mmgpu_set_refs_unpadded_device", "mmgpu_mvp_convert",
 ]
 
 
@@ -85,11 +85,13 @@ def load_library():
         f.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_set_ref_unpadded_wrap.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32), i32]
     L.mmgpu_set_ref_unpadded_device.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32), i32, vp]
+    L.mmgpu_set_refs_unpadded_device.argtypes = [vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32), i32, vp]
     L.mmgpu_rodrigues.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mmgpu_fixed_to_float.restype = C.c_float
     L.mmgpu_fixed_to_float.argtypes = [C.c_int32, C.c_int32]
     L.mmgpu_set_rotation.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.mmgpu_reproject.argtypes = [vp, i32, i32, i32, i32, i32, i32, Mv, i32, i32, vp, vp]
+    L.mmgpu_mvp_convert.argtypes = [vp, i32, i32, Mv] + [i32] * 14 + [C.POINTER(Mv)]
     L.mmgpu_mc.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, Mv, i32, i32, i32, i32, i32, i32, vp, i32]
     L.mmgpu_add_avg.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32]
     L.mmgpu_set_org.argtypes = [vp, vp, i32, i32, i32]
@@ -107,6 +109,7 @@ def load_library():
     L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
     L.mmgpu_dmvr_costs.argtypes = [vp, i32, vp, i32, i32, vp]
     L.mmgpu_mc_jobs.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.mmgpu_mc_jobs_device.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_dmvr_decide.argtypes = [vp, i32, i32, vp, vp]
     _lib = L
     return L
@@ -260,9 +263,29 @@ class MmGpu:
         self._keep[("refu", slot)] = keep
         self._chk(self.L.mmgpu_set_ref_unpadded_device(self.h, slot, poc, p, s, int(wrap_offset), C.c_void_p(stream) if stream else None))
 
+    def set_refs_unpadded_device(self, slots, pocs, ptrs, strides, wrap_offset=0, stream=None, keep=None):
+        """n pictures at once (ptrs / strides: n x 3 device addresses / sample strides): one launch copies and pads them all."""
+        n = len(slots)
+        sl = (C.c_int32 * n)(*[int(v) for v in slots])
+        pc = (C.c_int32 * n)(*[int(v) for v in pocs])
+        flat_p = [int(v) for row in ptrs for v in (list(row) + [0] * (3 - len(row)))]
+        flat_s = [int(v) for row in strides for v in (list(row) + [0] * (3 - len(row)))]
+        pp = (C.c_void_p * (3 * n))(*flat_p)
+        ss = (C.c_int32 * (3 * n))(*flat_s)
+        self._keep[("refus", tuple(slots))] = keep
+        self._chk(self.L.mmgpu_set_refs_unpadded_device(self.h, n, sl, pc, pp, ss, int(wrap_offset), C.c_void_p(stream) if stream else None))
+
     def set_rotation(self, rot_slot, R):
         r = (C.c_float * 9)(*[float(v) for v in R])
         self._chk(self.L.mmgpu_set_rotation(self.h, rot_slot, r))
+
+    def mvp_convert(self, pos, mv, model_orig, model_desired, cand, cur, shift=(4, 4), rot_slots=(0, 0)):
+        """MVReprojection::motionVectorInDesiredMotionModel; cand / cur = (x, y, w, h) of the candidate's / the current block."""
+        out = Mv()
+        self._chk(self.L.mmgpu_mvp_convert(self.h, pos[0], pos[1], Mv(mv[0], mv[1]), model_orig, model_desired, shift[0], shift[1],
+                                           rot_slots[0], rot_slots[1], cand[0], cand[1], cand[2], cand[3], cur[0], cur[1], cur[2], cur[3],
+                                           C.byref(out)))
+        return out.hor, out.ver
 
     # -- a1 ------------------------------------------------------------------------------------
     def reproject(self, pos, size, mv, model, comp=0, chroma_fmt=0, rot_slot=0):
@@ -335,6 +358,13 @@ class MmGpu:
         p, s = self._planes([a.ctypes.data for a in planes], [a.strides[0] // 2 for a in planes])
         self._chk(self.L.mmgpu_mc_jobs(self.h, len(jobs), jobs.ctypes.data, clp[0], clp[1], p, s))
         return planes
+
+    def mc_jobs_device(self, jobs, ptrs, strides, clp=(0, 1023)):
+        """mc_jobs with the destination planes in device memory (ptrs: device addresses); asynchronous on the context's stream."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        self._keep["jobs"] = jobs
+        p, s = self._planes(list(ptrs), list(strides))
+        self._chk(self.L.mmgpu_mc_jobs_device(self.h, len(jobs), jobs.ctypes.data, clp[0], clp[1], p, s))
 
     def dmvr_costs(self, subpus, clp=(0, 1023)):
         """subpus: numpy array of DMVR_DTYPE -> (n, 25) uint64 xDMVRCost values at m_pSearchOffset."""

@@ -197,6 +197,15 @@ void mmk_map(cudaStream_t s, const MmParams& P, int first, int count, int model,
 // FIR + distortion (or prediction write-out) of items [first, first+count)
 void mmk_fir(cudaStream_t s, const MmParams& P, int first, int count, int mode, const int2* pos);
 void mmk_tan_selftest(cudaStream_t s, uint32_t stride, unsigned long long* out);
+#define MM_PAD_MAX 24   // planes per k_pad_planes launch (8 pictures x 3 components)
+struct MmPadPlane
+{
+  const int16_t* src;   // un-padded plane
+  int16_t* dst00;       // sample (0,0) of the padded plane
+  int32_t srcStride, dstStride, w, h, mx, my, xoff, pad;
+};
+struct MmPadJobs { MmPadPlane p[MM_PAD_MAX]; };
+void mmk_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxGroups, int maxRows);
 void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my, int xoff);
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi);

@@ -222,6 +222,44 @@ __global__ void k_extend_border(int16_t* plane00, int stride, int w, int h, int 
   plane00[(long)Y * stride + X] = plane00[(long)sy * stride + sx];
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_pad_planes: un-padded planes (e.g. the landing buffer of an all-gather) -> padded reference planes, copy and border
+// extension (Picture::extendPicBorder / extendWrapBorder) in ONE launch for up to MM_PAD_MAX planes: blockIdx.z = plane,
+// one thread per 8 samples (16 bytes) of a padded row; interior groups are one 16-byte load + store.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pad_planes(MmPadJobs J)
+{
+  const MmPadPlane p = J.p[blockIdx.z];
+  const int gpr = (p.w + 2 * p.mx) >> 3;                       // 8-sample groups per padded row (w, mx multiples of 8)
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = (int)blockIdx.y - p.my;
+  if (g >= gpr || (int)blockIdx.y >= p.h + 2 * p.my) return;
+  const int X0 = g * 8 - p.mx;
+  const int sy = min(max(Y, 0), p.h - 1);
+  const int16_t* srow = p.src + (long)sy * p.srcStride;
+  int16_t* drow = p.dst00 + (long)Y * p.dstStride + X0;
+  uint4 v;
+  if (X0 >= 0 && X0 + 8 <= p.w)
+    v = *reinterpret_cast<const uint4*>(srow + X0);
+  else
+  {
+    int16_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+      const int X = X0 + i;
+      int sx;
+      if (X < 0) sx = (-1 - X < p.xoff) ? X + p.xoff : 0;
+      else if (X >= p.w) sx = (X - p.w < p.xoff) ? X - p.xoff : p.w - 1;
+      else sx = X;
+      t[i] = srow[sx];
+    }
+    v.x = (uint16_t)t[0] | ((uint32_t)(uint16_t)t[1] << 16); v.y = (uint16_t)t[2] | ((uint32_t)(uint16_t)t[3] << 16);
+    v.z = (uint16_t)t[4] | ((uint32_t)(uint16_t)t[5] << 16); v.w = (uint16_t)t[6] | ((uint32_t)(uint16_t)t[7] << 16);
+  }
+  *reinterpret_cast<uint4*>(drow) = v;
+}
+
 __global__ void k_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                           int shift, int offset, int lo, int hi)
 {
@@ -242,6 +280,11 @@ void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int 
 {
   dim3 tb(32, 8), gr((w + 2 * mx + 31) / 32, (h + 2 * my + 7) / 8);
   k_extend_border<<<gr, tb, 0, s>>>(plane00, stride, w, h, mx, my, xoff);
+}
+void mmk_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxGroups, int maxRows)
+{
+  dim3 gr((maxGroups + 255) / 256, maxRows, nPlanes);
+  k_pad_planes<<<gr, 256, 0, s>>>(J);
 }
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi)

@@ -74,7 +74,7 @@ __global__ void k_mc_generic(MmParams P, int refSlot, int comp, int csx, int csy
 // One sub-block of one component into `out` (row stride 4): mapping (or classic MV) + OOB rule + FIR.
 __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w,
                                                int h, mmgpu_mv mv, int model, int rotSlot, bool bi, int row, int col,
-                                               int16_t* out)
+                                               const MmCand& c, int16_t* out)
 {
   const int sbw = 4 >> csx, sbh = 4 >> csy;
   const MmRef ref = P.refs[refSlot];
@@ -89,8 +89,6 @@ __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, i
   else
   {
     const float* R = mm_rot_ptr(P.rot, model, rotSlot);
-    MmCand c;
-    mm_cand_setup(P.g, model, comp == 0, x, y, w, h, mv.hor, mv.ver, R, &c);
     mm_subblock_pos(P.g, P.mpa, P.mpaVip, P.thTab, P.phTab, model, comp, csx, csy, x, y, w, h, c, R, row, col, &fx, &fy);
     const int xP = fx >> shH, yP = fy >> shV;
     const int picw = P.picW >> csx, pich = P.picH >> csy;
@@ -106,7 +104,15 @@ __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, i
   int xF = fx & ((1 << shH) - 1), yF = fy & ((1 << shV) - 1);
   mm_classic_chroma_phase(model, comp, csx, csy, &xF, &yF);
   if (comp == 0)
-    mm_fir_generic<8>(P.fir, ref.plane00[0], ref.stride[0], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
+  {
+    // luma: packed dp2a two-pass FIR (same identity as k_fir; the bi variant keeps the 14-bit intermediate like k_dmvr)
+    const uint2* btaps = reinterpret_cast<const uint2*>(P.hTaps + MM_HTAPS_WORDS);
+    int pred[16];
+    if (bi) mm_fir_luma4x4_wide<true>(P.fir, __ldg(btaps + xF), __ldg(btaps + yF), ref.plane00[0], ref.stride[0], xP, yP, xF, yF, P.clpMin, P.clpMax, pred);
+    else mm_fir_luma4x4_wide<false>(P.fir, __ldg(btaps + xF), __ldg(btaps + yF), ref.plane00[0], ref.stride[0], xP, yP, xF, yF, P.clpMin, P.clpMax, pred);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = (int16_t)pred[i];
+  }
   else
     mm_fir_generic<4>(P.fir, ref.plane00[comp], ref.stride[comp], xP, yP, xF, yF, sbw, sbh, !bi, P.clpMin, P.clpMax, out, 4);
 }
@@ -124,14 +130,23 @@ __global__ void k_mc_jobs(MmParams P, const mmgpu_mc_job* __restrict__ jobs, int
   const int rows = j.h / sbh, cols = j.w / sbw;
   int16_t* plane = j.comp == 0 ? dstY : (j.comp == 1 ? dstCb : dstCr);
   const int stride = j.comp == 0 ? strideY : strideC;
+  // per-(block, MV) scalars of the motion model: once per job and list, not once per sub-block
+  __shared__ MmCand s_c[2];
+  if (j.model != MM_CLASSIC && threadIdx.x < (j.bi ? 2 : 1))
+  {
+    const int l = threadIdx.x;
+    const mmgpu_mv mv = l ? j.mv1 : j.mv0;
+    mm_cand_setup(P.g, j.model, j.comp == 0, j.x, j.y, j.w, j.h, mv.hor, mv.ver, mm_rot_ptr(P.rot, j.model, l ? j.rot_slot1 : j.rot_slot0), &s_c[l]);
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
   {
     const int col = i / rows, row = i - col * rows;
     int16_t a[16], b[16];
-    mm_mc_subblock(P, j.ref_slot0, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv0, j.model, j.rot_slot0, j.bi != 0, row, col, a);
+    mm_mc_subblock(P, j.ref_slot0, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv0, j.model, j.rot_slot0, j.bi != 0, row, col, s_c[0], a);
     if (j.bi)
     {
-      mm_mc_subblock(P, j.ref_slot1, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv1, j.model, j.rot_slot1, true, row, col, b);
+      mm_mc_subblock(P, j.ref_slot1, j.comp, csx, csy, j.x, j.y, j.w, j.h, j.mv1, j.model, j.rot_slot1, true, row, col, s_c[1], b);
       for (int r = 0; r < sbh; ++r)
         for (int q = 0; q < sbw; ++q)
           a[r * 4 + q] = (int16_t)mm_clip(((int)a[r * 4 + q] + (int)b[r * 4 + q] + avgOffset) >> avgShift, P.clpMin, P.clpMax);

@@ -241,12 +241,12 @@ MM_HD void mm_mpa_to_perspective(const MmGeom& g, int model, float X, float Y, b
 }
 // ---- per-candidate scalars -----------------------------------------------------------------------
 // blk = position/size of pu.blocks[compID] (component units, quirk Q1); R = rotation of the GED model.
-MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int posY, int sizeW, int sizeH, int mvHor,
-                         int mvVer, const float* R, MmCand* c)
+// mvX, mvY: the motion vector as float (MVReprojection.cpp:123-124 for the 1/16-pel MVs of MC / ME; the MM-MVP conversion
+// passes MVs of other precisions, MVReprojection.cpp:186-187)
+MM_HD void mm_cand_setup_float(const MmGeom& g, int model, bool isLuma, int posX, int posY, int sizeW, int sizeH, float mvX,
+                               float mvY, const float* R, MmCand* c)
 {
   const bool fma = g.fmaBuild != 0;
-  const float mvX = MM_FADD((float)(mvHor >> 4), MM_FDIV((float)(mvHor & 15), 16.0f));
-  const float mvY = MM_FADD((float)(mvVer >> 4), MM_FDIV((float)(mvVer & 15), 16.0f));
   c->mvX = mvX;
   c->mvY = mvY;
   c->mvZero = (mvX == 0.0f && mvY == 0.0f) ? 1 : 0;
@@ -313,6 +313,14 @@ MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int 
       c->p[0] = MM_FDIV(mm_sinf(MM_FADD(sc[1], c->p[1]), fma), mm_sinf(c->p[1], fma));
     }
   }
+}
+
+MM_HD void mm_cand_setup(const MmGeom& g, int model, bool isLuma, int posX, int posY, int sizeW, int sizeH, int mvHor,
+                         int mvVer, const float* R, MmCand* c)
+{
+  const float mvX = MM_FADD((float)(mvHor >> 4), MM_FDIV((float)(mvHor & 15), 16.0f));
+  const float mvY = MM_FADD((float)(mvVer >> 4), MM_FDIV((float)(mvVer & 15), 16.0f));
+  mm_cand_setup_float(g, model, isLuma, posX, posY, sizeW, sizeH, mvX, mvY, R, c);
 }
 
 // ---- one sub-block -------------------------------------------------------------------------------

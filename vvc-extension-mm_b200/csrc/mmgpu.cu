@@ -11,6 +11,7 @@
 #include <vector>
 #include "mm_common.cuh"
 #include "mm_fir.cuh"
+#include "mm_mvp.cuh"
 
 #define MM_MAX_ROT 64
 
@@ -68,6 +69,7 @@ struct mmgpu_ctx
   std::vector<int16_t*> ownedPlanes;  // [slot*3+c] base allocations owned by the context
   // rotations
   float* dRot;
+  std::vector<float> hRot;  // host mirror (mmgpu_mvp_convert runs on the host)
   // MPA caches
   float2* dMpa[3];
   uint8_t* dMpaVip[3];
@@ -306,6 +308,7 @@ extern "C" int mmgpu_create(const mmgpu_config* cfg, mmgpu_ctx** out)
     mmgpu_rodrigues(ez, &rot[18]);
     for (int s = 0; s < MM_MAX_ROT; ++s) mmgpu_rodrigues(e0, &rot[9 * (MM_ROT_USER0 + s)]);  // EpipoleList.h:15-17
     CUC(cudaMemcpy(ctx->dRot, rot.data(), rot.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->hRot = rot;
   }
   const int n4 = g.rows4 * g.cols4;
   for (int m = 0; m < 3; ++m)
@@ -671,11 +674,65 @@ extern "C" int mmgpu_set_ref_unpadded_device(mmgpu_ctx* ctx, int slot, int poc, 
   return MMGPU_OK;
 }
 
+extern "C" int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs,
+                                              const int16_t* const* d_plane, const int32_t* stride, int wrap_offset, void* stream)
+{
+  if (!ctx || !slots || !pocs || !d_plane || !stride || n <= 0) return MMGPU_ERR_ARG;
+  const int nc = numComps(ctx);
+  if (n * nc > MM_PAD_MAX) return fail(ctx, MMGPU_ERR_ARG, "too many pictures for one call");
+  if (wrap_offset < 0 || wrap_offset > ctx->cfg.pic_w) return fail(ctx, MMGPU_ERR_ARG, "wrap_offset must be 0..pic_w");
+  if ((ctx->cfg.pic_w & 15) || (ctx->cfg.margin & 15)) return fail(ctx, MMGPU_ERR_ARG, "batched padding needs picture width and margin multiples of 16");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  MmPadJobs J;
+  memset(&J, 0, sizeof(J));
+  int maxGroups = 0, maxRows = 0, k = 0;
+  for (int i = 0; i < n; ++i)
+  {
+    const int slot = slots[i];
+    if (slot < 0 || slot >= ctx->cfg.max_refs) return fail(ctx, MMGPU_ERR_ARG, "ref slot out of range");
+    MmRef r;
+    memset(&r, 0, sizeof(r));
+    r.poc = pocs[i];
+    bool fresh = false;
+    for (int c = 0; c < nc; ++c, ++k)
+    {
+      const int16_t* src = d_plane[i * 3 + c];
+      if (!src || ((uintptr_t)src & 15) || (stride[i * 3 + c] & 7)) return fail(ctx, MMGPU_ERR_ARG, "planes must be 16-byte aligned, stride a multiple of 8");
+      int w, h, mx, my, pitch;
+      int16_t* d00;
+      compDims(ctx, c, &w, &h, &mx, &my);
+      if (!ctx->ownedPlanes[(size_t)slot * 3 + c]) fresh = true;
+      int rc = ensureOwnedPlane(ctx, slot, c, &d00, &pitch);
+      if (rc) return rc;
+      MmPadPlane& p = J.p[k];
+      p.src = src; p.dst00 = d00; p.srcStride = stride[i * 3 + c]; p.dstStride = pitch; p.w = w; p.h = h; p.mx = mx; p.my = my;
+      p.xoff = wrap_offset >> scaleX(c, ctx->cfg.chroma_fmt);
+      maxGroups = std::max(maxGroups, (w + 2 * mx) >> 3);
+      maxRows = std::max(maxRows, h + 2 * my);
+      r.plane00[c] = d00;
+      r.stride[c] = pitch;
+    }
+    if (fresh || ctx->hRefs[slot].plane00[0] != r.plane00[0])
+    {
+      ctx->hRefs[slot] = r;
+      int rc = publishRef(ctx, slot);
+      if (rc) return rc;
+    }
+    else ctx->hRefs[slot].poc = pocs[i];
+  }
+  mmk_pad_planes(st, J, k, maxGroups, maxRows);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return MMGPU_OK;
+}
+
 extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9])
 {
   if (!ctx || !R) return MMGPU_ERR_ARG;
   if (rot_slot < 0 || rot_slot >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "rotation slot out of range");
   cudaSetDevice(ctx->cfg.device);
+  memcpy(&ctx->hRot[9 * (MM_ROT_USER0 + rot_slot)], R, 9 * sizeof(float));
   CU(cudaMemcpyAsync(ctx->dRot + 9 * (MM_ROT_USER0 + rot_slot), R, 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return MMGPU_OK;
@@ -758,6 +815,29 @@ extern "C" int mmgpu_reproject(mmgpu_ctx* ctx, int comp, int chroma_fmt, int x, 
   CU(cudaMemcpyAsync(out_x, dx, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(out_y, dy, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+// ---- 8f-1: MM-MVP conversion (host) ---------------------------------------------------------------------------
+extern "C" int mmgpu_mvp_convert(mmgpu_ctx* ctx, int pos_x, int pos_y, mmgpu_mv mv_orig, int model_orig, int model_desired,
+                                 int shift_hor, int shift_ver, int rot_slot_orig, int rot_slot_desired, int cand_x, int cand_y,
+                                 int cand_w, int cand_h, int cur_x, int cur_y, int cur_w, int cur_h, mmgpu_mv* out)
+{
+  if (!ctx || !out) return MMGPU_ERR_ARG;
+  if (model_orig < MMGPU_CLASSIC || model_orig > MMGPU_GEODESIC_CAMPOSE || model_desired < MMGPU_CLASSIC || model_desired > MMGPU_GEODESIC_CAMPOSE)
+    return fail(ctx, MMGPU_ERR_ARG, "bad model");
+  if (shift_hor < 0 || shift_hor > 8 || shift_ver < 0 || shift_ver > 8) return fail(ctx, MMGPU_ERR_ARG, "bad shift");
+  if (rot_slot_orig < 0 || rot_slot_orig >= MM_MAX_ROT || rot_slot_desired < 0 || rot_slot_desired >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad rot_slot");
+  auto rotOf = [&](int model, int slot) -> const float* {
+    const int s = (model == MMGPU_GEODESIC_CAMPOSE) ? (MM_ROT_USER0 + slot) : (model - MMGPU_GEODESIC_X);
+    return &ctx->hRot[9 * (s < 0 ? 0 : s)];
+  };
+  int h = 0, v = 0;
+  mm_mvp_convert(ctx->g, pos_x, pos_y, mv_orig.hor, mv_orig.ver, model_orig, model_desired, shift_hor, shift_ver, rotOf(model_orig, rot_slot_orig),
+                 rotOf(model_desired, rot_slot_desired), rot_slot_orig == rot_slot_desired, cand_x, cand_y, cand_w, cand_h, cur_x, cur_y, cur_w,
+                 cur_h, &h, &v);
+  out->hor = h;
+  out->ver = v;
   return MMGPU_OK;
 }
 
@@ -1298,13 +1378,9 @@ extern "C" int mmgpu_dmvr_decide(const uint64_t costs25[25], int w, int h, int32
 }
 
 // ---- whole-picture reconstruction shape -------------------------------------------------------------------
-extern "C" int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max,
-                             int16_t* const dst[3], const int32_t dst_stride[3])
+static int checkJobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, bool used[3], long area[3])
 {
-  if (!ctx || !jobs || !dst || !dst_stride || n_jobs <= 0) return MMGPU_ERR_ARG;
-  cudaSetDevice(ctx->cfg.device);
   const int fmt = ctx->cfg.chroma_fmt;
-  bool used[3] = {false, false, false};
   for (int i = 0; i < n_jobs; ++i)
   {
     const mmgpu_mc_job& j = jobs[i];
@@ -1320,8 +1396,53 @@ extern "C" int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* job
       if (ro < 0 || ro >= MM_MAX_ROT) return fail(ctx, MMGPU_ERR_ARG, "bad rot_slot in job");
     }
     used[j.comp] = true;
+    area[j.comp] += (long)j.w * j.h;
   }
+  return MMGPU_OK;
+}
+
+static int launchJobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max, int16_t* const d[3], const int pitch[3])
+{
   int rc;
+  if ((rc = ensureCap(ctx, &ctx->dJobs, &ctx->capJobs, (size_t)n_jobs))) return rc;
+  CU(cudaMemcpyAsync(ctx->dJobs, jobs, sizeof(mmgpu_mc_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+  MmParams P = baseParams(ctx);
+  P.clpMin = clp_min;
+  P.clpMax = clp_max;
+  P.oobMode = MMGPU_OOB_PRED;
+  const int fmt = ctx->cfg.chroma_fmt;
+  const int shift = ctx->fir.cpShift + 1, offset = (1 << (shift - 1)) + 2 * 8192;
+  mmk_mc_jobs(ctx->stream, P, n_jobs, ctx->dJobs, d[0], d[1], d[2], pitch[0], pitch[1], scaleX(1, fmt), scaleY(1, fmt), shift, offset);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_mc_jobs_device(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max,
+                                    int16_t* const d_dst[3], const int32_t dst_stride[3])
+{
+  if (!ctx || !jobs || !d_dst || !dst_stride || n_jobs <= 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  bool used[3] = {false, false, false};
+  long area[3] = {0, 0, 0};
+  int rc = checkJobs(ctx, n_jobs, jobs, used, area);
+  if (rc) return rc;
+  if (numComps(ctx) == 3 && used[1] && used[2] && dst_stride[1] != dst_stride[2]) return fail(ctx, MMGPU_ERR_ARG, "Cb and Cr planes must share one stride");
+  for (int c = 0; c < numComps(ctx); ++c)
+    if (used[c] && !d_dst[c]) return fail(ctx, MMGPU_ERR_ARG, "null destination plane");
+  const int pitch[3] = {dst_stride[0], dst_stride[1], dst_stride[2]};
+  return launchJobs(ctx, n_jobs, jobs, clp_min, clp_max, d_dst, pitch);
+}
+
+extern "C" int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max,
+                             int16_t* const dst[3], const int32_t dst_stride[3])
+{
+  if (!ctx || !jobs || !dst || !dst_stride || n_jobs <= 0) return MMGPU_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  bool used[3] = {false, false, false};
+  long area[3] = {0, 0, 0};
+  int rc = checkJobs(ctx, n_jobs, jobs, used, area);
+  if (rc) return rc;
   int pitch[3] = {0, 0, 0}, cw[3], ch[3];
   for (int c = 0; c < numComps(ctx); ++c)
   {
@@ -1331,21 +1452,13 @@ extern "C" int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* job
     if (!used[c]) continue;
     if (!dst[c]) return fail(ctx, MMGPU_ERR_ARG, "null destination plane");
     if ((rc = ensureCap(ctx, &ctx->dPic[c], &ctx->capPic[c], (size_t)pitch[c] * ch[c]))) return rc;
-    // the caller's picture already holds the samples of blocks this call does not cover
-    CU(cudaMemcpy2DAsync(ctx->dPic[c], 2 * (size_t)pitch[c], dst[c], 2 * (size_t)dst_stride[c], 2 * (size_t)cw[c], ch[c],
-                         cudaMemcpyHostToDevice, ctx->stream));
+    // the caller's picture already holds the samples of blocks this call does not cover; when the jobs tile the whole
+    // plane (blocks of one reconstruction never overlap) there is nothing to preserve and the upload is skipped
+    if (area[c] < (long)cw[c] * ch[c])
+      CU(cudaMemcpy2DAsync(ctx->dPic[c], 2 * (size_t)pitch[c], dst[c], 2 * (size_t)dst_stride[c], 2 * (size_t)cw[c], ch[c],
+                           cudaMemcpyHostToDevice, ctx->stream));
   }
-  if ((rc = ensureCap(ctx, &ctx->dJobs, &ctx->capJobs, (size_t)n_jobs))) return rc;
-  CU(cudaMemcpyAsync(ctx->dJobs, jobs, sizeof(mmgpu_mc_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
-  MmParams P = baseParams(ctx);
-  P.clpMin = clp_min;
-  P.clpMax = clp_max;
-  P.oobMode = MMGPU_OOB_PRED;
-  const int shift = ctx->fir.cpShift + 1, offset = (1 << (shift - 1)) + 2 * 8192;
-  mmk_mc_jobs(ctx->stream, P, n_jobs, ctx->dJobs, ctx->dPic[0], ctx->dPic[1], ctx->dPic[2], pitch[0], pitch[1], scaleX(1, fmt),
-              scaleY(1, fmt), shift, offset);
-  ctx->launches++;
-  CU(cudaGetLastError());
+  if ((rc = launchJobs(ctx, n_jobs, jobs, clp_min, clp_max, ctx->dPic, pitch))) return rc;
   for (int c = 0; c < numComps(ctx); ++c)
     if (used[c])
       CU(cudaMemcpy2DAsync(dst[c], 2 * (size_t)dst_stride[c], ctx->dPic[c], 2 * (size_t)pitch[c], 2 * (size_t)cw[c], ch[c],

@@ -26,6 +26,154 @@ struct PelBuf { int16_t* buf; int stride; unsigned width, height; };
 typedef uint64_t Distortion;                       // TypeDef.h:282
 enum MvPrecision { MV_PRECISION_INTERNAL = 0, MV_PRECISION_QUARTER = 2, MV_PRECISION_HALF = 3, MV_PRECISION_INT = 4 };  // value = left shift to internal
 
+// ---- a14: candidate enumerators of the integer motion search (data only) + the compare chain of xTZSearchHelp ------------
+// Each enumerator lists, in the reference's visiting order, the points one call of the reference function evaluates; the
+// whole list goes to the device as ONE batch (evalCandidates) and tzReplay() then walks the reference's compare chain over
+// the returned distortions, so the search takes the same decisions with the same uiBestSad.
+struct SearchRange { int left, right, top, bottom; };           // EncoderLib/InterSearch.h SearchRange
+struct TzPoint { int x, y; uint8_t pointNr; unsigned distance; };
+struct TzBest                                                    // the IntTZSearchStruct fields xTZSearchHelp updates
+{
+  Distortion uiBestSad; int iBestX, iBestY; unsigned uiBestDistance, uiBestRound; uint8_t ucPointNr;
+};
+
+// xTZ8PointDiamondSearch (EncoderLib/InterSearch.cpp:535-737)
+inline void tzDiamondRound(const SearchRange& sr, int startX, int startY, int dist, bool cornersAtDist1, std::vector<TzPoint>& out)
+{
+  const int top = startY - dist, bottom = startY + dist, left = startX - dist, right = startX + dist;
+  auto add = [&](int x, int y, int nr, int d) { out.push_back(TzPoint{x, y, (uint8_t)nr, (unsigned)d}); };
+  if (dist == 1)
+  {
+    if (top >= sr.top)
+    {
+      if (cornersAtDist1)
+      {
+        if (left >= sr.left) add(left, top, 1, dist);
+        add(startX, top, 2, dist);
+        if (right <= sr.right) add(right, top, 3, dist);
+      }
+      else add(startX, top, 2, dist);
+    }
+    if (left >= sr.left) add(left, startY, 4, dist);
+    if (right <= sr.right) add(right, startY, 5, dist);
+    if (bottom <= sr.bottom)
+    {
+      if (cornersAtDist1)
+      {
+        if (left >= sr.left) add(left, bottom, 6, dist);
+        add(startX, bottom, 7, dist);
+        if (right <= sr.right) add(right, bottom, 8, dist);
+      }
+      else add(startX, bottom, 7, dist);
+    }
+    return;
+  }
+  const bool inside = top >= sr.top && left >= sr.left && right <= sr.right && bottom <= sr.bottom;
+  if (dist <= 8)
+  {
+    const int h = dist >> 1, top2 = startY - h, bottom2 = startY + h, left2 = startX - h, right2 = startX + h;
+    if (inside)
+    {
+      add(startX, top, 2, dist); add(left2, top2, 1, h); add(right2, top2, 3, h); add(left, startY, 4, dist);
+      add(right, startY, 5, dist); add(left2, bottom2, 6, h); add(right2, bottom2, 8, h); add(startX, bottom, 7, dist);
+      return;
+    }
+    if (top >= sr.top) add(startX, top, 2, dist);
+    if (top2 >= sr.top)
+    {
+      if (left2 >= sr.left) add(left2, top2, 1, h);
+      if (right2 <= sr.right) add(right2, top2, 3, h);
+    }
+    if (left >= sr.left) add(left, startY, 4, dist);
+    if (right <= sr.right) add(right, startY, 5, dist);
+    if (bottom2 <= sr.bottom)
+    {
+      if (left2 >= sr.left) add(left2, bottom2, 6, h);
+      if (right2 <= sr.right) add(right2, bottom2, 8, h);
+    }
+    if (bottom <= sr.bottom) add(startX, bottom, 7, dist);
+    return;
+  }
+  // dist > 8: the four tips, then three rings of four points along the edges of the diamond
+  if (inside)
+  {
+    add(startX, top, 0, dist); add(left, startY, 0, dist); add(right, startY, 0, dist); add(startX, bottom, 0, dist);
+    for (int i = 1; i < 4; ++i)
+    {
+      const int q = (dist >> 2) * i, yT = top + q, yB = bottom - q, xL = startX - q, xR = startX + q;
+      add(xL, yT, 0, dist); add(xR, yT, 0, dist); add(xL, yB, 0, dist); add(xR, yB, 0, dist);
+    }
+    return;
+  }
+  if (top >= sr.top) add(startX, top, 0, dist);
+  if (left >= sr.left) add(left, startY, 0, dist);
+  if (right <= sr.right) add(right, startY, 0, dist);
+  if (bottom <= sr.bottom) add(startX, bottom, 0, dist);
+  for (int i = 1; i < 4; ++i)
+  {
+    const int q = (dist >> 2) * i, yT = top + q, yB = bottom - q, xL = startX - q, xR = startX + q;
+    if (yT >= sr.top)
+    {
+      if (xL >= sr.left) add(xL, yT, 0, dist);
+      if (xR <= sr.right) add(xR, yT, 0, dist);
+    }
+    if (yB <= sr.bottom)
+    {
+      if (xL >= sr.left) add(xL, yB, 0, dist);
+      if (xR <= sr.right) add(xR, yB, 0, dist);
+    }
+  }
+}
+
+// xTZ2PointSearch (InterSearch.cpp:456-481): the two untested neighbours of the best point of a distance-1 round
+inline void tz2Point(const SearchRange& sr, int bestX, int bestY, uint8_t pointNr, std::vector<TzPoint>& out)
+{
+  static const int xo[2][9] = {{0, -1, -1, 0, -1, +1, -1, -1, +1}, {0, 0, +1, +1, -1, +1, 0, +1, 0}};
+  static const int yo[2][9] = {{0, 0, -1, -1, +1, -1, 0, +1, 0}, {0, -1, -1, 0, -1, +1, +1, +1, +1}};
+  for (int k = 0; k < 2; ++k)
+  {
+    const int x = bestX + xo[k][pointNr], y = bestY + yo[k][pointNr];
+    if (x >= sr.left && x <= sr.right && y >= sr.top && y <= sr.bottom) out.push_back(TzPoint{x, y, 0, 2});
+  }
+}
+
+// raster scan of xTZSearch (InterSearch.cpp:5611-5647) and, with step 1, the full grid of xPatternSearch (:5287-5322)
+inline void tzRaster(const SearchRange& sr, int step, std::vector<TzPoint>& out)
+{
+  for (int y = sr.top; y <= sr.bottom; y += step)
+    for (int x = sr.left; x <= sr.right; x += step) out.push_back(TzPoint{x, y, 0, (unsigned)step});
+}
+
+// xTZSearchHelp (InterSearch.cpp:363-453, the branch taken by every motion model but CLASSIC with subShiftMode 1):
+// motion cost only added when the raw distortion already beats the best; strict "<" twice.
+template <typename MvCost>
+inline void tzReplay(const std::vector<TzPoint>& pts, const Distortion* dist, MvCost mvCost, TzBest& b)
+{
+  for (size_t i = 0; i < pts.size(); ++i)
+  {
+    Distortion sad = dist[i];
+    if (sad < b.uiBestSad)
+    {
+      sad += mvCost(pts[i].x, pts[i].y);
+      if (sad < b.uiBestSad)
+      {
+        b.uiBestSad = sad; b.iBestX = pts[i].x; b.iBestY = pts[i].y; b.uiBestDistance = pts[i].distance; b.uiBestRound = 0;
+        b.ucPointNr = pts[i].pointNr;
+      }
+    }
+  }
+}
+// xPatternSearch's chain (InterSearch.cpp:5299-5317): cost always added, strict "<"
+template <typename MvCost>
+inline void fullSearchReplay(const std::vector<TzPoint>& pts, const Distortion* dist, MvCost mvCost, Distortion& best, int& bestX, int& bestY)
+{
+  for (size_t i = 0; i < pts.size(); ++i)
+  {
+    const Distortion sad = dist[i] + mvCost(pts[i].x, pts[i].y);
+    if (sad < best) { best = sad; bestX = pts[i].x; bestY = pts[i].y; }
+  }
+}
+
 class GpuInterPrediction
 {
 public:
@@ -127,6 +275,20 @@ public:
       if (u < best) { best = u; rcMvRefined = cand[i]; }
     }
     return best;
+  }
+
+  // One call of xTZ8PointDiamondSearch / raster / 2-point on the device: the enumerated points as one batch, then the
+  // reference's compare chain (uiBestRound is incremented by the diamond round itself, InterSearch.cpp:549).
+  template <typename MvCost>
+  void tzEvaluate(const std::vector<TzPoint>& pts, const Position& blkPos, const Size& blkSize, int refSlot, int motionModel,
+                  const CPelBuf& pcPatternKey, int subShift, const ClpRng& clpRng, MvCost mvCost, TzBest& best, int rotSlot = 0)
+  {
+    if (pts.empty()) return;
+    std::vector<Mv> mvs(pts.size());
+    for (size_t i = 0; i < pts.size(); ++i) { mvs[i].hor = pts[i].x; mvs[i].ver = pts[i].y; }
+    std::vector<Distortion> d;
+    evalCandidates(blkPos, blkSize, refSlot, motionModel, pcPatternKey, mvs, MV_PRECISION_INT, false, subShift, clpRng, d, rotSlot);
+    tzReplay(pts, d.data(), mvCost, best);
   }
 
   mmgpu_ctx* ctx() { return m_ctx; }
