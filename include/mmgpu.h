@@ -137,6 +137,13 @@ int mmgpu_mvp_convert(mmgpu_ctx* ctx, int pos_x, int pos_y, mmgpu_mv mv_orig, in
 int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, int x, int y, int w, int h, mmgpu_mv mv, int model,
              int rot_slot, int bi, int clp_min, int clp_max, int oob_mode, int16_t* dst, int dst_stride);
 
+/* xPredInterBlk with bioApplied (InterPrediction.cpp:1007-1015, 1054-1093): classic bi-prediction MC of a luma block into the
+ * BDOF work buffer -- the (w x h) 14-bit prediction at (2,2) of a buffer with stride w + 4 and, around it, the one-sample ring
+ * of integer-position reference samples ((ref << IF_INTERNAL_FRAC_BITS) - IF_INTERNAL_OFFS, taken at the nearest integer
+ * position: offset 1 where the fraction is below half a sample).  dst: HOST pointer to the start of that buffer
+ * (m_filteredBlockTmp[2 + refList][COMPONENT_Y]), (w + 4) x (h + 4) samples. */
+int mmgpu_mc_bdof(mmgpu_ctx* ctx, int ref_slot, int x, int y, int w, int h, mmgpu_mv mv, int clp_min, int clp_max, int16_t* dst);
+
 /* Whole-picture reconstruction shape (DecCu::xReconInter -> InterPrediction::motionCompensation -> xPredInterUni /
  * xPredInterBi, InterPrediction.cpp:455-681): many PUs x components in one call. */
 typedef struct {

@@ -673,6 +673,35 @@ void orc_mc_block_classic(const int16_t* ref, int rs, int comp, int chroma_fmt, 
   }
 }
 
+void orc_mc_bdof(const int16_t* ref, int rs, int pos_x, int pos_y, int size_w, int size_h, int mv_hor, int mv_ver, int bd, int lo,
+                 int hi, int16_t* tmp)
+{
+  /* xPredInterBlk with bioApplied, luma (InterPrediction.cpp:1007-1015, 1054-1093): the 14-bit prediction goes to (2,2) of a
+   * buffer of stride width + 2*BIO_EXTEND_SIZE + 2 = w + 4; the ring around it holds integer-position reference samples
+   * (leftShift_round(ref, IF_INTERNAL_FRAC_BITS) - IF_INTERNAL_OFFS), fetched one sample up/left when the fraction is < 8. */
+  const int stride = size_w + 4, width = size_w + 4, height = size_h + 4;
+  orc_mc_block_classic(ref, rs, 0, 0, pos_x, pos_y, size_w, size_h, mv_hor, mv_ver, 1, bd, lo, hi, tmp + 2 * stride + 2, stride);
+  const int shift = 14 - bd < 2 ? 2 : 14 - bd;
+  const int xFrac = mv_hor & 15, yFrac = mv_ver & 15;
+  const int xOffset = (xFrac < 8) ? 1 : 0, yOffset = (yFrac < 8) ? 1 : 0;
+  const int16_t* refBuf = ref + (long)(pos_y + (mv_ver >> 4)) * rs + (pos_x + (mv_hor >> 4));
+  const int16_t* refPel = refBuf - yOffset * rs - xOffset;
+  int16_t* dstPel = tmp + stride + 1;
+  for (int w = 0; w < width - 2; w++) dstPel[w] = (int16_t)((int16_t)(refPel[w] << shift) - (int16_t)8192);
+  refPel = refBuf + (1 - yOffset) * rs - xOffset;
+  dstPel = tmp + 2 * stride + 1;
+  for (int h = 0; h < height - 2 - 2; h++)
+  {
+    dstPel[0] = (int16_t)((int16_t)(refPel[0] << shift) - (int16_t)8192);
+    dstPel[width - 3] = (int16_t)((int16_t)(refPel[width - 3] << shift) - (int16_t)8192);
+    refPel += rs;
+    dstPel += stride;
+  }
+  refPel = refBuf + (height - 2 - 2 + 1 - yOffset) * rs - xOffset;
+  dstPel = tmp + (height - 2) * stride + 1;
+  for (int w = 0; w < width - 2; w++) dstPel[w] = (int16_t)((int16_t)(refPel[w] << shift) - (int16_t)8192);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * RdCost SAD / HAD
  * ------------------------------------------------------------------------------------------- */

@@ -101,6 +101,9 @@ uint64_t orc_had(const int16_t* org, int org_stride, const int16_t* cur, int cur
 /* ME candidate evaluation = xMVReprojectionInterpolation + distFunc for n MVs of one block
  * (InterSearch.cpp:363-453, 6222-6249, 6263-6275).  mv_prec_shift: 4 = integer MVs, 3 = half,
  * 2 = quarter, 0 = internal (Mv::changePrecision to MV_PRECISION_INTERNAL). */
+/* xPredInterBlk with bioApplied (InterPrediction.cpp:1007-1015, 1054-1093): tmp = (w + 4) x (h + 4) BDOF work buffer */
+void orc_mc_bdof(const int16_t* ref, int rs, int pos_x, int pos_y, int size_w, int size_h, int mv_hor, int mv_ver, int bd, int lo,
+                 int hi, int16_t* tmp);
 void orc_me_block(OrcCtx* c, const int16_t* ref, int ref_stride, const int16_t* org, int org_stride, int pos_x,
                   int pos_y, int size_w, int size_h, int model, int n, const int32_t* mv_hor, const int32_t* mv_ver,
                   int mv_prec_shift, int dist_kind, int sub_shift, int had_mode, int clp_min, int clp_max,

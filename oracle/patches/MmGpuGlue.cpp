@@ -52,7 +52,7 @@ struct State
   std::vector<mmgpu_mv> mvScratch;
   std::vector<uint64_t> distScratch;
   // statistics
-  uint64_t nMcClassic = 0;
+  uint64_t nMcClassic = 0, nMvp = 0;
   uint64_t nMc = 0, nMeBatches = 0, nMeCands = 0, nMeHits = 0, nMeSingles = 0, nUploads = 0;
 };
 State g;
@@ -107,6 +107,11 @@ struct AtExit { ~AtExit() { if (g.ctx) { printStats(); mmgpu_destroy(g.ctx); g.c
 }  // namespace
 
 bool enabled() { return g_enabled; }
+bool mvpOnLibrary()
+{
+  static const bool on = !(getenv("MMGPU_MVP") && getenv("MMGPU_MVP")[0] == '0');
+  return on;
+}
 bool classicOnGpu()
 {
   static const bool on = !(getenv("MMGPU_CLASSIC") && getenv("MMGPU_CLASSIC")[0] == '0');
@@ -198,6 +203,30 @@ void predInterBlkClassic(ComponentID compID, ChromaFormat chFmt, const Position&
   const mmgpu_mv m = {mv.hor, mv.ver};
   chk(mmgpu_mc(g.ctx, slot, (int)compID, (int)chFmt, blockPos.x, blockPos.y, width, height, m, MMGPU_CLASSIC, 0, bi ? 1 : 0, clpRng.min,
                clpRng.max, MMGPU_OOB_PRED, dstBuf.buf, (int)dstBuf.stride), "mc (classic)");
+  g.nMcClassic++;
+}
+
+Mv mvpConvert(const Position& position, const Mv& mvOrig, MotionModelID modelOrig, MotionModelID modelDesired, int shiftHor, int shiftVer,
+              int curPOCOrig, int refPOCOrig, int curPOCDesired, int refPOCDesired, const Position& candPos, const Size& candSize,
+              const Position& curPos, const Size& curSize)
+{
+  const int ro = (modelOrig == GEODESIC_CAMPOSE) ? rotSlot(curPOCOrig, refPOCOrig) : 0;
+  const int rd = (modelDesired == GEODESIC_CAMPOSE) ? rotSlot(curPOCDesired, refPOCDesired) : 0;
+  const mmgpu_mv in = {mvOrig.hor, mvOrig.ver};
+  mmgpu_mv out = {0, 0};
+  chk(mmgpu_mvp_convert(g.ctx, position.x, position.y, in, (int)modelOrig, (int)modelDesired, shiftHor, shiftVer, ro, rd, candPos.x, candPos.y,
+                        (int)candSize.width, (int)candSize.height, curPos.x, curPos.y, (int)curSize.width, (int)curSize.height, &out),
+      "mvp_convert");
+  g.nMvp++;
+  return Mv(out.hor, out.ver);
+}
+
+void predInterBlkClassicBdof(const Position& blockPos, int width, int height, const Picture* refPic, bool wrapRef, const Mv& mv,
+                             const ClpRng& clpRng, Pel* bdofBuf)
+{
+  const int slot = ensureRef(refPic, wrapRef);
+  const mmgpu_mv m = {mv.hor, mv.ver};
+  chk(mmgpu_mc_bdof(g.ctx, slot, blockPos.x, blockPos.y, width, height, m, clpRng.min, clpRng.max, bdofBuf), "mc_bdof");
   g.nMcClassic++;
 }
 
@@ -418,7 +447,7 @@ void dumpMc(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, co
 
 void printStats()
 {
-  fprintf(stderr, "[mmgpu] classic MC calls %llu\n", (unsigned long long)g.nMcClassic);
+  fprintf(stderr, "[mmgpu] classic MC calls %llu | MM-MVP conversions %llu\n", (unsigned long long)g.nMcClassic, (unsigned long long)g.nMvp);
   fprintf(stderr, "[mmgpu] MC calls %llu | ME batches %llu, candidates %llu (%.1f per batch), look-ahead hits %llu, single evaluations %llu | "
                   "reference uploads %llu | kernels launched %llu\n",
           (unsigned long long)g.nMc, (unsigned long long)g.nMeBatches, (unsigned long long)g.nMeCands,

@@ -15,6 +15,7 @@
 namespace mmglue
 {
 bool enabled();
+bool mvpOnLibrary();    // MMGPU_MVP=0 keeps the MM-MVP conversion on the reference's code
 bool classicOnGpu();   // MMGPU_CLASSIC=0 keeps the classic translational MC on the reference's code
 
 // MVReprojection::init (MVReprojection.cpp:7-65): creates the device context (MPA caches, ERP tables on the device)
@@ -32,6 +33,15 @@ void predInterBlkMM(ComponentID compID, ChromaFormat chFmt, const Position& bloc
 // RPR / BDOF border / DMVR padding / IBC / alternative half-pel filter -- those stay on the reference's code)
 void predInterBlkClassic(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, int width, int height, const Picture* refPic,
                          bool wrapRef, const Mv& mv, bool bi, const ClpRng& clpRng, PelBuf& dstBuf);
+
+// MVReprojection::motionVectorInDesiredMotionModel (MVReprojection.cpp:168-217): MM-MVP candidate conversion
+Mv mvpConvert(const Position& position, const Mv& mvOrig, MotionModelID modelOrig, MotionModelID modelDesired, int shiftHor, int shiftVer,
+              int curPOCOrig, int refPOCOrig, int curPOCDesired, int refPOCDesired, const Position& candPos, const Size& candSize,
+              const Position& curPos, const Size& curSize);
+
+// xPredInterBlk with bioApplied, luma: prediction + ring of integer samples into the BDOF work buffer (stride width + 4)
+void predInterBlkClassicBdof(const Position& blockPos, int width, int height, const Picture* refPic, bool wrapRef, const Mv& mv,
+                             const ClpRng& clpRng, Pel* bdofBuf);
 
 // ---- motion estimation: xApplyMvVA / xMVReprojectionInterpolation + m_cDistParam.distFunc (InterSearch.cpp:363-453,
 //      5287-5322, 6168-6385).  The search control flow is untouched: candidate sets the reference is about to visit are

@@ -27,6 +27,15 @@ def edit_picture(t):
 def edit_mvreprojection(t):
     t = sub(t, '#include "MVReprojection.h"\n', '#include "MVReprojection.h"\n#include "MmGpuGlue.h"\n')
     t = sub(t, "  m_initialized = true;\n}\n", "  m_initialized = true;\n  mmglue::init( resolution, sps, epipoleList );\n}\n")
+    # MM-MVP candidate conversion through the library (host code of libmmgpu.so, 8f-1)
+    t = sub(t, """                                                    const Position &currentBlockPos, const Size &currentBlockSize) const {
+  if (motionVectorOrig.hor == 0 && motionVectorOrig.ver == 0) {""", """                                                    const Position &currentBlockPos, const Size &currentBlockSize) const {
+  if( mmglue::enabled() && mmglue::mvpOnLibrary() )
+  {
+    return mmglue::mvpConvert( position, motionVectorOrig, motionModelIDOrig, motionModelIDDesired, shiftHor, shiftVer, curPOCOrig, refPOCOrig,
+                               curPOCDesired, refPOCDesired, candidateBlockPos, candidateBlockSize, currentBlockPos, currentBlockSize );
+  }
+  if (motionVectorOrig.hor == 0 && motionVectorOrig.ver == 0) {""")
     return t
 
 
@@ -69,6 +78,15 @@ def edit_interprediction(t):
         && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
     {
       mmglue::predInterBlkClassic( compID, chFmt, pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, bi, clpRng, dstBuf );
+      return;
+    }
+    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && bioApplied && compID == COMPONENT_Y && bi && !bilinearMC && !dmvrWidth && !srcPadBuf
+        && !useAltHpelIf && width >= 8 && height >= 8 && ( width & ( width - 1 ) ) == 0 && ( height & ( height - 1 ) ) == 0
+        && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
+    {
+      // prediction + BDOF border fetch into the work buffer, as the code below does
+      mmglue::predInterBlkClassicBdof( pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, clpRng,
+                                       m_filteredBlockTmp[2 + m_iRefListIdx][compID] );
       return;
     }
 

@@ -50,6 +50,7 @@ def lib():
         L.orc_filter_ver.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 8
         L.orc_mc_block.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 14 + [C.c_void_p, C.c_int]
         L.orc_mc_block_classic.argtypes = [C.c_void_p] + [C.c_int] * 13 + [C.c_void_p, C.c_int]
+        L.orc_mc_bdof.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]
         L.orc_sad.restype = C.c_uint64
         L.orc_sad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_had.restype = C.c_uint64
@@ -145,6 +146,12 @@ class Oracle:
         self.L.orc_mc_block_classic(plane.origin, plane.stride, comp, chroma_fmt, pos[0], pos[1], size[0], size[1],
                                     mv[0], mv[1], int(bi), self.bit_depth, clp[0], clp[1], dst.ctypes.data, size[0])
         return dst
+
+    def mc_bdof(self, plane, pos, size, mv, clp=(0, 1023)):
+        tmp = np.zeros((size[1] + 4, size[0] + 4), dtype=np.int16)
+        self.L.orc_mc_bdof(plane.origin, plane.stride, pos[0], pos[1], size[0], size[1], mv[0], mv[1], self.bit_depth, clp[0], clp[1],
+                           tmp.ctypes.data)
+        return tmp
 
     def me_block(self, plane, org, org_stride_or_none, pos, size, model, mvs, mv_prec_shift=4, dist=DIST_SAD,
                  sub_shift=0, had_mode=HAD_SIMD, clp=(0, 1023)):

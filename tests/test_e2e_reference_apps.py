@@ -178,3 +178,37 @@ def test_encoder_app_with_gpu_me_bitstream_identical(tmp_path):
     assert r.returncode == 0, log[-2000:]
     assert "ME batches" in log, "GPU path not active"
     assert open(bit, "rb").read() == open(os.path.join(GOLD, "mm_ldp_q37.bin"), "rb").read(), log[-3000:]
+
+
+# ---- random access (BASELINE config 1 shape: encoder_randomaccess_vtm.cfg -- B slices, bi-prediction with 14-bit
+#      intermediates + addAvg, DMVR / BDOF / affine / AMVR on the classic side, MM-MVP) ---------------------------------
+RA_ARGS = [a if a != "3" else "5" for a in ENC_ARGS]     # -f 5
+
+
+@pytest.mark.gpu
+def test_decoder_app_random_access_stream(tmp_path):
+    dec, _, _ = _apps()
+    out = str(tmp_path / "dec.yuv")
+    r = subprocess.run([dec, "-b", os.path.join(GOLD, "mm_ra_q37.bin"), "-o", out], capture_output=True, text=True, timeout=900)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-2000:]
+    assert "[mmgpu] context" in log, "GPU path not active"
+    assert log.count("(OK)") == 5 and "***ERROR***" not in log, log[-2000:]
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == open(os.path.join(GOLD, "mm_ra_q37.md5")).read().strip()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("MMGPU_E2E_RA_ENCODE", "0") != "1",
+                    reason="several minutes of encoder time: MMGPU_E2E_RA_ENCODE=1 (run once per round, log under profiles/)")
+def test_encoder_app_random_access_bitstream_identical(tmp_path):
+    _, enc, _ = _apps()
+    cfg = os.path.join(E2E, "encoder_randomaccess_vtm.cfg")
+    yuv = os.path.join(str(tmp_path), "erp.yuv")
+    with lzma.open(os.path.join(GOLD, "erp_256x128_5f_seed2.yuv.xz")) as f, open(yuv, "wb") as g:
+        g.write(f.read())
+    bit = str(tmp_path / "enc.bin")
+    r = subprocess.run([enc, "-c", cfg, "-i", yuv, "-b", bit] + RA_ARGS, capture_output=True, text=True, timeout=3000)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-2000:]
+    print(log[-1500:])
+    assert open(bit, "rb").read() == open(os.path.join(GOLD, "mm_ra_q37.bin"), "rb").read(), log[-3000:]

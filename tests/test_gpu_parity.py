@@ -818,3 +818,18 @@ def test_mvp_convert_through_the_abi_equals_reference_source(env):
                 n += 1
     assert n == 11 * 11 * 12
     g.set_rotation(1, mm.rodrigues([0.1, 0.9, -0.2]))
+
+
+def test_classic_bi_mc_with_bdof_border_fetch(env):
+    """a8: xPredInterBlk with bioApplied -- the 14-bit prediction inside the BDOF work buffer plus the ring of
+    integer-position samples around it (InterPrediction.cpp:1007-1015, 1054-1093): mmgpu_mc_bdof == oracle, for fractions
+    below / at / above half a sample (the ring fetch moves by one sample), integer MVs and blocks at the picture border."""
+    o, g, planes, ref, cur = env
+    rng = np.random.default_rng(88)
+    for i, (w, h) in enumerate([(8, 8), (16, 8), (8, 16), (16, 16), (32, 32), (64, 16), (128, 128), (64, 64)] * 3):
+        x = [0, W - w, int(rng.integers(0, (W - w) // 4)) * 4][i % 3]
+        y = [int(rng.integers(0, (H - h) // 4)) * 4, 0, H - h][i % 3]
+        mv = [(0, 0), (7, 8), (8, 7), (-9, 23), (16, -32), (int(rng.integers(-900, 900)), int(rng.integers(-500, 500)))][i % 6]
+        exp = o.mc_bdof(planes[0], (x, y), (w, h), mv)
+        got = g.mc_bdof(0, (x, y), (w, h), mv)
+        assert np.array_equal(got[1:h + 3, 1:w + 3], exp[1:h + 3, 1:w + 3]), (x, y, w, h, mv)

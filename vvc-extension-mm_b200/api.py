@@ -21,7 +21,7 @@ EXPORTS = [
     "mmgpu_set_ref", "mmgpu_set_ref_device", "mmgpu_set_ref_unpadded", "mmgpu_rodrigues", "mmgpu_fixed_to_float",
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
-    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode", "mmgpu_mc_jobs_device", "mmgpu_set_refs_unpadded_device", "mmgpu_mvp_convert",
+    "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode", "mmgpu_mc_jobs_device", "mmgpu_set_refs_unpadded_device", "mmgpu_mvp_convert", "mmgpu_mc_bdof",
 ]
 
 
@@ -108,6 +108,7 @@ def load_library():
     L.mmgpu_plan_samples.argtypes = [vp]
     L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
     L.mmgpu_dmvr_costs.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.mmgpu_mc_bdof.argtypes = [vp, i32, i32, i32, i32, i32, Mv, i32, i32, vp]
     L.mmgpu_mc_jobs.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_mc_jobs_device.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_dmvr_decide.argtypes = [vp, i32, i32, vp, vp]
@@ -303,6 +304,13 @@ class MmGpu:
         dst = np.zeros((size[1], size[0]), dtype=np.int16)
         self._chk(self.L.mmgpu_mc(self.h, ref_slot, comp, chroma_fmt, pos[0], pos[1], size[0], size[1], Mv(mv[0], mv[1]),
                                   model, rot_slot, int(bi), clp[0], clp[1], oob, dst.ctypes.data, size[0]))
+        return dst
+
+    def mc_bdof(self, ref_slot, pos, size, mv, clp=(0, 1023)):
+        """Classic bi MC of a luma block into the BDOF work buffer: returns the (h + 4) x (w + 4) buffer (outer frame untouched = 0)."""
+        w, h = size
+        dst = np.zeros((h + 4, w + 4), dtype=np.int16)
+        self._chk(self.L.mmgpu_mc_bdof(self.h, ref_slot, pos[0], pos[1], w, h, Mv(mv[0], mv[1]), clp[0], clp[1], dst.ctypes.data))
         return dst
 
     def add_avg(self, src0, src1, clp=(0, 1023)):

@@ -211,7 +211,9 @@ void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, 
                  int shift, int offset, int lo, int hi);
 void mmk_mc_generic(cudaStream_t s, const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h,
                     mmgpu_mv mv, int model, int rotSlot, int bi, int16_t* dst, int dstStride);
-void mmk_mc_jobs(cudaStream_t s, const MmParams& P, int nJobs, const mmgpu_mc_job* jobs, int16_t* dstY, int16_t* dstCb,
+void mmk_bdof_ring(cudaStream_t s, const int16_t* ref, int stride, int x0, int y0, int xOff, int yOff, int w, int h, int shift, int16_t* tmp);
+#define MM_JOB_CHUNK 64   // sub-blocks per k_mc_jobs CTA
+void mmk_mc_jobs(cudaStream_t s, const MmParams& P, int nItems, const mmgpu_mc_job* jobs, const int2* items, int16_t* dstY, int16_t* dstCb,
                  int16_t* dstCr, int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset);
 void mmk_dmvr(cudaStream_t s, const MmParams& P, const mmgpu_dmvr_subpu* subpus, const MmDmvrItem* items, int nItems,
               int simdSad, unsigned long long* costs);

@@ -121,10 +121,15 @@ __device__ __forceinline__ void mm_mc_subblock(const MmParams& P, int refSlot, i
 // InterPrediction.cpp:455-681): one CTA per job (one component of one PU); uni-prediction writes the clipped
 // prediction, bi-prediction interpolates both lists at 14 bit and applies PelBuf::addAvg (Buffer.cpp:551-587) in
 // registers before the store.  dst planes are un-padded device pictures.
-__global__ void k_mc_jobs(MmParams P, const mmgpu_mc_job* __restrict__ jobs, int16_t* dstY, int16_t* dstCb, int16_t* dstCr,
-                          int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset)
+// items[i] = (job index, first sub-block): one CTA of MM_JOB_THREADS threads per chunk of MM_JOB_THREADS sub-blocks of a job, so
+// that a 128x128 PU is spread over 16 CTAs instead of being walked by one.
+#define MM_JOB_THREADS 64
+__global__ void __launch_bounds__(MM_JOB_THREADS) k_mc_jobs(MmParams P, const mmgpu_mc_job* __restrict__ jobs, const int2* __restrict__ items,
+                                                            int16_t* dstY, int16_t* dstCb, int16_t* dstCr, int strideY, int strideC, int csxC,
+                                                            int csyC, int avgShift, int avgOffset)
 {
-  const mmgpu_mc_job j = jobs[blockIdx.x];
+  const int2 it = items[blockIdx.x];
+  const mmgpu_mc_job j = jobs[it.x];
   const int csx = j.comp ? csxC : 0, csy = j.comp ? csyC : 0;
   const int sbw = 4 >> csx, sbh = 4 >> csy;
   const int rows = j.h / sbh, cols = j.w / sbw;
@@ -139,7 +144,8 @@ __global__ void k_mc_jobs(MmParams P, const mmgpu_mc_job* __restrict__ jobs, int
     mm_cand_setup(P.g, j.model, j.comp == 0, j.x, j.y, j.w, j.h, mv.hor, mv.ver, mm_rot_ptr(P.rot, j.model, l ? j.rot_slot1 : j.rot_slot0), &s_c[l]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+  const int i = it.y + threadIdx.x;
+  if (i < rows * cols)
   {
     const int col = i / rows, row = i - col * rows;
     int16_t a[16], b[16];
@@ -221,6 +227,28 @@ __global__ void __launch_bounds__(128) k_dmvr(const MmParams P, const mmgpu_dmvr
   if (valid && within == 0) costs[(long)it.subpu * 25 + off] = ((unsigned long long)sad << 1) >> 1;
 }
 
+// Ring of integer-position samples around a classic bi-predicted luma block (xPredInterBlk, InterPrediction.cpp:1054-1093).
+// tmp: (w + 4) x (h + 4) buffer; ring sample (i, j), i in [0, w+1], j in [0, h+1] on the border of the (w+2) x (h+2) box, is
+// stored at tmp[(j + 1) * (w + 4) + (i + 1)] and comes from reference sample (x0 + i - xOff, y0 + j - yOff).
+__global__ void k_bdof_ring(const int16_t* __restrict__ ref, int stride, int x0, int y0, int xOff, int yOff, int w, int h, int shift,
+                            int16_t* __restrict__ tmp)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 2 * (w + 2) + 2 * h;
+  if (t >= n) return;
+  int i, j;
+  if (t < w + 2) { i = t; j = 0; }
+  else if (t < 2 * (w + 2)) { i = t - (w + 2); j = h + 1; }
+  else { const int k = t - 2 * (w + 2); j = 1 + (k >> 1); i = (k & 1) ? (w + 1) : 0; }
+  const int v = ref[(long)(y0 + j - yOff) * stride + (x0 + i - xOff)];
+  tmp[(j + 1) * (w + 4) + (i + 1)] = (int16_t)((int16_t)(v << shift) - (int16_t)8192);
+}
+void mmk_bdof_ring(cudaStream_t s, const int16_t* ref, int stride, int x0, int y0, int xOff, int yOff, int w, int h, int shift, int16_t* tmp)
+{
+  const int n = 2 * (w + 2) + 2 * h;
+  k_bdof_ring<<<(n + 127) / 128, 128, 0, s>>>(ref, stride, x0, y0, xOff, yOff, w, h, shift, tmp);
+}
+
 // ---- launch wrappers -----------------------------------------------------------------------------
 void mmk_mc_generic(cudaStream_t s, const MmParams& P, int refSlot, int comp, int csx, int csy, int x, int y, int w, int h,
                     mmgpu_mv mv, int model, int rotSlot, int bi, int16_t* dst, int dstStride)
@@ -228,10 +256,10 @@ void mmk_mc_generic(cudaStream_t s, const MmParams& P, int refSlot, int comp, in
   const int n = (w / (4 >> csx)) * (h / (4 >> csy));
   k_mc_generic<<<(n + 63) / 64, 64, 0, s>>>(P, refSlot, comp, csx, csy, x, y, w, h, mv, model, rotSlot, bi, dst, dstStride);
 }
-void mmk_mc_jobs(cudaStream_t s, const MmParams& P, int nJobs, const mmgpu_mc_job* jobs, int16_t* dstY, int16_t* dstCb,
+void mmk_mc_jobs(cudaStream_t s, const MmParams& P, int nItems, const mmgpu_mc_job* jobs, const int2* items, int16_t* dstY, int16_t* dstCb,
                  int16_t* dstCr, int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset)
 {
-  k_mc_jobs<<<nJobs, 64, 0, s>>>(P, jobs, dstY, dstCb, dstCr, strideY, strideC, csxC, csyC, avgShift, avgOffset);
+  k_mc_jobs<<<nItems, MM_JOB_THREADS, 0, s>>>(P, jobs, items, dstY, dstCb, dstCr, strideY, strideC, csxC, csyC, avgShift, avgOffset);
 }
 void mmk_dmvr(cudaStream_t s, const MmParams& P, const mmgpu_dmvr_subpu* subpus, const MmDmvrItem* items, int nItems,
               int simdSad, unsigned long long* costs)

@@ -95,6 +95,8 @@ struct mmgpu_ctx
   size_t capSubpus;
   mmgpu_mc_job* dJobs;
   size_t capJobs;
+  int2* dJobItems;
+  size_t capJobItems;
   int16_t* dPic[3];   // reconstruction picture planes for mmgpu_mc_jobs
   size_t capPic[3];
   MmDmvrItem* dDmvrItems;
@@ -410,6 +412,7 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
   cudaFree(ctx->dJobs);
+  cudaFree(ctx->dJobItems);
   for (int c = 0; c < 3; ++c) cudaFree(ctx->dPic[c]);
   for (auto e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -824,6 +827,10 @@ extern "C" int mmgpu_mvp_convert(mmgpu_ctx* ctx, int pos_x, int pos_y, mmgpu_mv 
                                  int cand_w, int cand_h, int cur_x, int cur_y, int cur_w, int cur_h, mmgpu_mv* out)
 {
   if (!ctx || !out) return MMGPU_ERR_ARG;
+  // the reference's two early returns come first: callers pass INVALID (-1) / NUM_MODELS for unavailable candidates with a
+  // zero MV or equal models (MVReprojection.cpp:174-184)
+  if (mv_orig.hor == 0 && mv_orig.ver == 0) { out->hor = 0; out->ver = 0; return MMGPU_OK; }
+  if (model_desired == model_orig && (model_desired != MMGPU_GEODESIC_CAMPOSE || rot_slot_orig == rot_slot_desired)) { *out = mv_orig; return MMGPU_OK; }
   if (model_orig < MMGPU_CLASSIC || model_orig > MMGPU_GEODESIC_CAMPOSE || model_desired < MMGPU_CLASSIC || model_desired > MMGPU_GEODESIC_CAMPOSE)
     return fail(ctx, MMGPU_ERR_ARG, "bad model");
   if (shift_hor < 0 || shift_hor > 8 || shift_ver < 0 || shift_ver > 8) return fail(ctx, MMGPU_ERR_ARG, "bad shift");
@@ -865,6 +872,38 @@ extern "C" int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, 
   ctx->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpy2DAsync(dst, sizeof(int16_t) * dst_stride, ctx->dTmp, sizeof(int16_t) * w, sizeof(int16_t) * w, h,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_mc_bdof(mmgpu_ctx* ctx, int ref_slot, int x, int y, int w, int h, mmgpu_mv mv, int clp_min, int clp_max, int16_t* dst)
+{
+  if (!ctx || !dst) return MMGPU_ERR_ARG;
+  if (ref_slot < 0 || ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[ref_slot].plane00[0]) return fail(ctx, MMGPU_ERR_STATE, "reference slot not set");
+  int rc = checkBlockShape(ctx, 0, 0, x, y, w, h);
+  if (rc) return rc;
+  // the ring reads one sample beyond the block at integer MV offsets: same clipMv contract as xPredInterBlk
+  const int mg = ctx->cfg.margin - 16;
+  const int x0 = x + (mv.hor >> 4), y0 = y + (mv.ver >> 4);
+  if (x0 < -mg || y0 < -mg || x0 + w > ctx->cfg.pic_w + mg || y0 + h > ctx->cfg.pic_h + mg)
+    return fail(ctx, MMGPU_ERR_ARG, "mc_bdof: MV not clipped to the padded picture (clipMv)");
+  cudaSetDevice(ctx->cfg.device);
+  const int stride = w + 4, n = stride * (h + 4);
+  if ((rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)n + 64))) return rc;
+  MmParams P = baseParams(ctx);
+  P.clpMin = clp_min;
+  P.clpMax = clp_max;
+  P.oobMode = MMGPU_OOB_PRED;
+  CU(cudaMemsetAsync(ctx->dTmp, 0, sizeof(int16_t) * n, ctx->stream));
+  mmk_mc_generic(ctx->stream, P, ref_slot, 0, 0, 0, x, y, w, h, mv, MMGPU_CLASSIC, 0, 1, ctx->dTmp + 2 * stride + 2, stride);
+  const MmRef& r = ctx->hRefs[ref_slot];
+  mmk_bdof_ring(ctx->stream, r.plane00[0], r.stride[0], x0, y0, ((mv.hor & 15) < 8) ? 1 : 0, ((mv.ver & 15) < 8) ? 1 : 0, w, h, ctx->fir.cpShift,
+                ctx->dTmp);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  // only the ring box (rows 1 .. h+2, columns 1 .. w+2) is defined by the reference: copy exactly that
+  CU(cudaMemcpy2DAsync(dst + stride + 1, sizeof(int16_t) * stride, ctx->dTmp + stride + 1, sizeof(int16_t) * stride, sizeof(int16_t) * (w + 2), h + 2,
                        cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return MMGPU_OK;
@@ -1404,15 +1443,28 @@ static int checkJobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, bool 
 static int launchJobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max, int16_t* const d[3], const int pitch[3])
 {
   int rc;
+  // work list: chunks of MM_JOB_CHUNK sub-blocks
+  const int fmtc = ctx->cfg.chroma_fmt;
+  std::vector<int2> items;
+  items.reserve((size_t)n_jobs * 2);
+  for (int i = 0; i < n_jobs; ++i)
+  {
+    const int sbw = 4 >> scaleX(jobs[i].comp, fmtc), sbh = 4 >> scaleY(jobs[i].comp, fmtc);
+    const int n = (jobs[i].w / sbw) * (jobs[i].h / sbh);
+    for (int f = 0; f < n; f += MM_JOB_CHUNK) items.push_back(make_int2(i, f));
+  }
   if ((rc = ensureCap(ctx, &ctx->dJobs, &ctx->capJobs, (size_t)n_jobs))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dJobItems, &ctx->capJobItems, items.size()))) return rc;
   CU(cudaMemcpyAsync(ctx->dJobs, jobs, sizeof(mmgpu_mc_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->dJobItems, items.data(), sizeof(int2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
   MmParams P = baseParams(ctx);
   P.clpMin = clp_min;
   P.clpMax = clp_max;
   P.oobMode = MMGPU_OOB_PRED;
   const int fmt = ctx->cfg.chroma_fmt;
   const int shift = ctx->fir.cpShift + 1, offset = (1 << (shift - 1)) + 2 * 8192;
-  mmk_mc_jobs(ctx->stream, P, n_jobs, ctx->dJobs, d[0], d[1], d[2], pitch[0], pitch[1], scaleX(1, fmt), scaleY(1, fmt), shift, offset);
+  mmk_mc_jobs(ctx->stream, P, (int)items.size(), ctx->dJobs, ctx->dJobItems, d[0], d[1], d[2], pitch[0], pitch[1], scaleX(1, fmt), scaleY(1, fmt),
+              shift, offset);
   ctx->launches++;
   CU(cudaGetLastError());
   return MMGPU_OK;
