@@ -315,6 +315,23 @@ void meEval(const MeBlock& b, const DistParam& dp, const Mv& mv, MvPrecision pre
   g.pendingValid = true;
 }
 
+namespace
+{
+MeBlock g_cfBlk;
+Mv g_cfBase;
+bool g_cfActive = false;
+}
+void classicFracBegin(const MeBlock& b, const Mv& baseInt, bool usable)
+{
+  g_cfBlk = b;
+  g_cfBase = baseInt;
+  g_cfActive = usable;
+}
+bool classicFracActive() { return g_cfActive; }
+void classicFracEnd() { g_cfActive = false; }
+const MeBlock& classicFracBlock() { return g_cfBlk; }
+Mv classicFracMv(const Mv& relQuarter) { return Mv(g_cfBase.hor * 4 + relQuarter.hor, g_cfBase.ver * 4 + relQuarter.ver); }
+
 void beginCollect()
 {
   CHECK(g.collecting, "mmglue: nested dry run");

@@ -61,6 +61,14 @@ struct MeBlock
 void meSetup(DistParam& dp, bool useHadamard);
 // evaluate one candidate (look-ahead hit, or a one-candidate batch); its distortion is what dp.distFunc returns next
 void meEval(const MeBlock& b, const DistParam& dp, const Mv& mv, MvPrecision prec);
+// classic fractional refinement (xPatternSearchFracDIF -> xPatternRefinement, InterSearch.cpp:739-853, 6093-6159: the
+// reference up-samples the block once and compares 9 + 9 shifted views of it; the same predictions are the classic MC at the
+// half / quarter-pel MVs): the caller announces the block and the integer base MV, xPatternRefinement asks per candidate.
+void classicFracBegin(const MeBlock& b, const Mv& baseInt, bool usable);
+bool classicFracActive();
+void classicFracEnd();
+const MeBlock& classicFracBlock();
+Mv classicFracMv(const Mv& relQuarter);   // absolute quarter-pel MV of a candidate given relative to the integer base
 // look-ahead: the listed MVs will (probably) be visited next
 void mePrefetch(const MeBlock& b, const DistParam& dp, const Mv* mvs, int n, MvPrecision prec);
 // dry run of one of the reference's own enumerators: while collecting, xTZSearchHelp only records the point

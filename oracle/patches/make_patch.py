@@ -393,6 +393,67 @@ def edit_intersearch(t):
   }
 }
 """ % meblk("rcStruct"))
+    # --- classic fractional refinement: the 9 + 9 candidates of xPatternRefinement as classic MC + distortion on the device
+    t = sub(t, """  //  Half-pel refinement
+  m_pcRdCost->setCostScale(1);
+  xExtDIFUpSamplingH(&cPatternRoi, cStruct.useAltHpelIf);
+""", """  //  Half-pel refinement
+  m_pcRdCost->setCostScale(1);
+  xExtDIFUpSamplingH(&cPatternRoi, cStruct.useAltHpelIf);
+  if( ( mmglue::enabled() && mmglue::classicOnGpu() ) || mmglue::dumping() )
+  {
+    // the reference picture the search runs on: cStruct.pcRefBuf is the block-sized view for CLASSIC (:4993), its plane origin
+    // is blkPos samples before it
+    const Picture* refPicC = pu.cu->slice->getRefPic( m_currRefPicList, m_currRefPicIndex );
+    const bool wrapC = refPicC->isWrapAroundEnabled( pu.cs->pps );
+    const CPelBuf planeC = refPicC->getRecoBuf( COMPONENT_Y, wrapC );
+    if( mmglue::enabled() ) mmglue::ensureRef( refPicC, wrapC ); else mmglue::dumpRef( refPicC, wrapC );
+    mmglue::classicFracBegin( mmglue::MeBlock{ cStruct.blkPos, cStruct.blkSize, planeC.buf, CLASSIC, cStruct.curPOC, cStruct.refPOC, m_lumaClpRng },
+                              rcMvBaseI, !cStruct.useAltHpelIf );
+  }
+""")
+    t = sub(t, """    rcMvRefinedQ += cMvQter;
+  }
+}
+""", """    rcMvRefinedQ += cMvQter;
+  }
+  mmglue::classicFracEnd();
+}
+""")
+    t = sub(t, """  m_pcRdCost->setDistParam( m_cDistParam, *pcPatternKey, m_filteredBlock[0][0][0], iRefStride, m_lumaClpRng.bd, COMPONENT_Y, 0, 1, m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard );
+
+  const Mv* pcMvRefine = (iFrac == 2 ? s_acMvRefineH : s_acMvRefineQ);""", """  m_pcRdCost->setDistParam( m_cDistParam, *pcPatternKey, m_filteredBlock[0][0][0], iRefStride, m_lumaClpRng.bd, COMPONENT_Y, 0, 1, m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard );
+
+  const Mv* pcMvRefine = (iFrac == 2 ? s_acMvRefineH : s_acMvRefineQ);
+  const bool mmgpuFrac = mmglue::classicFracActive() && !m_skipFracME;
+  if( mmgpuFrac && mmglue::enabled() )
+  {
+    mmglue::meSetup( m_cDistParam, m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard );
+    Mv ahead[9];
+    for( uint32_t i = 0; i < 9; i++ )
+    {
+      const Mv rel = pcMvRefine[i] + baseRefMv;
+      ahead[i] = mmglue::classicFracMv( Mv( rel.hor * iFrac, rel.ver * iFrac ) );
+    }
+    mmglue::mePrefetch( mmglue::classicFracBlock(), m_cDistParam, ahead, 9, MV_PRECISION_QUARTER );
+  }
+  else if( mmgpuFrac && mmglue::dumping() )
+  {
+    mmglue::meDumpSetup( m_cDistParam, m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard );
+  }""")
+    t = sub(t, """    m_cDistParam.cur.buf   = piRefPos;
+    dist                   = m_cDistParam.distFunc(m_cDistParam);
+    dist += m_pcRdCost->getCostOfVectorWithPredictor(cMvTest.getHor(), cMvTest.getVer(), 0);
+""", """    m_cDistParam.cur.buf   = piRefPos;
+    if( mmgpuFrac )
+    {
+      const Mv absQ = mmglue::classicFracMv( Mv( horVal, verVal ) );
+      if( mmglue::enabled() ) mmglue::meEval( mmglue::classicFracBlock(), m_cDistParam, absQ, MV_PRECISION_QUARTER );
+      else mmglue::meDumpCandidate( mmglue::classicFracBlock(), absQ, MV_PRECISION_QUARTER );
+    }
+    dist                   = m_cDistParam.distFunc(m_cDistParam);
+    dist += m_pcRdCost->getCostOfVectorWithPredictor(cMvTest.getHor(), cMvTest.getVer(), 0);
+""")
     t = sub(t, """  Mv mv(_mv);
   // Luma interpolation filter with quarter pixel precision and MVReprojection requires MV_PRECISION_INTERNAL
   // for COMPONENT_Y.

@@ -5,7 +5,7 @@ the apps built by `make -C oracle -f vtm.mk stock gpu` exist; the GPU box only r
   mm_ldp_q37.bin            bitstream of the STOCK reference EncoderApp (CPU), low-delay P, all five motion-model families
   mm_ldp_q37.md5            MD5 of the stock encoder's reconstruction (= what DecoderApp must output)
   trace_ldp_q37.npz         what the reference's CPU path computed during that encode: every 8th xPredInterBlkMM call
-                            (parameters + CRC32 of the predicted block) and every 63rd motion search (original block,
+                            (parameters + CRC32 of the predicted block) and every 65th motion search (MM integer / half / quarter-pel searches and the classic fractional refinement) (original block,
                             every candidate MV with the distortion m_cDistParam.distFunc returned), plus the two
                             reference pictures -- written by the MMGPU_DUMP mode of the patched app running its CPU path.
 
@@ -46,7 +46,7 @@ def main():
     with open(os.path.join(OUT, "mm_ldp_q37.md5"), "w") as f:
         f.write(hashlib.md5(open(rec, "rb").read()).hexdigest() + "\n")
     trace = os.path.join(tmp, "trace.bin")
-    env = dict(os.environ, MMGPU="0", MMGPU_DUMP=trace, MMGPU_DUMP_ME="7")
+    env = dict(os.environ, MMGPU="0", MMGPU_DUMP=trace, MMGPU_DUMP_ME="5")
     bit2 = os.path.join(tmp, "dump.bin")
     subprocess.check_call([os.path.join(VTM, "EncoderApp_gpu"), "-c", CFG, "-i", yuv, "-b", bit2] + ENC_ARGS, env=env,
                           stdout=open(os.path.join(tmp, "dump.log"), "w"))
@@ -54,7 +54,7 @@ def main():
     compact(trace, os.path.join(OUT, "trace_ldp_q37.npz"))
 
 
-def compact(trace, out, mc_every=8, me_every=9):
+def compact(trace, out, mc_every=8, me_every=13):
     refs = {}
     mc = []
     i = 0

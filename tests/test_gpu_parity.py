@@ -833,3 +833,21 @@ def test_classic_bi_mc_with_bdof_border_fetch(env):
         exp = o.mc_bdof(planes[0], (x, y), (w, h), mv)
         got = g.mc_bdof(0, (x, y), (w, h), mv)
         assert np.array_equal(got[1:h + 3, 1:w + 3], exp[1:h + 3, 1:w + 3]), (x, y, w, h, mv)
+
+
+def test_mc_non_power_of_two_blocks(env):
+    """The encoder's RD search also predicts 12 / 24 / 48-wide blocks (found by the random-access end-to-end run: a 48x8
+    xPredInterBlkMM call): mmgpu_mc takes every size that is a multiple of the sub-block."""
+    o, g, planes, ref, cur = env
+    rng = np.random.default_rng(48)
+    for (w, h) in [(48, 8), (24, 16), (12, 8), (8, 12), (96, 32), (48, 48)]:
+        for model in (0, 1, 4, 5, 6, 10):
+            x, y = int(rng.integers(0, (W - w) // 4)) * 4, int(rng.integers(0, (H - h) // 4)) * 4
+            mv = (int(rng.integers(-300, 300)), int(rng.integers(-200, 200)))
+            for comp in (0, 1):
+                cx, cy, cw, ch = (x, y, w, h) if comp == 0 else (x // 2, y // 2, w // 2, h // 2)
+                for bi in (False, True):
+                    exp = (o.mc_block_classic(planes[comp], comp, 1, (cx, cy), (cw, ch), mv, bi) if model == 0 else
+                           o.mc_block(planes[comp], comp, 1, (cx, cy), (cw, ch), mv, model, bi))
+                    got = g.mc(0, comp, 1, (cx, cy), (cw, ch), mv, model, bi=bi)
+                    assert np.array_equal(exp, got), (w, h, model, comp, bi)

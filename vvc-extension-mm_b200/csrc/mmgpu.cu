@@ -768,14 +768,19 @@ static int ensureCap(mmgpu_ctx* ctx, T** p, size_t* cap, size_t need)
   return MMGPU_OK;
 }
 
-static int checkBlockShape(mmgpu_ctx* ctx, int comp, int fmt, int x, int y, int w, int h)
+// anyMultiple: MC entry points take every size that is a multiple of the sub-block (the encoder's RD search also predicts
+// 12/24/48-wide blocks); the batch / Hadamard work lists index with power-of-two arithmetic
+static int checkBlockShape(mmgpu_ctx* ctx, int comp, int fmt, int x, int y, int w, int h, bool anyMultiple = false)
 {
   const int sx = scaleX(comp, fmt), sy = scaleY(comp, fmt);
   const int sbw = 4 >> sx, sbh = 4 >> sy;
+  char dims[96];
+  snprintf(dims, sizeof(dims), " (comp %d fmt %d: %dx%d at %d,%d)", comp, fmt, w, h, x, y);
   if (w < sbw || h < sbh || (w % sbw) || (h % sbh) || (x % sbw) || (y % sbh) || x < 0 || y < 0)
-    return fail(ctx, MMGPU_ERR_ARG, "block must be aligned to the sub-block grid");
-  if (!pow2(w) || !pow2(h) || (w << sx) > 128 || (h << sy) > 128) return fail(ctx, MMGPU_ERR_ARG, "block size must be a power of two <= 128");
-  if (((x + w) << sx) > ctx->cfg.pic_w || ((y + h) << sy) > ctx->cfg.pic_h) return fail(ctx, MMGPU_ERR_ARG, "block outside the picture");
+    return fail(ctx, MMGPU_ERR_ARG, std::string("block must be aligned to the sub-block grid") + dims);
+  if ((!anyMultiple && (!pow2(w) || !pow2(h))) || (w << sx) > 128 || (h << sy) > 128)
+    return fail(ctx, MMGPU_ERR_ARG, std::string("block size must be a power of two <= 128") + dims);
+  if (((x + w) << sx) > ctx->cfg.pic_w || ((y + h) << sy) > ctx->cfg.pic_h) return fail(ctx, MMGPU_ERR_ARG, std::string("block outside the picture") + dims);
   return MMGPU_OK;
 }
 
@@ -858,7 +863,7 @@ extern "C" int mmgpu_mc(mmgpu_ctx* ctx, int ref_slot, int comp, int chroma_fmt, 
   if (comp != 0 && chroma_fmt != ctx->cfg.chroma_fmt) return fail(ctx, MMGPU_ERR_ARG, "chroma_fmt differs from the context's");
   if (ref_slot < 0 || ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[ref_slot].plane00[comp])
     return fail(ctx, MMGPU_ERR_STATE, "reference slot not set");
-  int rc = checkBlockShape(ctx, comp, chroma_fmt, x, y, w, h);
+  int rc = checkBlockShape(ctx, comp, chroma_fmt, x, y, w, h, true);
   if (rc) return rc;
   cudaSetDevice(ctx->cfg.device);
   const int csx = scaleX(comp, chroma_fmt), csy = scaleY(comp, chroma_fmt);
@@ -1424,7 +1429,7 @@ static int checkJobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, bool 
   {
     const mmgpu_mc_job& j = jobs[i];
     if (j.comp < 0 || j.comp >= numComps(ctx)) return fail(ctx, MMGPU_ERR_ARG, "bad component in job");
-    int rc = checkBlockShape(ctx, j.comp, fmt, j.x, j.y, j.w, j.h);
+    int rc = checkBlockShape(ctx, j.comp, fmt, j.x, j.y, j.w, j.h, true);
     if (rc) return rc;
     if (j.model < MMGPU_CLASSIC || j.model > MMGPU_GEODESIC_CAMPOSE) return fail(ctx, MMGPU_ERR_ARG, "bad model in job");
     const int nl = j.bi ? 2 : 1;
