@@ -1,6 +1,8 @@
 """Parity tests proper: the sm_100a path, called through the C ABI (ctypes), against the CPU oracle on
 the same seeded inputs.  Bit-exact everywhere (integer positions, samples, distortions).
 Reference lines each case follows are quoted in oracle/mm_oracle.c next to the restated function."""
+import os
+
 import numpy as np
 import pytest
 
@@ -851,3 +853,87 @@ def test_mc_non_power_of_two_blocks(env):
                            o.mc_block(planes[comp], comp, 1, (cx, cy), (cw, ch), mv, model, bi))
                     got = g.mc(0, comp, 1, (cx, cy), (cw, ch), mv, model, bi=bi)
                     assert np.array_equal(exp, got), (w, h, model, comp, bi)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("8bit", dict(bit_depth=8)), ("9bit", dict(bit_depth=9)), ("400", dict(chroma_fmt=0)), ("422", dict(chroma_fmt=2)),
+    ("444", dict(chroma_fmt=3)), ("ged_original", dict(ged_flavor=0)), ("offset1.5", dict(offset4x4=1.5)),
+    ("maxcu64", dict(max_cu=64, margin=160)),
+])
+def test_other_configurations_accepted_by_create(name, kw):
+    """Everything mmgpu_create accepts is checked against the oracle, not only 10-bit 4:2:0 modulated-GED offset 1.0: other
+    bit depths (FIR shifts / offsets, clip range, the int16 intermediates), chroma formats (sub-block sizes, position scaling,
+    classic chroma phase), the original GED flavor, MMOffset4x4 = 4 (1.5), a smaller CTU; luma 4x4 blocks included."""
+    w, h = 512, 256
+    bd = kw.get("bit_depth", 10)
+    fmt = kw.get("chroma_fmt", 1)
+    o = ol.Oracle(w, h, chroma_fmt=fmt, max_cu=kw.get("max_cu", 128), offset4x4=kw.get("offset4x4", 1.0), ged_flavor=kw.get("ged_flavor", 1),
+                  bit_depth=bd)
+    g = mm.MmGpu(w, h, max_refs=1, **kw)
+    try:
+        R = ol.Oracle.rodrigues(EPIPOLE)
+        o.set_rotation(ol.GED_CAMPOSE, R)
+        g.set_rotation(0, mm.rodrigues(EPIPOLE))
+        margin = kw.get("margin", 288)
+        planes = wl.synth_frame(w, h, seed=5, chroma_fmt=fmt, bit_depth=bd)
+        ref = wl.pad_frame(planes, margin, fmt)
+        g.set_ref(0, 0, [p.origin for p in ref], [p.stride for p in ref])
+        cur = wl.synth_frame(w, h, seed=6, chroma_fmt=fmt, bit_depth=bd, shift=(1.5, 0.5))
+        hi = (1 << bd) - 1
+        rng = np.random.default_rng(len(name))
+        csx = 1 if fmt in (1, 2) else 0
+        csy = 1 if fmt == 1 else 0
+        for i, (bw, bh) in enumerate([(4, 4), (8, 4), (16, 16), (32, 8), (64, 64), (4, 16)] * 3):
+            x, y = int(rng.integers(0, (w - bw) // 8)) * 8, int(rng.integers(0, (h - bh) // 8)) * 8
+            mv = (int(rng.integers(-200, 200)), int(rng.integers(-120, 120)))
+            for model in (0, 1, 3, 4, 5, 6, 7, 10):
+                ncomp = 1 if fmt == 0 else 3
+                for comp in range(ncomp):
+                    cx, cy, cw, ch = (x, y, bw, bh) if comp == 0 else (x >> csx, y >> csy, bw >> csx, bh >> csy)
+                    if cw < (4 >> (csx if comp else 0)) or ch < (4 >> (csy if comp else 0)):
+                        continue
+                    for bi in (False, True):
+                        exp = (o.mc_block_classic(ref[comp], comp, fmt, (cx, cy), (cw, ch), mv, bi, clp=(0, hi)) if model == 0 else
+                               o.mc_block(ref[comp], comp, fmt, (cx, cy), (cw, ch), mv, model, bi, clp=(0, hi)))
+                        got = g.mc(0, comp, fmt, (cx, cy), (cw, ch), mv, model, bi=bi, clp=(0, hi))
+                        assert np.array_equal(exp, got), (name, bw, bh, model, comp, bi)
+        # motion search batches (luma): SAD and Hadamard, 4x4 blocks included
+        g.set_org(cur[0])
+        blocks, mvs, prec = wl.frame_batch(w, h, seed=3, cands_per_block=3, mv_range=24, models=(1, 2, 3, 4, 5, 6, 10, 7), frac=True)
+        extra = np.zeros(8, dtype=mm.api.BLOCK_DTYPE)
+        emv = np.zeros(8 * 3, dtype=mm.api.MV_DTYPE)
+        for i in range(8):
+            extra[i] = (8 * i + 64, 32, 4, 4, [1, 4, 5, 6, 10, 2, 3, 7][i], 0, 0, len(mvs) + 3 * i, 3, 8 * i + 64, 32, 0)
+            emv["hor"][3 * i:3 * i + 3] = rng.integers(-60, 60, 3)
+            emv["ver"][3 * i:3 * i + 3] = rng.integers(-60, 60, 3)
+        blocks = np.concatenate([blocks, extra])
+        mvs = np.concatenate([mvs, emv])
+        for dist in (mm.DIST_SAD, mm.DIST_HAD):
+            got = g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=dist, clp=(0, hi))
+            for b in blocks[::5].tolist() + extra.tolist():
+                b = dict(zip(mm.api.BLOCK_DTYPE.names, b))
+                sl = slice(b["cand_first"], b["cand_first"] + b["cand_count"])
+                org = cur[0][b["y"]:b["y"] + b["h"], b["x"]:b["x"] + b["w"]]
+                m = np.stack([mvs["hor"][sl], mvs["ver"][sl]], axis=1)
+                exp = o.me_block(ref[0], org, None, (b["x"], b["y"]), (b["w"], b["h"]), b["model"], m, mv_prec_shift=prec, dist=dist,
+                                 had_mode=ol.HAD_SIMD, clp=(0, hi))
+                assert np.array_equal(exp, got[sl]), (name, dist, b)
+    finally:
+        g.close()
+        o.close()
+
+
+def test_bench_batch_equals_oracle(env):
+    """The exact batch bench.py times (2048x1024, 1978 blocks x 16 candidates, MPA_FB/LR/TB + GED_CAMPOSE(1,0,0) + ROT, Hadamard)
+    against the oracle: all 31 648 distortions."""
+    import bench
+    o, g, planes, ref, cur = env
+    g.set_rotation(0, mm.rodrigues(bench.EPIPOLE))
+    try:
+        blocks, mvs, prec = wl.frame_batch(W, H, seed=1, cands_per_block=bench.CANDS, mv_range=bench.MV_RANGE, models=bench.models())
+        g.set_org(cur[0])
+        got = g.me_batch(blocks, mvs, mv_prec_shift=prec, dist=mm.DIST_HAD)
+        exp = bench.oracle_distortions(ref[0], cur[0], blocks, mvs, prec, os.cpu_count() or 4)
+        assert len(got) == 31648 and np.array_equal(got, exp)
+    finally:
+        g.set_rotation(0, mm.rodrigues(EPIPOLE))
