@@ -54,7 +54,8 @@ class ClockSampler:
 
     def __init__(self, index):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu,pcie.link.gen.current," \
+            "pcie.link.width.current"
         self.cmd = ["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"]
         self.proc = None
 
@@ -81,8 +82,9 @@ class ClockSampler:
         mx = [int(r[1]) for r in rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower().startswith("active")})
+        pcie = sorted({"gen%s x%s" % (r[7], r[8]) for r in busy if len(r) >= 9})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(rows), "samples_under_load": len(busy)}
+                "samples": len(rows), "samples_under_load": len(busy), "pcie_link_under_load": pcie}
 
 
 def cpu_workload(seed=1):
@@ -529,6 +531,18 @@ def main():
         sus_steps = int(n_sus.item())
     sus_ms, _ = timed(device_step, sus_steps, lambda s: None)
     clocks = sampler.stop()
+    # what the box's PCIe path gives a plain pinned host->device copy (e2e moves h2d bytes per step over it)
+    probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    h2d_probe = 0.0
+    for _ in range(4):
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        probe_d.copy_(probe_h, non_blocking=True)
+        pe1.record()
+        torch.cuda.synchronize()
+        h2d_probe = max(h2d_probe, (64 << 20) / 1e9 / (pe0.elapsed_time(pe1) / 1000.0))
+    del probe_h, probe_d
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)   # host work (plan building, copies) is part of the call: use the larger clock
 
     t = torch.tensor([dev_ms, e2e_ms, float(samples_rank), float(alg_bytes_rank), k_ms, kmap_ms, sus_ms], dtype=torch.float64, device=dev)
@@ -588,7 +602,9 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "luma sample-candidates/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": int(h_dist.numel() * 8), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(h_dist.numel() * 8), "ms_per_step": e2e_ms / args.steps,
+                    "rank0_device_ms_per_step": e2e_dev_ms / args.steps, "rank0_host_ms_per_step": e2e_wall_ms / args.steps,
+                    "h2d_probe_gbs": h2d_probe},
             "gpu_launches": int(launches),
             "parity": parity,
             "sustained": {"seconds": sus_ms / 1000.0, "steps": sus_steps, "ms_per_step": sus_ms / sus_steps,

@@ -185,6 +185,38 @@ int mmgpu_dmvr_costs(mmgpu_ctx* ctx, int n_subpus, const mmgpu_dmvr_subpu* subpu
  * 2502-2583): 25 costs -> pu.mvdL0SubPu (1/16 pel) and minCost; returns notZeroCost (0/1). */
 int mmgpu_dmvr_decide(const uint64_t costs25[25], int w, int h, int32_t delta_mv[2], uint64_t* min_cost);
 
+/* ---- f4 (second half): classic DMVR, InterPrediction::xProcessDMVR (InterPrediction.cpp:2239-2439) ------------------ */
+/* One sub-PU (min(16,w) x min(16,h) luma) of the integer search.  The reference prefetches a (w + 7) x (h + 7) window per
+ * list (xPrefetch :1891-1936) and filters bilinear predictions from it (xinitMC :2177-2223, FILTER_DMVR): org = position of
+ * the first prefetched luma sample = pu.lumaPos() + (clipMv(mergeMv - (3 << 4)) >> 4), frac = clipMv(mergeMv) & 15. */
+typedef struct {
+  int32_t w, h;                              /* 8 or 16 each */
+  int32_t ref_slot0, ref_slot1;
+  int32_t org_x0, org_y0, org_x1, org_y1;    /* luma samples, picture coordinates (may lie in the margin) */
+  int32_t frac_x0, frac_y0, frac_x1, frac_y1;
+} mmgpu_dmvr_classic_subpu;
+/* costs[i*25 + k] = xDMVRCost (:2147-2155) of the bilinear predictions, L0 moved by +o_k and L1 by -o_k, o_k = m_pSearchOffset[k]
+ * (index 12 = centre, raw: the caller's mmgpu_dmvr_decide applies minCost -= minCost >> 2 and the rest of :2364-2395). */
+int mmgpu_dmvr_classic_costs(mmgpu_ctx* ctx, int n_subpus, const mmgpu_dmvr_classic_subpu* subpus, uint64_t* costs);
+/* One component of one list of xFinalPaddedMCForDMVR (:2075-2145): xPredInterBlk(bi = true) reading from the prefetched
+ * window padded by replication (xPad :1938-1956) instead of the picture. */
+typedef struct {
+  int32_t comp, ref_slot;
+  int32_t org_x, org_y;        /* first prefetched sample of the component (xPrefetch's Rec_offset) */
+  int32_t w, h;                /* component block (<= 16 x 16) */
+  int32_t pad;                 /* xPad's padsize: 2 >> scaleY (0: the window is not padded, e.g. a sub-PU that did not move) */
+  int32_t dint_x, dint_y;      /* deltaIntMv (:2126-2127), |d| <= pad */
+  int32_t frac_x, frac_y;      /* of cMvClipped: luma & 15, chroma phase of 32 (:965-971) */
+  int32_t alt_hpel;            /* pu.cu->imv == IMV_HPEL (:948) */
+  int32_t bio;                 /* luma with bioApplied: (w + 4) x (h + 4) BDOF buffer, prediction at (2,2), ring of integer samples */
+  int32_t dst_offset, dst_stride; /* where the job's output starts in dst (samples) and its stride (bio: stride is w + 4) */
+} mmgpu_dmvr_mc_job;
+/* dst: HOST buffer of dst_samples int16 (14-bit intermediates as xPredInterBlk with bi = true writes them). */
+int mmgpu_dmvr_final_mc(mmgpu_ctx* ctx, int n_jobs, const mmgpu_dmvr_mc_job* jobs, int16_t* dst, int dst_samples);
+/* xPredInterBlk (:928-1096) of a classic luma block with the alternative half-pel filter (pu.cu->imv == IMV_HPEL). */
+int mmgpu_mc_alt_hpel(mmgpu_ctx* ctx, int ref_slot, int x, int y, int w, int h, mmgpu_mv mv, int bi, int clp_min, int clp_max,
+                      int16_t* dst, int dst_stride);
+
 /* ---- a9-a11 + a6: candidate evaluation, xTZSearchHelp/xPatternRefinementProjected's
  *      xMVReprojectionInterpolation + m_cDistParam.distFunc pair (InterSearch.cpp:363-453, 6222-6249) --- */
 /* original samples (pcPatternKey or the whole current picture), HOST memory */

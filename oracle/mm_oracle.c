@@ -884,6 +884,163 @@ void orc_dmvr_costs(OrcCtx* c, const int16_t* ref0, int rs0, const int16_t* ref1
   }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * DMVR (classic): InterPrediction::xProcessDMVR (InterPrediction.cpp:2239-2439) -- literal: a prefetched window in a
+ * small buffer (xPrefetch :1891-1936), padded by replication (xPad :1938-1956), bilinear search predictions from it
+ * (xinitMC :2177-2223, FILTER_DMVR = m_bilinearFilterPrec4, 10-bit output), 8-tap final MC from it
+ * (xFinalPaddedMCForDMVR :2075-2145).
+ * ------------------------------------------------------------------------------------------- */
+static const int16_t kLumaAltHpel[8] = {0, 3, 9, 20, 20, 9, 3, 0};  /* InterpolationFilter.cpp:186 */
+
+/* filterCopy<true,false> / filter<2,*,isFirst,false> with biMCForDMVR (InterpolationFilter.cpp:416-447, 588-600) */
+static void filter_bilinear(int vertical, int is_first, const int16_t* src, int ss, int16_t* dst, int ds, int w, int h, int frac, int bd)
+{
+  if (frac == 0)  /* only reached as filterHor's copy: isFirst = true */
+  {
+    for (int r = 0; r < h; ++r, src += ss, dst += ds)
+      for (int x = 0; x < w; ++x)
+      {
+        if (bd - 10 > 0) dst[x] = (int16_t)((src[x] + (1 << (bd - 10 - 1))) >> (bd - 10));
+        else dst[x] = (int16_t)(src[x] << (10 - bd));
+      }
+    return;
+  }
+  const int cs = vertical ? ss : 1;
+  const int c0 = 16 - frac, c1 = frac;                       /* m_bilinearFilterPrec4[frac] (:297-315) */
+  const int shift = is_first ? 4 - (10 - bd) : 4, offset = 1 << (shift - 1);
+  for (int r = 0; r < h; ++r, src += ss, dst += ds)
+    for (int x = 0; x < w; ++x) dst[x] = (int16_t)((src[x] * c0 + src[x + cs] * c1 + offset) >> shift);
+}
+
+/* window of the reference plane -> pad buffer at (2,2) (xPrefetch: copyBuffer of (w + taps-1) x (h + taps-1)) */
+static void dmvr_prefetch(const int16_t* ref, int rs, int ox, int oy, int ww, int wh, int16_t* pad, int S)
+{
+  for (int y = 0; y < wh; ++y)
+    for (int x = 0; x < ww; ++x) pad[(2 + y) * S + 2 + x] = ref[(long)(oy + y) * rs + ox + x];
+}
+/* g_pelBufOP.padding (Buffer.cpp paddingCore): left/right columns, then whole rows up and down */
+static void dmvr_pad(int16_t* pad, int S, int ww, int wh, int padsize)
+{
+  int16_t* p = pad + 2 * S + 2;
+  for (int y = 0; y < wh; ++y)
+    for (int k = 1; k <= padsize; ++k) { p[y * S - k] = p[y * S]; p[y * S + ww - 1 + k] = p[y * S + ww - 1]; }
+  for (int k = 1; k <= padsize; ++k)
+    for (int x = -padsize; x < ww + padsize; ++x) { p[-k * S + x] = p[x]; p[(wh - 1 + k) * S + x] = p[(wh - 1) * S + x]; }
+}
+
+void orc_dmvr_classic_costs(const int16_t* ref0, int rs0, const int16_t* ref1, int rs1, int ox0, int oy0, int fx0, int fy0,
+                            int ox1, int oy1, int fx1, int fy1, int dx, int dy, int bd, uint64_t costs25[25])
+{
+  /* (ox, oy): xPrefetch's Rec_offset of the list -- luma position of the first prefetched sample, i.e.
+   * pu.lumaPos() + (clipMv(mergeMv - (3 << 4)) >> 4); (fx, fy) = clipMv(mergeMv) & 15 (xinitMC, xPredInterBlk :965-966). */
+  const int S = dx + 4 + 8, PS = dx + 4;   /* pcPad stride (:1907), m_biLinearBufStride (:2307) */
+  int16_t pad[2][(16 + 12) * (16 + 12)], pred[2][20 * 20], tmp[20 * 21];
+  const int16_t* ref[2] = {ref0, ref1};
+  const int rs[2] = {rs0, rs1}, ox[2] = {ox0, ox1}, oy[2] = {oy0, oy1}, fx[2] = {fx0, fx1}, fy[2] = {fy0, fy1};
+  for (int l = 0; l < 2; ++l)
+  {
+    memset(pad[l], 0, sizeof(pad[l]));
+    dmvr_prefetch(ref[l], rs[l], ox[l], oy[l], dx + 7, dy + 7, pad[l], S);
+    /* xinitMC: offset = (2 + 3) * (S + 1) - 2 * S - 2; xPredInterBlk(bi = true, dmvrWidth = dx + 4, bilinearMC) (:1019-1049) */
+    const int16_t* src = pad[l] + 3 * (S + 1);
+    const int w = dx + 4, h = dy + 4;
+    if (fy[l] == 0) filter_bilinear(0, 1, src, S, pred[l], PS, w, h, fx[l], bd);
+    else if (fx[l] == 0) filter_bilinear(1, 1, src, S, pred[l], PS, w, h, fy[l], bd);
+    else
+    {
+      filter_bilinear(0, 1, src, S, tmp, w, w, h + 1, fx[l], bd);   /* tmpBuf = PelBuf(.., Size(dmvrWidth, dmvrHeight)): stride w */
+      filter_bilinear(1, 0, tmp, w, pred[l], PS, w, h, fy[l], bd);
+    }
+  }
+  for (int k = 0; k < 25; ++k)
+  {
+    const int oh = kSearchOffset[k][0], ov = kSearchOffset[k][1];  /* xBIPMVRefine (:2050-2073): L0 + offset, L1 - offset */
+    costs25[k] = dmvr_cost(pred[0] + (2 + ov) * PS + 2 + oh, PS, pred[1] + (2 - ov) * PS + 2 - oh, PS, dx, dy, 0);
+  }
+}
+
+/* the 14-bit prediction + integer-sample ring of xPredInterBlk with bioApplied (:1007-1015, 1054-1093) from any source pointer */
+static void bdof_ring(const int16_t* refBuf, int rs, int size_w, int size_h, int xFrac, int yFrac, int bd, int16_t* tmp)
+{
+  const int stride = size_w + 4, width = size_w + 4, height = size_h + 4;
+  const int shift = 14 - bd < 2 ? 2 : 14 - bd;
+  const int xOffset = (xFrac < 8) ? 1 : 0, yOffset = (yFrac < 8) ? 1 : 0;
+  const int16_t* refPel = refBuf - yOffset * rs - xOffset;
+  int16_t* dstPel = tmp + stride + 1;
+  for (int w = 0; w < width - 2; w++) dstPel[w] = (int16_t)((int16_t)(refPel[w] << shift) - (int16_t)8192);
+  refPel = refBuf + (1 - yOffset) * rs - xOffset;
+  dstPel = tmp + 2 * stride + 1;
+  for (int h = 0; h < height - 2 - 2; h++)
+  {
+    dstPel[0] = (int16_t)((int16_t)(refPel[0] << shift) - (int16_t)8192);
+    dstPel[width - 3] = (int16_t)((int16_t)(refPel[width - 3] << shift) - (int16_t)8192);
+    refPel += rs;
+    dstPel += stride;
+  }
+  refPel = refBuf + (height - 2 - 2 + 1 - yOffset) * rs - xOffset;
+  dstPel = tmp + (height - 2) * stride + 1;
+  for (int w = 0; w < width - 2; w++) dstPel[w] = (int16_t)((int16_t)(refPel[w] << shift) - (int16_t)8192);
+}
+
+/* xPredInterBlk's filter cascade (:1019-1049) from any source pointer, default filters, optional alternative half-pel filter */
+static void mc_from_ptr(const int16_t* p, int rs, int is_luma, int xF, int yF, int w, int h, int rnd, int alt, int bd, int lo, int hi,
+                        int16_t* dst, int ds)
+{
+  const int taps = is_luma ? 8 : 4;
+  const int altx = alt && is_luma && xF == 8, alty = alt && is_luma && yF == 8;   /* InterpolationFilter.cpp:713-716, 781-784 */
+  if (yF == 0)
+  {
+    if (altx) filter_n(8, 0, 1, rnd, p, rs, dst, ds, w, h, kLumaAltHpel, bd, lo, hi);
+    else orc_filter_hor(is_luma, p, rs, dst, ds, w, h, xF, rnd, bd, lo, hi);
+  }
+  else if (xF == 0)
+  {
+    if (alty) filter_n(8, 1, 1, rnd, p, rs, dst, ds, w, h, kLumaAltHpel, bd, lo, hi);
+    else orc_filter_ver(is_luma, p, rs, dst, ds, w, h, yF, 1, rnd, bd, lo, hi);
+  }
+  else
+  {
+    int16_t* tmp = (int16_t*)malloc(sizeof(int16_t) * w * (h + taps - 1));
+    const int16_t* q = p - ((taps >> 1) - 1) * rs;
+    if (altx) filter_n(8, 0, 1, 0, q, rs, tmp, w, w, h + taps - 1, kLumaAltHpel, bd, lo, hi);
+    else orc_filter_hor(is_luma, q, rs, tmp, w, w, h + taps - 1, xF, 0, bd, lo, hi);
+    if (alty) filter_n(8, 1, 0, rnd, tmp + ((taps >> 1) - 1) * w, w, dst, ds, w, h, kLumaAltHpel, bd, lo, hi);
+    else orc_filter_ver(is_luma, tmp + ((taps >> 1) - 1) * w, w, dst, ds, w, h, yF, 0, rnd, bd, lo, hi);
+    free(tmp);
+  }
+}
+
+void orc_dmvr_final_mc(const int16_t* ref, int rs, int is_luma, int ox, int oy, int w, int h, int padsize, int dix, int diy,
+                       int xFrac, int yFrac, int alt_hpel, int bio, int bd, int lo, int hi, int16_t* dst, int ds)
+{
+  /* one component of one list of xFinalPaddedMCForDMVR for a sub-PU that moved (or luma of one that did not):
+   * (ox, oy) = xPrefetch's Rec_offset in component samples, (w, h) the component block, padsize = 2 >> scaleY (:1950),
+   * (dix, diy) = deltaIntMv (:2126-2127), fractions from cMvClipped; output as xPredInterBlk(bi = true): 14-bit, and with
+   * bio (luma) into (2,2) of the (w + 4)-stride BDOF buffer with its ring. */
+  const int taps = is_luma ? 8 : 4, left = (taps >> 1) - 1;
+  const int S = w + 4 + 8;
+  int16_t* pad = (int16_t*)calloc((size_t)S * (h + 4 + 8), sizeof(int16_t));
+  dmvr_prefetch(ref, rs, ox, oy, w + taps - 1, h + taps - 1, pad, S);
+  dmvr_pad(pad, S, w + taps - 1, h + taps - 1, padsize);
+  const int16_t* src = pad + (2 + left) * (S + 1) + diy * S + dix;   /* :2131-2134 */
+  if (bio && is_luma)
+  {
+    const int stride = w + 4;
+    mc_from_ptr(src, S, 1, xFrac, yFrac, w, h, 0, alt_hpel, bd, lo, hi, dst + 2 * stride + 2, stride);
+    bdof_ring(src, S, w, h, xFrac, yFrac, bd, dst);
+  }
+  else mc_from_ptr(src, S, is_luma, xFrac, yFrac, w, h, 0, alt_hpel, bd, lo, hi, dst, ds);
+  free(pad);
+}
+
+/* xPredInterBlk from the reference picture with pu.cu->imv == IMV_HPEL (:948): the alternative half-pel luma filter */
+void orc_mc_block_classic_alt(const int16_t* ref, int rs, int pos_x, int pos_y, int size_w, int size_h, int mv_hor, int mv_ver, int bi,
+                              int bd, int lo, int hi, int16_t* dst, int ds)
+{
+  const int16_t* p = ref + (long)(pos_y + (mv_ver >> 4)) * rs + (pos_x + (mv_hor >> 4));
+  mc_from_ptr(p, rs, 1, mv_hor & 15, mv_ver & 15, size_w, size_h, !bi, 1, bd, lo, hi, dst, ds);
+}
+
 static int32_t div_for_maxq7(int64_t N, int64_t D)
 {
   int32_t sign = 0, q = 0;

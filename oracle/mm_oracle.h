@@ -127,6 +127,18 @@ int orc_dmvr_decide(const uint64_t costs25[25], int dx, int dy, int32_t delta_mv
 
 uint64_t orc_dmvr_cost(const int16_t* a, int as, const int16_t* b, int bs, int w, int h, int simd_sad);
 
+/* Classic DMVR (InterPrediction::xProcessDMVR, InterPrediction.cpp:2239-2439), one sub-PU.  ref0/ref1: luma sample (0,0) of the
+ * padded planes of list 0 / list 1.  (ox, oy): first prefetched luma sample (xPrefetch's Rec_offset), (fx, fy): fraction of the
+ * clipped merge MV.  costs25 as orc_dmvr_costs (index 12 = centre, raw); the decision is orc_dmvr_decide. */
+void orc_dmvr_classic_costs(const int16_t* ref0, int rs0, const int16_t* ref1, int rs1, int ox0, int oy0, int fx0, int fy0,
+                            int ox1, int oy1, int fx1, int fy1, int dx, int dy, int bd, uint64_t costs25[25]);
+/* xFinalPaddedMCForDMVR (:2075-2145) of one component of one list from the prefetched + padded window. */
+void orc_dmvr_final_mc(const int16_t* ref, int rs, int is_luma, int ox, int oy, int w, int h, int padsize, int dix, int diy,
+                       int xFrac, int yFrac, int alt_hpel, int bio, int bd, int lo, int hi, int16_t* dst, int ds);
+/* classic luma MC with the alternative half-pel filter (pu.cu->imv == IMV_HPEL, InterPrediction.cpp:948) */
+void orc_mc_block_classic_alt(const int16_t* ref, int rs, int pos_x, int pos_y, int size_w, int size_h, int mv_hor, int mv_ver, int bi,
+                              int bd, int lo, int hi, int16_t* dst, int ds);
+
 /* Picture::extendPicBorder (Picture.cpp:988-1048): replicate a w x h plane into its margins in place. */
 void orc_extend_border(int16_t* plane00, int stride, int w, int h, int margin_x, int margin_y);
 /* Picture::extendWrapBorder (Picture.cpp:1049-1092): margins continue the picture from the opposite side for the first

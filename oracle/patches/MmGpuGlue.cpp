@@ -230,6 +230,133 @@ void predInterBlkClassicBdof(const Position& blockPos, int width, int height, co
   g.nMcClassic++;
 }
 
+void predInterBlkClassicAltHpel(const Position& blockPos, int width, int height, const Picture* refPic, bool wrapRef, const Mv& mv, bool bi,
+                                const ClpRng& clpRng, PelBuf& dstBuf)
+{
+  const int slot = ensureRef(refPic, wrapRef);
+  const mmgpu_mv m = {mv.hor, mv.ver};
+  chk(mmgpu_mc_alt_hpel(g.ctx, slot, blockPos.x, blockPos.y, width, height, m, bi ? 1 : 0, clpRng.min, clpRng.max, dstBuf.buf, (int)dstBuf.stride),
+      "mc_alt_hpel");
+  g.nMcClassic++;
+}
+
+// ---- classic DMVR -----------------------------------------------------------------------------------------------------
+namespace
+{
+std::vector<mmgpu_dmvr_classic_subpu> g_dmvrSubs;
+std::vector<uint64_t> g_dmvrCosts;
+int g_dmvrDx = 0, g_dmvrDy = 0, g_dmvrCur = -1;
+std::vector<mmgpu_dmvr_mc_job> g_dmvrJobs;
+std::vector<DmvrFinal> g_dmvrFinals;
+std::vector<int16_t> g_dmvrOut;
+uint64_t g_nDmvrSubPus = 0, g_nDmvrFinal = 0, g_nDmvrVerified = 0;
+}
+bool dmvrOnGpu()
+{
+  static const bool on = !(getenv("MMGPU_DMVR") && getenv("MMGPU_DMVR")[0] == '0');
+  return on;
+}
+bool verifying()
+{
+  static const bool on = getenv("MMGPU_VERIFY") && getenv("MMGPU_VERIFY")[0] == '1';
+  return on;
+}
+void dmvrBegin(int dx, int dy)
+{
+  g_dmvrSubs.clear();
+  g_dmvrDx = dx; g_dmvrDy = dy; g_dmvrCur = -1;
+}
+void dmvrAdd(const DmvrList& l0, const DmvrList& l1)
+{
+  mmgpu_dmvr_classic_subpu s;
+  s.w = g_dmvrDx; s.h = g_dmvrDy;
+  s.ref_slot0 = ensureRef(l0.refPic, l0.wrapRef);
+  s.ref_slot1 = ensureRef(l1.refPic, l1.wrapRef);
+  s.org_x0 = l0.orgX; s.org_y0 = l0.orgY; s.frac_x0 = l0.fracX; s.frac_y0 = l0.fracY;
+  s.org_x1 = l1.orgX; s.org_y1 = l1.orgY; s.frac_x1 = l1.fracX; s.frac_y1 = l1.fracY;
+  g_dmvrSubs.push_back(s);
+}
+void dmvrRun()
+{
+  g_dmvrCosts.resize(g_dmvrSubs.size() * 25);
+  chk(mmgpu_dmvr_classic_costs(g.ctx, (int)g_dmvrSubs.size(), g_dmvrSubs.data(), g_dmvrCosts.data()), "dmvr_classic_costs");
+  g_nDmvrSubPus += g_dmvrSubs.size();
+}
+void dmvrSelect(int num)
+{
+  CHECK(num < 0 || num >= (int)g_dmvrSubs.size(), "mmglue: DMVR sub-PU index outside the batch");
+  g_dmvrCur = num;
+}
+bool dmvrActive() { return g_dmvrCur >= 0; }
+uint64_t dmvrCost(int k) { return g_dmvrCosts[(size_t)g_dmvrCur * 25 + k]; }
+void dmvrVerifyCost(int k, uint64_t cpuCost)
+{
+  if (dmvrCost(k) != cpuCost)
+  {
+    fprintf(stderr, "[mmgpu] VERIFY: DMVR cost of sub-PU %d, offset %d: device %llu, reference %llu\n", g_dmvrCur, k,
+            (unsigned long long)dmvrCost(k), (unsigned long long)cpuCost);
+    THROW("mmglue: MMGPU_VERIFY found a classic-DMVR cost that differs from the reference's own");
+  }
+  g_nDmvrVerified++;
+}
+void dmvrEnd() { g_dmvrCur = -1; }
+
+void dmvrFinalAdd(const DmvrFinal& f)
+{
+  mmgpu_dmvr_mc_job j;
+  j.comp = (int)f.compID;
+  j.ref_slot = ensureRef(f.refPic, f.wrapRef);
+  j.org_x = f.orgX; j.org_y = f.orgY; j.w = f.width; j.h = f.height; j.pad = f.pad; j.dint_x = f.dIntX; j.dint_y = f.dIntY;
+  j.frac_x = f.fracX; j.frac_y = f.fracY; j.alt_hpel = f.altHpel ? 1 : 0; j.bio = f.bio ? 1 : 0;
+  int off = 0;
+  if (!g_dmvrJobs.empty())
+  {
+    const mmgpu_dmvr_mc_job& p = g_dmvrJobs.back();
+    off = p.dst_offset + (p.bio ? (p.w + 4) * (p.h + 4) : p.w * p.h);
+  }
+  j.dst_offset = off;
+  j.dst_stride = f.width;
+  g_dmvrJobs.push_back(j);
+  g_dmvrFinals.push_back(f);
+}
+void dmvrFinalRun()
+{
+  if (g_dmvrJobs.empty()) return;
+  const mmgpu_dmvr_mc_job& l = g_dmvrJobs.back();
+  const int total = l.dst_offset + (l.bio ? (l.w + 4) * (l.h + 4) : l.w * l.h);
+  g_dmvrOut.resize(total);
+  chk(mmgpu_dmvr_final_mc(g.ctx, (int)g_dmvrJobs.size(), g_dmvrJobs.data(), g_dmvrOut.data(), total), "dmvr_final_mc");
+  for (size_t i = 0; i < g_dmvrJobs.size(); ++i)
+  {
+    const mmgpu_dmvr_mc_job& j = g_dmvrJobs[i];
+    const DmvrFinal& f = g_dmvrFinals[i];
+    const int16_t* src = g_dmvrOut.data() + j.dst_offset;
+    // bio: only the ring box (rows 1 .. h+2, columns 1 .. w+2) of the work buffer is defined by the reference
+    const int sStride = j.bio ? j.w + 4 : j.w, rows = j.bio ? j.h + 2 : j.h, cols = j.bio ? j.w + 2 : j.w, first = j.bio ? sStride + 1 : 0;
+    const int dStride = j.bio ? j.w + 4 : f.dstStride;
+    for (int y = 0; y < rows; ++y)
+    {
+      Pel* d = f.dst + first + y * dStride;
+      const int16_t* s = src + first + y * sStride;
+      if (verifying())
+      {
+        for (int x = 0; x < cols; ++x)
+          if (d[x] != s[x])
+          {
+            fprintf(stderr, "[mmgpu] VERIFY: DMVR final MC comp %d %dx%d pad %d dint (%d,%d) frac (%d,%d) alt %d bio %d at (%d,%d): device %d, reference %d\n",
+                    j.comp, j.w, j.h, j.pad, j.dint_x, j.dint_y, j.frac_x, j.frac_y, j.alt_hpel, j.bio, x, y, (int)s[x], (int)d[x]);
+            THROW("mmglue: MMGPU_VERIFY found a classic-DMVR final prediction that differs from the reference's own");
+          }
+        g_nDmvrVerified++;
+      }
+      else memcpy(d, s, sizeof(Pel) * cols);
+    }
+  }
+  g_nDmvrFinal += g_dmvrJobs.size();
+  g_dmvrJobs.clear();
+  g_dmvrFinals.clear();
+}
+
 // ---- ME -----------------------------------------------------------------------------------------------------------------
 static Distortion pendingDist(const DistParam&)
 {
@@ -465,6 +592,8 @@ void dumpMc(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, co
 void printStats()
 {
   fprintf(stderr, "[mmgpu] classic MC calls %llu | MM-MVP conversions %llu\n", (unsigned long long)g.nMcClassic, (unsigned long long)g.nMvp);
+  fprintf(stderr, "[mmgpu] classic DMVR: %llu sub-PU searches, %llu final-MC jobs%s\n", (unsigned long long)g_nDmvrSubPus, (unsigned long long)g_nDmvrFinal,
+          verifying() ? (" | VERIFY: " + std::to_string(g_nDmvrVerified) + " comparisons against the reference's own code, all equal").c_str() : "");
   fprintf(stderr, "[mmgpu] MC calls %llu | ME batches %llu, candidates %llu (%.1f per batch), look-ahead hits %llu, single evaluations %llu | "
                   "reference uploads %llu | kernels launched %llu\n",
           (unsigned long long)g.nMc, (unsigned long long)g.nMeBatches, (unsigned long long)g.nMeCands,

@@ -30,7 +30,7 @@ void predInterBlkMM(ComponentID compID, ChromaFormat chFmt, const Position& bloc
                     bool wrapRef, const Mv& mv, MotionModelID motionModel, bool bi, const ClpRng& clpRng, int curPOC, PelBuf& dstBuf);
 
 // plain case of InterPrediction::xPredInterBlk (InterPrediction.cpp:928-1096: classic translational MC of one component; no
-// RPR / BDOF border / DMVR padding / IBC / alternative half-pel filter -- those stay on the reference's code)
+// RPR / BDOF border / DMVR padding / IBC -- those have their own entry points below or stay on the reference's code)
 void predInterBlkClassic(ComponentID compID, ChromaFormat chFmt, const Position& blockPos, int width, int height, const Picture* refPic,
                          bool wrapRef, const Mv& mv, bool bi, const ClpRng& clpRng, PelBuf& dstBuf);
 
@@ -42,6 +42,49 @@ Mv mvpConvert(const Position& position, const Mv& mvOrig, MotionModelID modelOri
 // xPredInterBlk with bioApplied, luma: prediction + ring of integer samples into the BDOF work buffer (stride width + 4)
 void predInterBlkClassicBdof(const Position& blockPos, int width, int height, const Picture* refPic, bool wrapRef, const Mv& mv,
                              const ClpRng& clpRng, Pel* bdofBuf);
+
+// xPredInterBlk of a classic luma block with the alternative half-pel filter (pu.cu->imv == IMV_HPEL), no BDOF
+void predInterBlkClassicAltHpel(const Position& blockPos, int width, int height, const Picture* refPic, bool wrapRef, const Mv& mv, bool bi,
+                                const ClpRng& clpRng, PelBuf& dstBuf);
+
+// ---- classic DMVR, InterPrediction::xProcessDMVR (InterPrediction.cpp:2239-2439).  MMGPU_DMVR=0 keeps it on the reference's code;
+//      MMGPU_VERIFY=1 additionally runs the reference's own code next to the device and stops at the first difference.
+bool dmvrOnGpu();
+bool verifying();
+struct DmvrList
+{
+  const Picture* refPic;
+  bool wrapRef;
+  int orgX, orgY;     // xPrefetch's Rec_offset (luma): first prefetched sample
+  int fracX, fracY;   // fraction xinitMC's xPredInterBlk filters with
+};
+// integer search of every sub-PU of a PU in one batch: Begin, Add per sub-PU (in the loop's order), Run; Select(num) makes
+// sub-PU num's 25 costs current, Cost(k) = xDMVRCost at m_pSearchOffset[k], End forgets them (xBIPMVRefine asks Active()).
+void dmvrBegin(int dx, int dy);
+void dmvrAdd(const DmvrList& l0, const DmvrList& l1);
+void dmvrRun();
+void dmvrSelect(int num);
+bool dmvrActive();
+uint64_t dmvrCost(int k);
+void dmvrVerifyCost(int k, uint64_t cpuCost);
+void dmvrEnd();
+// final MC of one sub-PU (xFinalPaddedMCForDMVR): Add per (list, component) that reads the padded window, Run at the end
+struct DmvrFinal
+{
+  ComponentID compID;
+  const Picture* refPic;
+  bool wrapRef;
+  int orgX, orgY;       // xPrefetch's Rec_offset of the component
+  int width, height;    // component block
+  int pad;              // xPad's padsize (0: sub-PU did not move, window not padded)
+  int dIntX, dIntY;     // deltaIntMv
+  int fracX, fracY;
+  bool altHpel, bio;
+  Pel* dst;             // pcYUVTemp.bufs[compID].buf, or the BDOF work buffer (bio)
+  int dstStride;
+};
+void dmvrFinalAdd(const DmvrFinal& j);
+void dmvrFinalRun();
 
 // ---- motion estimation: xApplyMvVA / xMVReprojectionInterpolation + m_cDistParam.distFunc (InterSearch.cpp:363-453,
 //      5287-5322, 6168-6385).  The search control flow is untouched: candidate sets the reference is about to visit are

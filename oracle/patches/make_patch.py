@@ -93,6 +93,224 @@ def edit_interprediction(t):
     CPelBuf refBuf;
     {
       Position offset = pu.blocks[compID].pos().offset(mv.getHor() >> shiftHor, mv.getVer() >> shiftVer);""")
+    # luma with the alternative half-pel filter (pu.cu->imv == IMV_HPEL): own entry point; chroma ignores the flag
+    t = sub(t, """    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && !useAltHpelIf
+        && width >= 4""", """    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && useAltHpelIf
+        && compID == COMPONENT_Y && width >= 4 && height >= 4 && ( width % 4 ) == 0 && ( height % 4 ) == 0
+        && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
+    {
+      mmglue::predInterBlkClassicAltHpel( pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, bi, clpRng, dstBuf );
+      return;
+    }
+    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf
+        && ( !useAltHpelIf || compID != COMPONENT_Y ) && width >= 4""")
+    # ---- classic DMVR (xProcessDMVR): integer search of all sub-PUs in one batch, final MC of a sub-PU in one batch
+    t = sub(t, """    if (*(pSADsArray + sadOffset) == MAX_UINT64)
+    {
+      const uint64_t cost = xDMVRCost(bd, pRefL0, refStrideL0, pRefL1, refStrideL1, width, height);""", """    if (*(pSADsArray + sadOffset) == MAX_UINT64)
+    {
+      const uint64_t cost = mmglue::dmvrActive() ? mmglue::dmvrCost( nIdx ) : xDMVRCost(bd, pRefL0, refStrideL0, pRefL1, refStrideL1, width, height);""")
+    t = sub(t, """    srcPred0 = srcPred0.subBuf(UnitAreaRelative(pu, subPu));
+    srcPred1 = srcPred1.subBuf(UnitAreaRelative(pu, subPu));
+
+    int yStart = 0;
+    for (int y = puPos.y; y < (puPos.y + pu.lumaSize().height); y = y + dy, yStart = yStart + dy)
+    {
+      for (int x = puPos.x, xStart = 0; x < (puPos.x + pu.lumaSize().width); x = x + dx, xStart = xStart + dx)
+      {
+        PredictionUnit subPu = pu;
+        subPu.UnitArea::operator=(UnitArea(pu.chromaFormat, Area(x, y, dx, dy)));
+        xPrefetch(subPu, m_cYuvRefBuffDMVRL0, REF_PIC_LIST_0, 1);
+        xPrefetch(subPu, m_cYuvRefBuffDMVRL1, REF_PIC_LIST_1, 1);
+
+        xinitMC(subPu, clpRngs);
+
+        uint64_t minCost = MAX_UINT64;""", """    srcPred0 = srcPred0.subBuf(UnitAreaRelative(pu, subPu));
+    srcPred1 = srcPred1.subBuf(UnitAreaRelative(pu, subPu));
+
+    const bool gpuDmvr = mmglue::enabled() && mmglue::classicOnGpu() && mmglue::dmvrOnGpu() && ( dx == 8 || dx == 16 ) && ( dy == 8 || dy == 16 );
+    if( gpuDmvr )
+    {
+      // the bilinear integer search of every sub-PU in ONE device batch: per list the window origin of xPrefetch and the
+      // fraction xinitMC's xPredInterBlk filters with (same statements as there)
+      mmglue::dmvrBegin( dx, dy );
+      for( int y = puPos.y; y < ( puPos.y + pu.lumaSize().height ); y = y + dy )
+      {
+        for( int x = puPos.x; x < ( puPos.x + pu.lumaSize().width ); x = x + dx )
+        {
+          PredictionUnit sp = pu;
+          sp.UnitArea::operator=( UnitArea( pu.chromaFormat, Area( x, y, dx, dy ) ) );
+          mmglue::DmvrList l[2];
+          for( int k = 0; k < NUM_REF_PIC_LIST_01; k++ )
+          {
+            const RefPicList refId  = RefPicList( k );
+            const Picture*   refPic = sp.cu->slice->getRefPic( refId, sp.refIdx[refId] )->unscaledPic;
+            Mv cMv( sp.mv[refId].getHor(), sp.mv[refId].getVer() );
+            cMv += Mv( -( ( ( NTAPS_LUMA >> 1 ) - 1 ) << MV_FRACTIONAL_BITS_INTERNAL ), -( ( ( NTAPS_LUMA >> 1 ) - 1 ) << MV_FRACTIONAL_BITS_INTERNAL ) );
+            bool wrapRef = false;
+            if( refPic->isWrapAroundEnabled( sp.cs->pps ) )
+            {
+              wrapRef = wrapClipMv( cMv, sp.blocks[0].pos(), sp.blocks[0].size(), sp.cs->sps, sp.cs->pps, CLASSIC );
+            }
+            else
+            {
+              clipMv( cMv, sp.lumaPos(), sp.lumaSize(), *sp.cs->sps, *sp.cs->pps, CLASSIC );
+            }
+            Mv mergeMv( sp.mv[refId] );
+            if( !sp.cs->pps->getWrapAroundEnabledFlag() )
+            {
+              clipMv( mergeMv, sp.lumaPos(), sp.lumaSize(), *sp.cs->sps, *sp.cs->pps, CLASSIC );
+            }
+            if( refPic->isWrapAroundEnabled( sp.cs->pps ) )
+            {
+              wrapClipMv( mergeMv, sp.blocks[0].pos(), sp.blocks[0].size(), sp.cs->sps, sp.cs->pps, CLASSIC );
+            }
+            l[k] = mmglue::DmvrList{ refPic, wrapRef, x + ( cMv.getHor() >> MV_FRACTIONAL_BITS_INTERNAL ), y + ( cMv.getVer() >> MV_FRACTIONAL_BITS_INTERNAL ),
+                                     mergeMv.hor & 15, mergeMv.ver & 15 };
+          }
+          mmglue::dmvrAdd( l[0], l[1] );
+        }
+      }
+      mmglue::dmvrRun();
+    }
+
+    int yStart = 0;
+    for (int y = puPos.y; y < (puPos.y + pu.lumaSize().height); y = y + dy, yStart = yStart + dy)
+    {
+      for (int x = puPos.x, xStart = 0; x < (puPos.x + pu.lumaSize().width); x = x + dx, xStart = xStart + dx)
+      {
+        PredictionUnit subPu = pu;
+        subPu.UnitArea::operator=(UnitArea(pu.chromaFormat, Area(x, y, dx, dy)));
+        xPrefetch(subPu, m_cYuvRefBuffDMVRL0, REF_PIC_LIST_0, 1);
+        xPrefetch(subPu, m_cYuvRefBuffDMVRL1, REF_PIC_LIST_1, 1);
+
+        if( gpuDmvr )
+        {
+          mmglue::dmvrSelect( num );
+          if( mmglue::verifying() )
+          {
+            // the reference's own bilinear predictions and its 25 costs next to the device's
+            xinitMC( subPu, clpRngs );
+            for( int nIdx = 0; nIdx < 25; nIdx++ )
+            {
+              Pel* a0 = biLinearPredL0 + m_pSearchOffset[nIdx].hor + ( m_pSearchOffset[nIdx].ver * m_biLinearBufStride );
+              Pel* a1 = biLinearPredL1 - m_pSearchOffset[nIdx].hor - ( m_pSearchOffset[nIdx].ver * m_biLinearBufStride );
+              mmglue::dmvrVerifyCost( nIdx, xDMVRCost( bd, a0, m_biLinearBufStride, a1, m_biLinearBufStride, dx, dy ) );
+            }
+          }
+        }
+        else
+        {
+          xinitMC(subPu, clpRngs);
+        }
+
+        uint64_t minCost = MAX_UINT64;""")
+    t = sub(t, """            minCost = xDMVRCost(clpRngs.comp[COMPONENT_Y].bd, addrL0, m_biLinearBufStride, addrL1, m_biLinearBufStride, dx, dy);
+            minCost -= (minCost >>2);
+            if (minCost < (dx * dy))
+            {
+              notZeroCost = false;
+              break;
+            }
+            pSADsArray[0] = minCost;
+          }
+          if (!minCost)
+          {
+            notZeroCost = false;
+            break;
+          }
+
+          xBIPMVRefine(bd, addrL0, addrL1, minCost, deltaMV, pSADsArray, dx, dy);""", """            minCost = gpuDmvr ? mmglue::dmvrCost( 12 ) : xDMVRCost(clpRngs.comp[COMPONENT_Y].bd, addrL0, m_biLinearBufStride, addrL1, m_biLinearBufStride, dx, dy);
+            minCost -= (minCost >>2);
+            if (minCost < (dx * dy))
+            {
+              notZeroCost = false;
+              break;
+            }
+            pSADsArray[0] = minCost;
+          }
+          if (!minCost)
+          {
+            notZeroCost = false;
+            break;
+          }
+
+          xBIPMVRefine(bd, addrL0, addrL1, minCost, deltaMV, pSADsArray, dx, dy);""")
+    t = sub(t, """        xWeightedAverage(subPu, srcPred0, srcPred1, subPredBuf, subPu.cu->slice->getSPS()->getBitDepths(), subPu.cu->slice->clpRngs(), bioAppliedType[num]);
+        num++;
+      }
+    }
+  }
+  JVET_J0090_SET_CACHE_ENABLE(true);
+}""", """        xWeightedAverage(subPu, srcPred0, srcPred1, subPredBuf, subPu.cu->slice->getSPS()->getBitDepths(), subPu.cu->slice->clpRngs(), bioAppliedType[num]);
+        num++;
+      }
+    }
+    mmglue::dmvrEnd();
+  }
+  JVET_J0090_SET_CACHE_ENABLE(true);
+}""")
+    # xFinalPaddedMCForDMVR: the components that read the padded window go to the device in one batch per sub-PU
+    t = sub(t, """        offset = (DMVR_NUM_ITERATION + leftPixelExtra) * (pcPadTemp.bufs[compID].stride + 1);
+        offset += (deltaIntMvY)* pcPadTemp.bufs[compID].stride;
+        offset += (deltaIntMvX);
+        srcBufPelPtr = (srcBuf.buf + offset);
+      }
+""", """        offset = (DMVR_NUM_ITERATION + leftPixelExtra) * (pcPadTemp.bufs[compID].stride + 1);
+        offset += (deltaIntMvY)* pcPadTemp.bufs[compID].stride;
+        offset += (deltaIntMvX);
+        srcBufPelPtr = (srcBuf.buf + offset);
+        const int cw = pu.blocks[compID].width, ch = pu.blocks[compID].height;
+        if( mmglue::enabled() && mmglue::classicOnGpu() && mmglue::dmvrOnGpu() && cw <= 16 && ch <= 16
+            && cw == (int) pcYUVTemp.bufs[compID].width && ch == (int) pcYUVTemp.bufs[compID].height )
+        {
+          // window origin as xPrefetch computed it from the merge MV (InterPrediction.cpp:1906-1931) ...
+          const int filtersize = ( compID == COMPONENT_Y ) ? NTAPS_LUMA : NTAPS_CHROMA;
+          Mv wMv( startMv.getHor(), startMv.getVer() );
+          wMv += Mv( -( ( ( filtersize >> 1 ) - 1 ) << mvshiftTempHor ), -( ( ( filtersize >> 1 ) - 1 ) << mvshiftTempVer ) );
+          bool wrapRef = false;
+          if( refPic->isWrapAroundEnabled( pu.cs->pps ) )
+          {
+            wrapRef = wrapClipMv( wMv, pu.blocks[0].pos(), pu.blocks[0].size(), pu.cs->sps, pu.cs->pps, CLASSIC );
+          }
+          else
+          {
+            clipMv( wMv, pu.lumaPos(), pu.lumaSize(), *pu.cs->sps, *pu.cs->pps, CLASSIC );
+          }
+          // ... and the fraction xPredInterBlk filters with (:942-971)
+          Mv fMv( cMvClipped );
+          if( refPic->isWrapAroundEnabled( pu.cs->pps ) )
+          {
+            wrapClipMv( fMv, pu.blocks[0].pos(), pu.blocks[0].size(), pu.cs->sps, pu.cs->pps, CLASSIC );
+          }
+          const int csx = ::getComponentScaleX( (ComponentID) compID, pu.chromaFormat ), csy = ::getComponentScaleY( (ComponentID) compID, pu.chromaFormat );
+          const int xFrac = compID == COMPONENT_Y ? ( fMv.hor & 15 ) : ( fMv.hor * ( 1 << ( 1 - csx ) ) & 31 );
+          const int yFrac = compID == COMPONENT_Y ? ( fMv.ver & 15 ) : ( fMv.ver * ( 1 << ( 1 - csy ) ) & 31 );
+          const bool bio = bioApplied && compID == COMPONENT_Y;
+          mmglue::DmvrFinal job = { (ComponentID) compID, refPic, wrapRef,
+                                    pu.blocks[compID].x + ( wMv.getHor() >> mvshiftTempHor ), pu.blocks[compID].y + ( wMv.getVer() >> mvshiftTempVer ), cw, ch,
+                                    blockMoved ? ( DMVR_NUM_ITERATION >> csy ) : 0, deltaIntMvX, deltaIntMvY, xFrac, yFrac, pu.cu->imv == IMV_HPEL, bio,
+                                    bio ? m_filteredBlockTmp[2 + m_iRefListIdx][compID] : pcYUVTemp.bufs[compID].buf, (int) pcYUVTemp.bufs[compID].stride };
+          mmglue::dmvrFinalAdd( job );
+          if( !mmglue::verifying() )
+          {
+            continue;
+          }
+        }
+      }
+""")
+    t = sub(t, """    pcYUVTemp = pcYuvSrc1;
+    pcPadTemp = pcPad1;
+  }
+}
+
+uint64_t InterPrediction::xDMVRCost(""", """    pcYUVTemp = pcYuvSrc1;
+    pcPadTemp = pcPad1;
+  }
+  mmglue::dmvrFinalRun();
+}
+
+uint64_t InterPrediction::xDMVRCost(""")
     # debugging aid (MMGPU_DUMP): record the CPU path's result
     t = sub(t, """      }
     }

@@ -90,6 +90,21 @@ extern "C" void ref_filter_ver(int compID, const Pel* src, int srcStride, Pel* d
                   mk_clp(bd, lo, hi), InterpolationFilter::FILTER_DEFAULT, false);
 }
 
+// the same two with the filter index / alternative half-pel flag exposed: dmvr != 0 -> FILTER_DMVR (bilinear, xinitMC),
+// altHpel != 0 -> useAltHpelIf (pu.cu->imv == IMV_HPEL, InterPrediction.cpp:948)
+extern "C" void ref_filter_hor_x(const Pel* src, int srcStride, Pel* dst, int dstStride, int w, int h, int frac, int isLast, int bd,
+                                 int lo, int hi, int dmvr, int altHpel)
+{
+  g_if->filterHor(COMPONENT_Y, src, srcStride, dst, dstStride, w, h, frac, isLast != 0, mk_clp(bd, lo, hi),
+                  dmvr ? InterpolationFilter::FILTER_DMVR : InterpolationFilter::FILTER_DEFAULT, altHpel != 0);
+}
+extern "C" void ref_filter_ver_x(const Pel* src, int srcStride, Pel* dst, int dstStride, int w, int h, int frac, int isFirst,
+                                 int isLast, int bd, int lo, int hi, int dmvr, int altHpel)
+{
+  g_if->filterVer(COMPONENT_Y, src, srcStride, dst, dstStride, w, h, frac, isFirst != 0, isLast != 0, mk_clp(bd, lo, hi),
+                  dmvr ? InterpolationFilter::FILTER_DMVR : InterpolationFilter::FILTER_DEFAULT, altHpel != 0);
+}
+
 // RdCost::setDistParam(rcDP, org, piRefY, iRefStride, bitDepth, compID, subShiftMode, step, useHadamard) + distFunc:
 // what InterSearch does per ME candidate (InterSearch.cpp:6171, 6189, 6235; RdCost.cpp:225-311)
 extern "C" unsigned long long ref_dist(const Pel* org, int orgStride, const Pel* cur, int curStride, int w, int h, int bd,

@@ -65,6 +65,9 @@ def lib():
         L.orc_dmvr_cost.restype = C.c_uint64
         L.orc_dmvr_cost.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_dmvr_decide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_dmvr_classic_costs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 11 + [C.c_void_p]
+        L.orc_dmvr_final_mc.argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 15 + [C.c_void_p, C.c_int]
+        L.orc_mc_block_classic_alt.argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 10 + [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -175,6 +178,30 @@ def dmvr_costs(o, plane0, plane1, pos, size, mv0, mv1, model, R0=None, R1=None, 
                          mv0[0], mv0[1], mv1[0], mv1[1], model, None if r0 is None else r0.ctypes.data,
                          None if r1 is None else r1.ctypes.data, clp[0], clp[1], simd, out.ctypes.data)
     return out
+
+
+def dmvr_classic_costs(plane0, plane1, org0, frac0, org1, frac1, size, bd=10):
+    """xProcessDMVR's bilinear search of one sub-PU: org = xPrefetch's Rec_offset (luma), frac = clipped merge MV & 15."""
+    out = np.zeros(25, dtype=np.uint64)
+    lib().orc_dmvr_classic_costs(plane0.origin, plane0.stride, plane1.origin, plane1.stride, org0[0], org0[1], frac0[0], frac0[1],
+                                 org1[0], org1[1], frac1[0], frac1[1], size[0], size[1], bd, out.ctypes.data)
+    return out
+
+
+def dmvr_final_mc(plane, is_luma, org, size, padsize, dint, frac, alt_hpel=False, bio=False, bd=10, clp=(0, 1023)):
+    """xFinalPaddedMCForDMVR of one component of one list; bio: returns the (h + 4) x (w + 4) BDOF buffer."""
+    w, h = size
+    dst = np.zeros((h + 4, w + 4) if bio else (h, w), dtype=np.int16)
+    lib().orc_dmvr_final_mc(plane.origin, plane.stride, int(is_luma), org[0], org[1], w, h, padsize, dint[0], dint[1], frac[0], frac[1],
+                            int(alt_hpel), int(bio), bd, clp[0], clp[1], dst.ctypes.data, dst.shape[1])
+    return dst
+
+
+def mc_block_classic_alt(plane, pos, size, mv, bi=False, bd=10, clp=(0, 1023)):
+    dst = np.zeros((size[1], size[0]), dtype=np.int16)
+    lib().orc_mc_block_classic_alt(plane.origin, plane.stride, pos[0], pos[1], size[0], size[1], mv[0], mv[1], int(bi), bd, clp[0], clp[1],
+                                   dst.ctypes.data, size[0])
+    return dst
 
 
 def dmvr_decide(costs25, w, h):

@@ -25,6 +25,8 @@ def lib():
         L.ref_init.argtypes = [C.c_int]
         L.ref_filter_hor.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 7
         L.ref_filter_ver.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 8
+        L.ref_filter_hor_x.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 9
+        L.ref_filter_ver_x.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 10
         L.ref_dist.restype = C.c_uint64
         L.ref_dist.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 5
         L.ref_dist_subshift.restype = C.c_int
@@ -50,6 +52,21 @@ def filter_ver(comp, src, x0, y0, w, h, frac, is_first, is_last, bd=10, clp=(0, 
     dst = np.zeros((h, w), dtype=np.int16)
     lib().ref_filter_ver(comp, src.ctypes.data + 2 * (y0 * src.shape[1] + x0), src.shape[1], dst.ctypes.data, w, w, h, frac,
                          int(is_first), int(is_last), bd, clp[0], clp[1])
+    return dst
+
+
+def filter_hor_x(src, x0, y0, w, h, frac, is_last, bd=10, clp=(0, 1023), dmvr=False, alt_hpel=False):
+    """luma filterHor with FILTER_DMVR (bilinear) or useAltHpelIf; src: 2-D int16 array, (x0, y0) the first output sample"""
+    dst = np.zeros((h, w), dtype=np.int16)
+    lib().ref_filter_hor_x(src.ctypes.data + 2 * (y0 * src.shape[1] + x0), src.shape[1], dst.ctypes.data, w, w, h, frac, int(is_last),
+                           bd, clp[0], clp[1], int(dmvr), int(alt_hpel))
+    return dst
+
+
+def filter_ver_x(src, x0, y0, w, h, frac, is_first, is_last, bd=10, clp=(0, 1023), dmvr=False, alt_hpel=False):
+    dst = np.zeros((h, w), dtype=np.int16)
+    lib().ref_filter_ver_x(src.ctypes.data + 2 * (y0 * src.shape[1] + x0), src.shape[1], dst.ctypes.data, w, w, h, frac, int(is_first),
+                           int(is_last), bd, clp[0], clp[1], int(dmvr), int(alt_hpel))
     return dst
 
 

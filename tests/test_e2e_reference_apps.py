@@ -214,3 +214,23 @@ def test_encoder_app_random_access_bitstream_identical(tmp_path):
     assert r.returncode == 0, log[-2000:]
     print(log[-1500:])
     assert open(bit, "rb").read() == open(os.path.join(GOLD, "mm_ra_q37.bin"), "rb").read(), log[-3000:]
+
+
+@pytest.mark.gpu
+def test_decoder_app_random_access_verify_mode(tmp_path):
+    """MMGPU_VERIFY=1: classic DMVR (integer search costs and final padded MC) runs on the device AND through the reference's own
+    code in the same process; the app stops at the first differing cost or sample.  The stats line says how many were compared."""
+    dec, _, _ = _apps()
+    out = str(tmp_path / "dec.yuv")
+    env = dict(os.environ, MMGPU_VERIFY="1")
+    r = subprocess.run([dec, "-b", os.path.join(GOLD, "mm_ra_q37.bin"), "-o", out], capture_output=True, text=True, timeout=900, env=env)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-2000:]
+    line = [l for l in log.splitlines() if "classic DMVR" in l]
+    assert line, log[-2000:]
+    print(line[0])
+    assert log.count("(OK)") == 5 and "***ERROR***" not in log, log[-2000:]
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == open(os.path.join(GOLD, "mm_ra_q37.md5")).read().strip()
+    n_sub = int(line[0].split("classic DMVR:")[1].split()[0])
+    if n_sub:
+        assert "VERIFY:" in line[0] and int(line[0].split("VERIFY:")[1].split()[0]) > 0

@@ -837,6 +837,72 @@ def test_classic_bi_mc_with_bdof_border_fetch(env):
         assert np.array_equal(got[1:h + 3, 1:w + 3], exp[1:h + 3, 1:w + 3]), (x, y, w, h, mv)
 
 
+def test_classic_dmvr_search_and_final_mc(env):
+    """f4 (second half): InterPrediction::xProcessDMVR (InterPrediction.cpp:2239-2439).  The bilinear integer search of batched
+    sub-PUs (mmgpu_dmvr_classic_costs == oracle's literal prefetch-buffer restatement, incl. windows in the picture margin), the
+    decision (mmgpu_dmvr_decide == oracle) and the final MC from the window padded by replication (mmgpu_dmvr_final_mc):
+    luma / chroma, every integer displacement, the alternative half-pel filter and the BDOF ring."""
+    o, g, planes, ref, cur = env
+    ref1 = wl.pad_frame(wl.synth_frame(W, H, seed=13, shift=(-2.0, 0.5)), 288, 1)
+    g.set_ref(1, 1, [p.origin for p in ref1], [p.stride for p in ref1])
+    rng = np.random.default_rng(2239)
+    subs = np.zeros(96, dtype=mm.api.DMVR_CLASSIC_DTYPE)
+    for i in range(len(subs)):
+        w, h = [(16, 16), (8, 16), (16, 8), (8, 8)][i % 4]
+        s = subs[i]
+        s["w"], s["h"], s["ref_slot0"], s["ref_slot1"] = w, h, i % 2, 1 - i % 2
+        for l in "01":
+            if i % 5 == 0:   # windows reaching into the margin
+                s["org_x" + l] = [-250, W + 200, int(rng.integers(0, W))][i % 3]
+                s["org_y" + l] = [int(rng.integers(0, H)), -240, H + 190][i % 3]
+            else:
+                s["org_x" + l], s["org_y" + l] = int(rng.integers(-3, W - w - 4)), int(rng.integers(-3, H - h - 4))
+            s["frac_x" + l], s["frac_y" + l] = [(0, 0), (int(rng.integers(0, 16)), 0), (0, int(rng.integers(0, 16))),
+                                                 (int(rng.integers(1, 16)), int(rng.integers(1, 16)))][(i // 4 + int(l)) % 4]
+    got = g.dmvr_classic_costs(subs)
+    pl = [planes, ref1]
+    for i, s in enumerate(subs):
+        p0, p1 = pl[int(s["ref_slot0"])][0], pl[int(s["ref_slot1"])][0]
+        exp = ol.dmvr_classic_costs(p0, p1, (int(s["org_x0"]), int(s["org_y0"])), (int(s["frac_x0"]), int(s["frac_y0"])),
+                                    (int(s["org_x1"]), int(s["org_y1"])), (int(s["frac_x1"]), int(s["frac_y1"])), (int(s["w"]), int(s["h"])))
+        assert np.array_equal(exp, got[i]), (i, s)
+        assert ol.dmvr_decide(exp, int(s["w"]), int(s["h"])) == mm.dmvr_decide(got[i], int(s["w"]), int(s["h"]))
+    assert len({mm.dmvr_decide(c, 16, 16)[1] for c in got}) > 3     # the search does move
+    # final MC
+    jobs, exps, off = [], [], 0
+    for i in range(240):
+        comp = i % 3
+        luma = comp == 0
+        w, h = ([(16, 16), (8, 16), (16, 8), (8, 8)] if luma else [(8, 8), (4, 8), (8, 4), (4, 4)])[(i // 3) % 4]
+        pad = (2 if luma else 1) if i % 7 else 0
+        dint = (int(rng.integers(-pad, pad + 1)), int(rng.integers(-pad, pad + 1)))
+        nph = 16 if luma else 32
+        frac = [(0, 0), (8 if luma else 16, 0), (0, 8 if luma else 16), (8 if luma else 16,) * 2, (int(rng.integers(1, nph)), int(rng.integers(1, nph))),
+                (int(rng.integers(1, 8)), 0)][i % 6]
+        alt, bio = int(luma and i % 2 == 0), int(luma and i % 4 < 2)
+        pw, ph = (W, H) if luma else (W // 2, H // 2)
+        org = (int(rng.integers(-8, pw - w)), int(rng.integers(-8, ph - h))) if i % 11 else (-(100 >> (not luma)), ph + 20)
+        slot = i % 2
+        n = (w + 4) * (h + 4) if bio else w * h
+        jobs.append((comp, slot, org[0], org[1], w, h, pad, dint[0], dint[1], frac[0], frac[1], alt, bio, off, w))
+        exps.append((off, n, ol.dmvr_final_mc(pl[slot][comp], luma, org, (w, h), pad, dint, frac, alt_hpel=bool(alt), bio=bool(bio))))
+        off += n
+    out = g.dmvr_final_mc(np.array(jobs, dtype=mm.api.DMVR_MC_JOB_DTYPE), off)
+    for k, (o0, n, exp) in enumerate(exps):
+        gotk = out[o0:o0 + n].reshape(exp.shape)
+        if jobs[k][12]:   # bio: rows 1..h+2, columns 1..w+2 are defined
+            assert np.array_equal(gotk[1:-1, 1:-1], exp[1:-1, 1:-1]), jobs[k]
+        else:
+            assert np.array_equal(gotk, exp), jobs[k]
+    # plain xPredInterBlk with pu.cu->imv == IMV_HPEL
+    for (w, h) in [(8, 8), (16, 32), (64, 64), (128, 128), (48, 8), (4, 16)]:
+        for mv in [(8, 0), (0, 8), (8, 8), (-24, 40), (8, 3), (5, 8), (16, -16), (int(rng.integers(-500, 500)) * 8, int(rng.integers(-300, 300)) * 8)]:
+            x, y = rand_block(rng, w, h)
+            for bi in (False, True):
+                assert np.array_equal(ol.mc_block_classic_alt(planes[0], (x, y), (w, h), mv, bi=bi), g.mc_alt_hpel(0, (x, y), (w, h), mv, bi=bi)), (w, h, mv, bi)
+    g.set_ref(1, 0, [p.origin for p in ref], [p.stride for p in ref])
+
+
 def test_mc_non_power_of_two_blocks(env):
     """The encoder's RD search also predicts 12 / 24 / 48-wide blocks (found by the random-access end-to-end run: a 48x8
     xPredInterBlkMM call): mmgpu_mc takes every size that is a multiple of the sub-block."""

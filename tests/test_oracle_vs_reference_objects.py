@@ -129,3 +129,103 @@ def test_classic_chroma_phase_equals_reference_filters(fmt):
         ol.lib().orc_mc_block_classic(ref.ctypes.data, ref.shape[1], 1, fmt, x0, y0, w, h, mv[0], mv[1], 0, 10, 0, 1023,
                                       dst.ctypes.data, w)
         assert np.array_equal(dst, exp), (fmt, mv)
+
+
+class _Pl:
+    def __init__(self, arr, x0, y0):
+        self.arr, self.stride = arr, arr.shape[1]
+        self.origin = arr.ctypes.data + 2 * (y0 * arr.shape[1] + x0)
+
+
+def _ref_mc(src, x, y, w, h, xF, yF, bi, dmvr=False, alt=False, bd=10):
+    """xPredInterBlk's cascade (InterPrediction.cpp:1019-1049) on the reference's compiled luma filters"""
+    taps = 2 if dmvr else 8
+    if yF == 0:
+        return rl.filter_hor_x(src, x, y, w, h, xF, not bi, bd, dmvr=dmvr, alt_hpel=alt)
+    if xF == 0:
+        return rl.filter_ver_x(src, x, y, w, h, yF, 1, not bi, bd, dmvr=dmvr, alt_hpel=alt)
+    half = (taps >> 1) - 1
+    tmp = np.zeros((h + taps - 1, src.shape[1]), dtype=np.int16)
+    tmp[:, :w] = rl.filter_hor_x(src, x, y - half, w, h + taps - 1, xF, 0, bd, dmvr=dmvr, alt_hpel=alt)
+    return rl.filter_ver_x(tmp, 0, half, w, h, yF, 0, not bi, bd, dmvr=dmvr, alt_hpel=alt)
+
+
+@pytest.mark.parametrize("level", [0, 2])
+def test_classic_dmvr_search_equals_reference_filters(level):
+    """xProcessDMVR's integer search (InterPrediction.cpp:2343-2381): the expectation prefetches the window like xPrefetch, runs the
+    reference's own FILTER_DMVR filterHor/filterVer objects over it as xinitMC does and the reference's xDMVRCost on the 25 offsets."""
+    if level > rl.lib().ref_host_level():
+        pytest.skip("host lacks this SIMD level")
+    rl.init(level)
+    rng = np.random.default_rng(300 + level)
+    offs = [(ox, oy) for oy in range(-2, 3) for ox in range(-2, 3)]
+    for bd in (8, 10):
+        ref = [rng.integers(0, 1 << bd, size=(96, 128)).astype(np.int16) for _ in range(2)]
+        for (dx, dy) in [(16, 16), (8, 16), (16, 8), (8, 8)]:
+            for fr in [((0, 0), (0, 0)), ((5, 0), (0, 9)), ((3, 12), (15, 1)), ((8, 8), (0, 0)), ((0, 7), (11, 0))]:
+                org = [(int(rng.integers(8, 80)), int(rng.integers(8, 50))) for _ in range(2)]
+                pred = []
+                for l in range(2):
+                    S = dx + 12
+                    pad = np.zeros((dy + 12, S), dtype=np.int16)
+                    pad[2:2 + dy + 7, 2:2 + dx + 7] = ref[l][org[l][1]:org[l][1] + dy + 7, org[l][0]:org[l][0] + dx + 7]
+                    pred.append(_ref_mc(pad, 3, 3, dx + 4, dy + 4, fr[l][0], fr[l][1], True, dmvr=True, bd=bd))
+                exp = np.zeros(25, dtype=np.uint64)
+                for k, (oh, ov) in enumerate(offs):
+                    a = np.ascontiguousarray(pred[0][2 + ov:2 + ov + dy, 2 + oh:2 + oh + dx])
+                    b = np.ascontiguousarray(pred[1][2 - ov:2 - ov + dy, 2 - oh:2 - oh + dx])
+                    exp[k] = rl.lib().ref_dmvr_cost(a.ctypes.data, dx, b.ctypes.data, dx, dx, dy, bd)
+                got = ol.dmvr_classic_costs(_Pl(ref[0], 0, 0), _Pl(ref[1], 0, 0), org[0], fr[0], org[1], fr[1], (dx, dy), bd)
+                assert np.array_equal(exp, got), (bd, dx, dy, fr)
+    rl.init(-1)
+
+
+def test_classic_dmvr_final_mc_and_alt_hpel_equal_reference_filters():
+    """xFinalPaddedMCForDMVR (InterPrediction.cpp:2075-2145): window prefetched + padded by replication (numpy), then the reference's
+    own 8-tap / 4-tap filter objects from the moved position -- with the alternative half-pel filter (imv == IMV_HPEL) and the BDOF
+    ring; and plain xPredInterBlk with useAltHpelIf from the picture."""
+    rl.init(-1)
+    rng = np.random.default_rng(411)
+    ref = rng.integers(0, 1024, size=(96, 128)).astype(np.int16)
+    pl = _Pl(ref, 0, 0)
+    for is_luma, taps, padsize, (w, h) in [(1, 8, 2, (16, 16)), (1, 8, 2, (8, 16)), (0, 4, 1, (8, 8)), (0, 4, 1, (4, 8))]:
+        left = (taps >> 1) - 1
+        for (dix, diy) in [(0, 0), (2, -2), (-2, 2), (1, 0), (-padsize, -padsize)]:
+            if abs(dix) > padsize or abs(diy) > padsize:
+                continue
+            for (xF, yF) in [(0, 0), (8, 0), (0, 8), (8, 8), (5, 11), (8, 3)]:
+                for alt in (False, True):
+                    org = (int(rng.integers(8, 80)), int(rng.integers(8, 50)))
+                    ww, wh = w + taps - 1, h + taps - 1
+                    win = ref[org[1]:org[1] + wh, org[0]:org[0] + ww]
+                    S = w + 12
+                    pad = np.zeros((h + 12, S), dtype=np.int16)
+                    pad[2 - padsize:2 + wh + padsize, 2 - padsize:2 + ww + padsize] = np.pad(win, padsize, mode="edge")
+                    sx, sy = 2 + left + dix, 2 + left + diy
+                    if is_luma:
+                        exp = _ref_mc(pad, sx, sy, w, h, xF, yF, True, alt=alt)
+                    else:
+                        fx, fy = xF * 2, yF * 2      # any of the 32 chroma phases
+                        if fy == 0:
+                            exp = rl.filter_hor(1, pad, sx, sy, w, h, fx, 0)
+                        elif fx == 0:
+                            exp = rl.filter_ver(1, pad, sx, sy, w, h, fy, 1, 0)
+                        else:
+                            tmp = np.zeros((h + 3, S), dtype=np.int16)
+                            tmp[:, :w] = rl.filter_hor(1, pad, sx, sy - 1, w, h + 3, fx, 0)
+                            exp = rl.filter_ver(1, tmp, 0, 1, w, h, fy, 0, 0)
+                    got = ol.dmvr_final_mc(pl, is_luma, org, (w, h), padsize, (dix, diy), (xF, yF) if is_luma else (xF * 2, yF * 2), alt_hpel=alt)
+                    assert np.array_equal(exp, got), (is_luma, w, h, dix, diy, xF, yF, alt)
+                    if is_luma:
+                        # BDOF ring (:1054-1093): integer samples of the padded buffer around the moved block
+                        bio = ol.dmvr_final_mc(pl, 1, org, (w, h), padsize, (dix, diy), (xF, yF), alt_hpel=alt, bio=True)
+                        assert np.array_equal(bio[2:2 + h, 2:2 + w], exp)
+                        xo, yo = (1 if xF < 8 else 0), (1 if yF < 8 else 0)
+                        ring = (pad[sy - yo:sy - yo + h + 2, sx - xo:sx - xo + w + 2].astype(np.int32) << 4) - 8192
+                        assert np.array_equal(bio[1, 1:w + 3], ring[0]) and np.array_equal(bio[h + 2, 1:w + 3], ring[h + 1])
+                        assert np.array_equal(bio[2:h + 2, 1], ring[1:h + 1, 0]) and np.array_equal(bio[2:h + 2, w + 2], ring[1:h + 1, w + 1])
+    # xPredInterBlk from the picture with the alternative half-pel filter
+    for mv in [(8, 0), (0, 8), (8, 8), (24, -8), (8, 5), (3, 8), (16, 16)]:
+        for bi in (False, True):
+            exp = _ref_mc(ref, 40 + (mv[0] >> 4), 32 + (mv[1] >> 4), 16, 8, mv[0] & 15, mv[1] & 15, bi, alt=True)
+            assert np.array_equal(exp, ol.mc_block_classic_alt(pl, (40, 32), (16, 8), mv, bi=bi)), (mv, bi)

@@ -22,6 +22,7 @@ EXPORTS = [
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
     "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode", "mmgpu_mc_jobs_device", "mmgpu_set_refs_unpadded_device", "mmgpu_mvp_convert", "mmgpu_mc_bdof",
+    "mmgpu_dmvr_classic_costs", "mmgpu_dmvr_final_mc", "mmgpu_mc_alt_hpel",
 ]
 
 
@@ -55,6 +56,11 @@ JOB_DTYPE = np.dtype([("comp", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"),
 DMVR_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("model", "<i4"), ("ref_slot0", "<i4"),
                        ("ref_slot1", "<i4"), ("rot_slot0", "<i4"), ("rot_slot1", "<i4"), ("mv0_hor", "<i4"),
                        ("mv0_ver", "<i4"), ("mv1_hor", "<i4"), ("mv1_ver", "<i4")])
+DMVR_CLASSIC_DTYPE = np.dtype([("w", "<i4"), ("h", "<i4"), ("ref_slot0", "<i4"), ("ref_slot1", "<i4"), ("org_x0", "<i4"), ("org_y0", "<i4"),
+                               ("org_x1", "<i4"), ("org_y1", "<i4"), ("frac_x0", "<i4"), ("frac_y0", "<i4"), ("frac_x1", "<i4"), ("frac_y1", "<i4")])
+DMVR_MC_JOB_DTYPE = np.dtype([("comp", "<i4"), ("ref_slot", "<i4"), ("org_x", "<i4"), ("org_y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("pad", "<i4"),
+                              ("dint_x", "<i4"), ("dint_y", "<i4"), ("frac_x", "<i4"), ("frac_y", "<i4"), ("alt_hpel", "<i4"), ("bio", "<i4"),
+                              ("dst_offset", "<i4"), ("dst_stride", "<i4")])
 
 _lib = None
 
@@ -108,6 +114,9 @@ def load_library():
     L.mmgpu_plan_samples.argtypes = [vp]
     L.mmgpu_mc_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
     L.mmgpu_dmvr_costs.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.mmgpu_dmvr_classic_costs.argtypes = [vp, i32, vp, vp]
+    L.mmgpu_dmvr_final_mc.argtypes = [vp, i32, vp, vp, i32]
+    L.mmgpu_mc_alt_hpel.argtypes = [vp, i32, i32, i32, i32, i32, Mv, i32, i32, i32, vp, i32]
     L.mmgpu_mc_bdof.argtypes = [vp, i32, i32, i32, i32, i32, Mv, i32, i32, vp]
     L.mmgpu_mc_jobs.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
     L.mmgpu_mc_jobs_device.argtypes = [vp, i32, vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_int32)]
@@ -380,6 +389,27 @@ class MmGpu:
         out = np.zeros((len(subpus), 25), dtype=np.uint64)
         self._chk(self.L.mmgpu_dmvr_costs(self.h, len(subpus), subpus.ctypes.data, clp[0], clp[1], out.ctypes.data))
         return out
+
+    def dmvr_classic_costs(self, subpus):
+        """subpus: DMVR_CLASSIC_DTYPE -> (n, 25) uint64 xDMVRCost of xProcessDMVR's bilinear search (index 12 = centre, raw)."""
+        subpus = np.ascontiguousarray(subpus, dtype=DMVR_CLASSIC_DTYPE)
+        out = np.zeros((len(subpus), 25), dtype=np.uint64)
+        self._chk(self.L.mmgpu_dmvr_classic_costs(self.h, len(subpus), subpus.ctypes.data, out.ctypes.data))
+        return out
+
+    def dmvr_final_mc(self, jobs, dst_samples):
+        """jobs: DMVR_MC_JOB_DTYPE -> flat int16 buffer holding every job's output at its dst_offset (xFinalPaddedMCForDMVR)."""
+        jobs = np.ascontiguousarray(jobs, dtype=DMVR_MC_JOB_DTYPE)
+        out = np.zeros(int(dst_samples), dtype=np.int16)
+        self._chk(self.L.mmgpu_dmvr_final_mc(self.h, len(jobs), jobs.ctypes.data, out.ctypes.data, int(dst_samples)))
+        return out
+
+    def mc_alt_hpel(self, ref_slot, pos, size, mv, bi=False, clp=(0, 1023)):
+        """Classic luma xPredInterBlk with the alternative half-pel filter (pu.cu->imv == IMV_HPEL)."""
+        w, h = size
+        dst = np.zeros((h, w), dtype=np.int16)
+        self._chk(self.L.mmgpu_mc_alt_hpel(self.h, ref_slot, pos[0], pos[1], w, h, Mv(mv[0], mv[1]), int(bi), clp[0], clp[1], dst.ctypes.data, w))
+        return dst
 
     def plan(self, blocks, n_cands):
         blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)

@@ -1,6 +1,6 @@
 """Build libmmgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-Four translation units (host ABI + three kernel files) are compiled in parallel to objects under csrc/_obj/ and
+Five translation units (host ABI + four kernel files) are compiled in parallel to objects under csrc/_obj/ and
 linked into one shared library; only units whose sources changed are recompiled."""
 import os
 import subprocess
@@ -16,6 +16,7 @@ UNITS = {
     "mm_kernels_map.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_tan_exceptions.h", "mm_sbpos.cuh"],
     "mm_kernels_fir.cu": ["mm_common.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_fir.cuh", "mm_htaps.h"],
     "mm_kernels_mc.cu": HDRS,
+    "mm_kernels_dmvr.cu": ["mm_common.cuh"],
 }
 ABI_H = os.path.join(os.path.dirname(HERE), "include", "mmgpu.h")
 OUT = os.path.join(HERE, "libmmgpu.so")

@@ -215,5 +215,8 @@ void mmk_bdof_ring(cudaStream_t s, const int16_t* ref, int stride, int x0, int y
 #define MM_JOB_CHUNK 64   // sub-blocks per k_mc_jobs CTA
 void mmk_mc_jobs(cudaStream_t s, const MmParams& P, int nItems, const mmgpu_mc_job* jobs, const int2* items, int16_t* dstY, int16_t* dstCb,
                  int16_t* dstCr, int strideY, int strideC, int csxC, int csyC, int avgShift, int avgOffset);
+void mmk_dmvr_classic(cudaStream_t s, const MmRef* refs, const mmgpu_dmvr_classic_subpu* subpus, int n, int bd, unsigned long long* costs);
+void mmk_dmvr_final_mc(cudaStream_t s, const MmRef* refs, const MmFir& f, const mmgpu_dmvr_mc_job* jobs, int n, int rnd, int lo, int hi,
+                       int16_t* dst);
 void mmk_dmvr(cudaStream_t s, const MmParams& P, const mmgpu_dmvr_subpu* subpus, const MmDmvrItem* items, int nItems,
               int simdSad, unsigned long long* costs);

@@ -101,6 +101,10 @@ struct mmgpu_ctx
   size_t capPic[3];
   MmDmvrItem* dDmvrItems;
   size_t capDmvrItems;
+  mmgpu_dmvr_classic_subpu* dSubpusC;   // classic DMVR: search sub-PUs / final-MC jobs
+  size_t capSubpusC;
+  mmgpu_dmvr_mc_job* dDmvrJobs;
+  size_t capDmvrJobs;
   bool mapPerModel;
   int distOob;              // OOB rule of the DIST batches (mmgpu_set_dist_oob_mode)
   MmStage stage;            // staging of the synchronous entry points
@@ -411,6 +415,8 @@ extern "C" void mmgpu_destroy(mmgpu_ctx* ctx)
   if (ctx->prepStream) cudaStreamDestroy(ctx->prepStream);
   cudaFree(ctx->dSubpus);
   cudaFree(ctx->dDmvrItems);
+  cudaFree(ctx->dSubpusC);
+  cudaFree(ctx->dDmvrJobs);
   cudaFree(ctx->dJobs);
   cudaFree(ctx->dJobItems);
   for (int c = 0; c < 3; ++c) cudaFree(ctx->dPic[c]);
@@ -770,17 +776,22 @@ static int ensureCap(mmgpu_ctx* ctx, T** p, size_t* cap, size_t need)
 
 // anyMultiple: MC entry points take every size that is a multiple of the sub-block (the encoder's RD search also predicts
 // 12/24/48-wide blocks); the batch / Hadamard work lists index with power-of-two arithmetic
-static int checkBlockShape(mmgpu_ctx* ctx, int comp, int fmt, int x, int y, int w, int h, bool anyMultiple = false)
+static int badBlock(mmgpu_ctx* ctx, const char* what, int comp, int fmt, int x, int y, int w, int h)
 {
-  const int sx = scaleX(comp, fmt), sy = scaleY(comp, fmt);
-  const int sbw = 4 >> sx, sbh = 4 >> sy;
   char dims[96];
   snprintf(dims, sizeof(dims), " (comp %d fmt %d: %dx%d at %d,%d)", comp, fmt, w, h, x, y);
+  return fail(ctx, MMGPU_ERR_ARG, std::string(what) + dims);
+}
+static int checkBlockShape(mmgpu_ctx* ctx, int comp, int fmt, int x, int y, int w, int h, bool anyMultiple = false)
+{
+  // runs per block of every batch: nothing but comparisons on the good path
+  const int sx = scaleX(comp, fmt), sy = scaleY(comp, fmt);
+  const int sbw = 4 >> sx, sbh = 4 >> sy;
   if (w < sbw || h < sbh || (w % sbw) || (h % sbh) || (x % sbw) || (y % sbh) || x < 0 || y < 0)
-    return fail(ctx, MMGPU_ERR_ARG, std::string("block must be aligned to the sub-block grid") + dims);
+    return badBlock(ctx, "block must be aligned to the sub-block grid", comp, fmt, x, y, w, h);
   if ((!anyMultiple && (!pow2(w) || !pow2(h))) || (w << sx) > 128 || (h << sy) > 128)
-    return fail(ctx, MMGPU_ERR_ARG, std::string("block size must be a power of two <= 128") + dims);
-  if (((x + w) << sx) > ctx->cfg.pic_w || ((y + h) << sy) > ctx->cfg.pic_h) return fail(ctx, MMGPU_ERR_ARG, std::string("block outside the picture") + dims);
+    return badBlock(ctx, "block size must be a power of two <= 128", comp, fmt, x, y, w, h);
+  if (((x + w) << sx) > ctx->cfg.pic_w || ((y + h) << sy) > ctx->cfg.pic_h) return badBlock(ctx, "block outside the picture", comp, fmt, x, y, w, h);
   return MMGPU_OK;
 }
 
@@ -1369,6 +1380,115 @@ static int32_t divForMaxq7(int64_t N, int64_t D)   // InterPrediction.cpp:1958-1
   q = (q << 1);
   if (N >= (D >> 1)) q++;
   return sign ? -q : q;
+}
+
+// ---- f4: classic DMVR (xProcessDMVR) ----------------------------------------------------------------------
+// window [x, x + w) x [y, y + h) of component comp of a slot inside its padded plane?
+static bool windowInside(mmgpu_ctx* ctx, int comp, int x, int y, int w, int h)
+{
+  const int sx = scaleX(comp, ctx->cfg.chroma_fmt), sy = scaleY(comp, ctx->cfg.chroma_fmt);
+  const int mx = ctx->cfg.margin >> sx, my = ctx->cfg.margin >> sy, pw = ctx->cfg.pic_w >> sx, ph = ctx->cfg.pic_h >> sy;
+  return x >= -mx && y >= -my && x + w <= pw + mx && y + h <= ph + my;
+}
+
+extern "C" int mmgpu_dmvr_classic_costs(mmgpu_ctx* ctx, int n_subpus, const mmgpu_dmvr_classic_subpu* subpus, uint64_t* costs)
+{
+  if (!ctx || !subpus || !costs || n_subpus <= 0) return MMGPU_ERR_ARG;
+  for (int i = 0; i < n_subpus; ++i)
+  {
+    const mmgpu_dmvr_classic_subpu& s = subpus[i];
+    if ((s.w != 8 && s.w != 16) || (s.h != 8 && s.h != 16)) return fail(ctx, MMGPU_ERR_ARG, "classic DMVR sub-PU must be 8 or 16 wide and high");
+    if (s.ref_slot0 < 0 || s.ref_slot0 >= ctx->cfg.max_refs || !ctx->hRefs[s.ref_slot0].plane00[0] || s.ref_slot1 < 0 ||
+        s.ref_slot1 >= ctx->cfg.max_refs || !ctx->hRefs[s.ref_slot1].plane00[0])
+      return fail(ctx, MMGPU_ERR_STATE, "classic DMVR sub-PU references an unset reference slot");
+    if ((unsigned)s.frac_x0 > 15u || (unsigned)s.frac_y0 > 15u || (unsigned)s.frac_x1 > 15u || (unsigned)s.frac_y1 > 15u)
+      return fail(ctx, MMGPU_ERR_ARG, "classic DMVR: fraction out of range");
+    if (!windowInside(ctx, 0, s.org_x0, s.org_y0, s.w + 7, s.h + 7) || !windowInside(ctx, 0, s.org_x1, s.org_y1, s.w + 7, s.h + 7))
+      return fail(ctx, MMGPU_ERR_ARG, "classic DMVR: prefetch window outside the padded picture (clipMv)");
+  }
+  cudaSetDevice(ctx->cfg.device);
+  int rc;
+  if ((rc = ensureCap(ctx, &ctx->dSubpusC, &ctx->capSubpusC, (size_t)n_subpus))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dDist, &ctx->capDist, (size_t)n_subpus * 25))) return rc;
+  CU(cudaMemcpyAsync(ctx->dSubpusC, subpus, sizeof(mmgpu_dmvr_classic_subpu) * n_subpus, cudaMemcpyHostToDevice, ctx->stream));
+  mmk_dmvr_classic(ctx->stream, ctx->dRefs, ctx->dSubpusC, n_subpus, ctx->cfg.bit_depth, ctx->dDist);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(costs, ctx->dDist, sizeof(uint64_t) * 25 * n_subpus, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+static int checkDmvrJob(mmgpu_ctx* ctx, const mmgpu_dmvr_mc_job& j, int dst_samples)
+{
+  const int ncomp = numComps(ctx);
+  if (j.comp < 0 || j.comp >= ncomp) return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: bad component");
+  if (j.ref_slot < 0 || j.ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[j.ref_slot].plane00[j.comp])
+    return fail(ctx, MMGPU_ERR_STATE, "dmvr_final_mc: unset reference slot");
+  const int taps = j.comp == 0 ? 8 : 4;
+  if (j.w < 1 || j.h < 1 || j.w > 16 || j.h > 16) return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: block must be 1..16 wide and high");
+  if (j.pad < 0 || j.pad > 2 || abs(j.dint_x) > j.pad || abs(j.dint_y) > j.pad) return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: bad pad / deltaIntMv");
+  const int nph = j.comp == 0 ? 16 : 32;
+  if (j.frac_x < 0 || j.frac_x >= nph || j.frac_y < 0 || j.frac_y >= nph) return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: fraction out of range");
+  if (j.bio && j.comp != 0) return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: bio is a luma flag");
+  if (!windowInside(ctx, j.comp, j.org_x, j.org_y, j.w + taps - 1, j.h + taps - 1))
+    return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: prefetch window outside the padded picture (clipMv)");
+  const long last = j.bio ? (long)j.dst_offset + (long)(j.w + 4) * (j.h + 4) : (long)j.dst_offset + (long)(j.h - 1) * j.dst_stride + j.w;
+  if (j.dst_offset < 0 || (!j.bio && j.dst_stride < j.w) || last > dst_samples) return fail(ctx, MMGPU_ERR_ARG, "dmvr_final_mc: output outside dst");
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_dmvr_final_mc(mmgpu_ctx* ctx, int n_jobs, const mmgpu_dmvr_mc_job* jobs, int16_t* dst, int dst_samples)
+{
+  if (!ctx || !jobs || !dst || n_jobs <= 0 || dst_samples <= 0) return MMGPU_ERR_ARG;
+  int rc;
+  for (int i = 0; i < n_jobs; ++i)
+    if ((rc = checkDmvrJob(ctx, jobs[i], dst_samples))) return rc;
+  cudaSetDevice(ctx->cfg.device);
+  if ((rc = ensureCap(ctx, &ctx->dDmvrJobs, &ctx->capDmvrJobs, (size_t)n_jobs))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)dst_samples + 64))) return rc;
+  CU(cudaMemcpyAsync(ctx->dDmvrJobs, jobs, sizeof(mmgpu_dmvr_mc_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->dTmp, 0, sizeof(int16_t) * dst_samples, ctx->stream));
+  mmk_dmvr_final_mc(ctx->stream, ctx->dRefs, ctx->fir, ctx->dDmvrJobs, n_jobs, 0, 0, 0, ctx->dTmp);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(dst, ctx->dTmp, sizeof(int16_t) * dst_samples, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MMGPU_OK;
+}
+
+extern "C" int mmgpu_mc_alt_hpel(mmgpu_ctx* ctx, int ref_slot, int x, int y, int w, int h, mmgpu_mv mv, int bi, int clp_min, int clp_max,
+                                 int16_t* dst, int dst_stride)
+{
+  if (!ctx || !dst || dst_stride < w) return MMGPU_ERR_ARG;
+  if (ref_slot < 0 || ref_slot >= ctx->cfg.max_refs || !ctx->hRefs[ref_slot].plane00[0]) return fail(ctx, MMGPU_ERR_STATE, "reference slot not set");
+  int rc = checkBlockShape(ctx, 0, 0, x, y, w, h, true);
+  if (rc) return rc;
+  // 16x16 tiles, each its own un-padded window: identical to reading the picture
+  std::vector<mmgpu_dmvr_mc_job> jobs;
+  for (int ty = 0; ty < h; ty += 16)
+    for (int tx = 0; tx < w; tx += 16)
+    {
+      mmgpu_dmvr_mc_job j = {};
+      j.comp = 0; j.ref_slot = ref_slot;
+      j.org_x = x + tx + (mv.hor >> 4) - 3; j.org_y = y + ty + (mv.ver >> 4) - 3;
+      j.w = std::min(16, w - tx); j.h = std::min(16, h - ty);
+      j.frac_x = mv.hor & 15; j.frac_y = mv.ver & 15;
+      j.alt_hpel = 1;
+      j.dst_offset = ty * w + tx; j.dst_stride = w;
+      if ((rc = checkDmvrJob(ctx, j, w * h))) return rc;
+      jobs.push_back(j);
+    }
+  cudaSetDevice(ctx->cfg.device);
+  if ((rc = ensureCap(ctx, &ctx->dDmvrJobs, &ctx->capDmvrJobs, jobs.size()))) return rc;
+  if ((rc = ensureCap(ctx, &ctx->dTmp, &ctx->capTmp, (size_t)w * h + 64))) return rc;
+  CU(cudaMemcpyAsync(ctx->dDmvrJobs, jobs.data(), sizeof(mmgpu_dmvr_mc_job) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  mmk_dmvr_final_mc(ctx->stream, ctx->dRefs, ctx->fir, ctx->dDmvrJobs, (int)jobs.size(), bi ? 0 : 1, clp_min, clp_max, ctx->dTmp);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2DAsync(dst, sizeof(int16_t) * dst_stride, ctx->dTmp, sizeof(int16_t) * w, sizeof(int16_t) * w, h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // jobs (host vector) must outlive the upload
+  return MMGPU_OK;
 }
 
 extern "C" int mmgpu_dmvr_decide(const uint64_t costs25[25], int w, int h, int32_t delta_mv[2], uint64_t* min_cost)
