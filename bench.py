@@ -373,6 +373,10 @@ def main():
         return plans[key]
 
     exchange = shard.PictureExchange(xbytes, dev) if N > 1 else None
+    pull = exchange is not None and exchange.mode == "pull"
+    pull_ctas = int(os.environ.get("MMGPU_PULL_CTAS", "24"))
+    if exchange is not None and os.environ.get("MMGPU_EXCHANGE", "nccl").lower() == "pull" and (not pull or padded_x):
+        raise SystemExit("MMGPU_EXCHANGE=pull needs symmetric memory and the un-padded exchange (%s)" % getattr(exchange, "err", "padded form selected"))
 
     def prefetch(s):
         """Rank f owns frame f of step s: it copies its picture into the landing buffer and NCCL-broadcasts it.
@@ -380,6 +384,16 @@ def main():
         if N == 1:
             return
         p = s % 2
+        if pull:
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(freed[p])
+                exchange.publish(p, pool_unp[(s * N + rank) % POOL])
+                gpu.pull_refs_unpadded([POOL + p * N + f for f in range(N)], list(range(N)),
+                                       [[exchange.peer_ptr(f, p) + int(uoffs[c]) for c in range(3)] for f in range(N)],
+                                       [[w_ for w_, _ in uw]] * N, max_ctas=pull_ctas, stream=comm_stream.cuda_stream, keep=exchange)
+                exchange.done()
+                ready[p].record(comm_stream)
+            return
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(freed[p])
             exchange.allgather(comm[p], (pool_ref if padded_x else pool_unp)[(s * N + rank) % POOL])
@@ -491,7 +505,7 @@ def main():
     prefetch(0)
     if N > 1:
         barrier()
-        for f in range(N):
+        for f in range(N if not pull else 0):    # pull mode has no landing buffer: the oracle check of step 0 below covers every exchanged picture
             if not torch.equal(comm[0][f * xbytes:(f + 1) * xbytes], (pool_ref if padded_x else pool_unp)[f % POOL]):
                 raise SystemExit("bench self-check failed: picture %d arrived corrupted on rank %d (%s)" % (f, rank, exchange.mode))
     device_step(0)
@@ -592,8 +606,12 @@ def main():
             "config": bench_config(N, int(len(blocks)), int(n_cands), samples_all,
                                    ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each%s, one owner rank each) reach every GPU %s, "
                                     "prefetched one step ahead on a second stream"
-                                    % (N, N, xbytes / 1e6, " with margins" if padded_x else " un-padded; margins rebuilt on arrival by one k_pad_planes launch", "by copy-engine pulls from symmetric (peer) memory over NVLink"
-                                       if exchange.mode == "p2p" else "by one ncclAllGather")) if N > 1 else "1 gpu"),
+                                    % (N, N, xbytes / 1e6, " with margins" if padded_x else
+                                       (" un-padded; pulled row by row from the owners' symmetric memory by %d persistent CTAs that write the padded planes directly (k_pull_rows + k_pad_tb)" % pull_ctas
+                                        if pull else " un-padded; margins rebuilt on arrival by one k_pad_planes launch"),
+                                       "by SM loads over NVLink (mmgpu_pull_refs_unpadded)" if pull else
+                                       ("by copy-engine pulls from symmetric (peer) memory over NVLink" if exchange.mode == "p2p" else "by one ncclAllGather")))
+                                   if N > 1 else "1 gpu"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": counts["k_fir"]["dram_bytes"] if counts else None, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
                          "path": {"kernels": "k_map + k_fir<DIST>", "k_map_ms": kmap_avg_ms, "ms": path_ms,

@@ -110,6 +110,15 @@ int mmgpu_set_ref_unpadded_device(mmgpu_ctx* ctx, int slot, int poc, const int16
 int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs, const int16_t* const* d_plane,
                                    const int32_t* stride, int wrap_offset, void* stream);
 
+/* the multi-GPU form of it: d_plane are the OWNERS' un-padded planes in peer memory (NVLink-mapped device addresses, e.g.
+ * torch symmetric memory; the caller's own picture is a local address).  A persistent kernel of max_ctas CTAs pulls every
+ * row once over NVLink and writes it with its left / right margin into the slot's padded plane; a second one replicates the
+ * top / bottom rows locally (Picture::extendPicBorder, Picture.cpp:988-1048; replicate only).  The exchange and the border
+ * extension are one pass over the data; max_ctas is the SM budget it takes from the kernels of the running step.
+ * The caller brackets the call with its own cross-rank barriers (pictures published / pulls finished). */
+int mmgpu_pull_refs_unpadded(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs, const int16_t* const* d_plane,
+                             const int32_t* stride, int max_ctas, void* stream);
+
 /* ---- geodesic epipole: GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46) ------------ */
 void mmgpu_rodrigues(const float epipole[3], float R[9]);          /* host helper, row-major R */
 float mmgpu_fixed_to_float(int32_t fixed, int32_t precision);     /* Coordinate.cpp:75-77 (EPIPOLE_PRECISION_FIXED=24) */

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -41,6 +43,7 @@ struct State
   // ME
   bool useHadamard = false;
   Distortion pending = 0;
+  Distortion (*cpuDistFunc)(const DistParam&) = nullptr;
   bool pendingValid = false;
   std::unordered_map<uint64_t, Distortion> ahead;
   // signature of the search the look-ahead table belongs to
@@ -261,6 +264,57 @@ bool verifying()
   static const bool on = getenv("MMGPU_VERIFY") && getenv("MMGPU_VERIFY")[0] == '1';
   return on;
 }
+namespace
+{
+bool g_inVerify = false;
+std::vector<Pel> g_verifySaved;
+uint64_t g_nVerMcCalls = 0, g_nVerMcSamples = 0, g_nVerMv = 0, g_nVerDist = 0;
+}
+bool inVerify() { return g_inVerify; }
+void setInVerify(bool on) { g_inVerify = on; }
+void verifySave(const Pel* buf, int stride, int w, int h)
+{
+  g_verifySaved.resize((size_t)w * h);
+  for (int y = 0; y < h; ++y) memcpy(&g_verifySaved[(size_t)y * w], buf + (size_t)y * stride, sizeof(Pel) * w);
+}
+void verifyCompare(const Pel* buf, int stride, int w, int h, const char* what)
+{
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      if (buf[(size_t)y * stride + x] != g_verifySaved[(size_t)y * w + x])
+      {
+        fprintf(stderr, "[mmgpu] VERIFY: %s %dx%d at (%d,%d): device %d, reference %d\n", what, w, h, x, y, (int)g_verifySaved[(size_t)y * w + x],
+                (int)buf[(size_t)y * stride + x]);
+        THROW("mmglue: MMGPU_VERIFY found a prediction sample that differs from the reference's own");
+      }
+  g_nVerMcCalls++;
+  g_nVerMcSamples += (uint64_t)w * h;
+}
+void verifyMv(const Mv& a, const Mv& b)
+{
+  if (a.hor != b.hor || a.ver != b.ver)
+  {
+    fprintf(stderr, "[mmgpu] VERIFY: MM-MVP conversion: library (%d,%d), reference (%d,%d)\n", a.hor, a.ver, b.hor, b.ver);
+    THROW("mmglue: MMGPU_VERIFY found an MM-MVP conversion that differs from the reference's own");
+  }
+  g_nVerMv++;
+}
+void meVerify(const DistParam& dp)
+{
+  CHECK(!g.pendingValid || !g.cpuDistFunc, "mmglue: meVerify without a pending distortion");
+  DistParam c = dp;
+  c.distFunc = g.cpuDistFunc;
+  c.maximumDistortionForEarlyExit = std::numeric_limits<Distortion>::max();   // the device always returns the complete sum
+  const Distortion ref = g.cpuDistFunc(c);
+  if (ref != g.pending)
+  {
+    fprintf(stderr, "[mmgpu] VERIFY: candidate distortion (%s, %dx%d): device %llu, reference %llu\n", g.useHadamard ? "HAD" : "SAD", (int)dp.org.width,
+            (int)dp.org.height, (unsigned long long)g.pending, (unsigned long long)ref);
+    THROW("mmglue: MMGPU_VERIFY found a candidate distortion that differs from the reference's own");
+  }
+  g_nVerDist++;
+}
+
 void dmvrBegin(int dx, int dy)
 {
   g_dmvrSubs.clear();
@@ -372,6 +426,7 @@ void meSetup(DistParam& dp, bool useHadamard)
   g.ahead.clear();
   g.sigOrg = nullptr;
   g.pendingValid = false;
+  if (dp.distFunc != pendingDist) g.cpuDistFunc = dp.distFunc;   // what RdCost::setDistParam selected (MMGPU_VERIFY)
   dp.distFunc = pendingDist;
 }
 
@@ -594,6 +649,10 @@ void printStats()
   fprintf(stderr, "[mmgpu] classic MC calls %llu | MM-MVP conversions %llu\n", (unsigned long long)g.nMcClassic, (unsigned long long)g.nMvp);
   fprintf(stderr, "[mmgpu] classic DMVR: %llu sub-PU searches, %llu final-MC jobs%s\n", (unsigned long long)g_nDmvrSubPus, (unsigned long long)g_nDmvrFinal,
           verifying() ? (" | VERIFY: " + std::to_string(g_nDmvrVerified) + " comparisons against the reference's own code, all equal").c_str() : "");
+  if (verifying())
+    fprintf(stderr, "[mmgpu] VERIFY (device vs the reference's own code in this process, all equal): %llu MC calls / %llu samples, %llu candidate distortions, "
+                    "%llu MM-MVP conversions\n", (unsigned long long)g_nVerMcCalls, (unsigned long long)g_nVerMcSamples, (unsigned long long)g_nVerDist,
+            (unsigned long long)g_nVerMv);
   fprintf(stderr, "[mmgpu] MC calls %llu | ME batches %llu, candidates %llu (%.1f per batch), look-ahead hits %llu, single evaluations %llu | "
                   "reference uploads %llu | kernels launched %llu\n",
           (unsigned long long)g.nMc, (unsigned long long)g.nMeBatches, (unsigned long long)g.nMeCands,

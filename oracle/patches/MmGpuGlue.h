@@ -47,10 +47,20 @@ void predInterBlkClassicBdof(const Position& blockPos, int width, int height, co
 void predInterBlkClassicAltHpel(const Position& blockPos, int width, int height, const Picture* refPic, bool wrapRef, const Mv& mv, bool bi,
                                 const ClpRng& clpRng, PelBuf& dstBuf);
 
+// ---- MMGPU_VERIFY=1: every hooked call also runs the reference's own code in the same process (the hook re-enters the
+//      reference function with inVerify() set, so the second pass takes the CPU path) and the results are compared value by
+//      value; the app stops at the first difference and the stats line reports how many values were compared.
+bool verifying();
+bool inVerify();
+void setInVerify(bool on);
+void verifySave(const Pel* buf, int stride, int w, int h);
+void verifyCompare(const Pel* buf, int stride, int w, int h, const char* what);
+void verifyMv(const Mv& viaLibrary, const Mv& viaReference);
+void meVerify(const DistParam& dp);   // distortion of the last meEval() against the reference's distFunc on its own prediction
+
 // ---- classic DMVR, InterPrediction::xProcessDMVR (InterPrediction.cpp:2239-2439).  MMGPU_DMVR=0 keeps it on the reference's code;
 //      MMGPU_VERIFY=1 additionally runs the reference's own code next to the device and stops at the first difference.
 bool dmvrOnGpu();
-bool verifying();
 struct DmvrList
 {
   const Picture* refPic;

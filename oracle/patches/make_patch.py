@@ -30,10 +30,20 @@ def edit_mvreprojection(t):
     # MM-MVP candidate conversion through the library (host code of libmmgpu.so, 8f-1)
     t = sub(t, """                                                    const Position &currentBlockPos, const Size &currentBlockSize) const {
   if (motionVectorOrig.hor == 0 && motionVectorOrig.ver == 0) {""", """                                                    const Position &currentBlockPos, const Size &currentBlockSize) const {
-  if( mmglue::enabled() && mmglue::mvpOnLibrary() )
+  if( mmglue::enabled() && !mmglue::inVerify() && mmglue::mvpOnLibrary() )
   {
-    return mmglue::mvpConvert( position, motionVectorOrig, motionModelIDOrig, motionModelIDDesired, shiftHor, shiftVer, curPOCOrig, refPOCOrig,
-                               curPOCDesired, refPOCDesired, candidateBlockPos, candidateBlockSize, currentBlockPos, currentBlockSize );
+    const Mv viaLibrary = mmglue::mvpConvert( position, motionVectorOrig, motionModelIDOrig, motionModelIDDesired, shiftHor, shiftVer, curPOCOrig, refPOCOrig,
+                                              curPOCDesired, refPOCDesired, candidateBlockPos, candidateBlockSize, currentBlockPos, currentBlockSize );
+    if( mmglue::verifying() )
+    {
+      mmglue::setInVerify( true );
+      const Mv viaReference = motionVectorInDesiredMotionModel( position, motionVectorOrig, motionModelIDOrig, motionModelIDDesired, shiftHor, shiftVer, curPOCOrig,
+                                                                refPOCOrig, curPOCDesired, refPOCDesired, candidateBlockPos, candidateBlockSize, currentBlockPos,
+                                                                currentBlockSize );
+      mmglue::setInVerify( false );
+      mmglue::verifyMv( viaLibrary, viaReference );
+    }
+    return viaLibrary;
   }
   if (motionVectorOrig.hor == 0 && motionVectorOrig.ver == 0) {""")
     return t
@@ -50,11 +60,20 @@ def edit_interprediction(t):
     blockPos, blockSize, mv, motionModel, compID, chFmt, pu.cs->slice->getPOC(), refPic->getPOC());
 """, """  const Position blockPos = pu.blocks[compID].pos();
   const Size blockSize = pu.blocks[compID].size();
-  if( mmglue::enabled() && !srcPadBuf && !bilinearMC )
+  if( mmglue::enabled() && !mmglue::inVerify() && !srcPadBuf && !bilinearMC )
   {
     // GPU path: mapping + interpolation of the whole block in one call (libmmgpu.so, mmgpu_mc)
     mmglue::predInterBlkMM( compID, chFmt, blockPos, blockSize, refPic, wrapRef, mv, motionModel, bi, clpRng, pu.cs->slice->getPOC(),
                             dstPic.bufs[compID] );
+    if( mmglue::verifying() )
+    {
+      // MMGPU_VERIFY=1: the reference's own code on the same call, compared sample by sample
+      mmglue::verifySave( dstPic.bufs[compID].buf, (int) dstPic.bufs[compID].stride, (int) blockSize.width, (int) blockSize.height );
+      mmglue::setInVerify( true );
+      xPredInterBlkMM( compID, pu, refPic, _mv, dstPic, motionModel, bi, clpRng, bdofApplied, isIBC, scalingRation, bilinearMC, srcPadBuf, srcPadStride );
+      mmglue::setInVerify( false );
+      mmglue::verifyCompare( dstPic.bufs[compID].buf, (int) dstPic.bufs[compID].stride, (int) blockSize.width, (int) blockSize.height, "xPredInterBlkMM" );
+    }
     return;
   }
 #if INTERPRED_PROFILING
@@ -73,20 +92,38 @@ def edit_interprediction(t):
       Position offset = pu.blocks[compID].pos().offset(mv.getHor() >> shiftHor, mv.getVer() >> shiftVer);""", """    PelBuf & dstBuf = dstPic.bufs[compID];
     unsigned width  = dstBuf.width;
     unsigned height = dstBuf.height;
-    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && !useAltHpelIf
+    if( mmglue::enabled() && !mmglue::inVerify() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && !useAltHpelIf
         && width >= 4 && height >= 4 && ( width & ( width - 1 ) ) == 0 && ( height & ( height - 1 ) ) == 0
         && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
     {
       mmglue::predInterBlkClassic( compID, chFmt, pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, bi, clpRng, dstBuf );
+      if( mmglue::verifying() )
+      {
+        mmglue::verifySave( dstBuf.buf, (int) dstBuf.stride, (int) width, (int) height );
+        mmglue::setInVerify( true );
+        xPredInterBlk( compID, pu, refPic, _mv, dstPic, bi, clpRng, bioApplied, isIBC, scalingRatio, dmvrWidth, dmvrHeight, bilinearMC, srcPadBuf, srcPadStride );
+        mmglue::setInVerify( false );
+        mmglue::verifyCompare( dstBuf.buf, (int) dstBuf.stride, (int) width, (int) height, "xPredInterBlk" );
+      }
       return;
     }
-    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && bioApplied && compID == COMPONENT_Y && bi && !bilinearMC && !dmvrWidth && !srcPadBuf
+    if( mmglue::enabled() && !mmglue::inVerify() && mmglue::classicOnGpu() && !isIBC && bioApplied && compID == COMPONENT_Y && bi && !bilinearMC && !dmvrWidth && !srcPadBuf
         && !useAltHpelIf && width >= 8 && height >= 8 && ( width & ( width - 1 ) ) == 0 && ( height & ( height - 1 ) ) == 0
         && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
     {
       // prediction + BDOF border fetch into the work buffer, as the code below does
       mmglue::predInterBlkClassicBdof( pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, clpRng,
                                        m_filteredBlockTmp[2 + m_iRefListIdx][compID] );
+      if( mmglue::verifying() )
+      {
+        // the ring box: rows 1 .. h+2, columns 1 .. w+2 of the (w + 4)-stride work buffer
+        Pel* box = m_filteredBlockTmp[2 + m_iRefListIdx][compID] + ( width + 4 ) + 1;
+        mmglue::verifySave( box, (int) width + 4, (int) width + 2, (int) height + 2 );
+        mmglue::setInVerify( true );
+        xPredInterBlk( compID, pu, refPic, _mv, dstPic, bi, clpRng, bioApplied, isIBC, scalingRatio, dmvrWidth, dmvrHeight, bilinearMC, srcPadBuf, srcPadStride );
+        mmglue::setInVerify( false );
+        mmglue::verifyCompare( box, (int) width + 4, (int) width + 2, (int) height + 2, "xPredInterBlk (BDOF)" );
+      }
       return;
     }
 
@@ -94,15 +131,23 @@ def edit_interprediction(t):
     {
       Position offset = pu.blocks[compID].pos().offset(mv.getHor() >> shiftHor, mv.getVer() >> shiftVer);""")
     # luma with the alternative half-pel filter (pu.cu->imv == IMV_HPEL): own entry point; chroma ignores the flag
-    t = sub(t, """    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && !useAltHpelIf
-        && width >= 4""", """    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && useAltHpelIf
+    t = sub(t, """    if( mmglue::enabled() && !mmglue::inVerify() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && !useAltHpelIf
+        && width >= 4""", """    if( mmglue::enabled() && !mmglue::inVerify() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf && useAltHpelIf
         && compID == COMPONENT_Y && width >= 4 && height >= 4 && ( width % 4 ) == 0 && ( height % 4 ) == 0
         && width == pu.blocks[compID].width && height == pu.blocks[compID].height )
     {
       mmglue::predInterBlkClassicAltHpel( pu.blocks[compID].pos(), int( width ), int( height ), refPic, wrapRef, mv, bi, clpRng, dstBuf );
+      if( mmglue::verifying() )
+      {
+        mmglue::verifySave( dstBuf.buf, (int) dstBuf.stride, (int) width, (int) height );
+        mmglue::setInVerify( true );
+        xPredInterBlk( compID, pu, refPic, _mv, dstPic, bi, clpRng, bioApplied, isIBC, scalingRatio, dmvrWidth, dmvrHeight, bilinearMC, srcPadBuf, srcPadStride );
+        mmglue::setInVerify( false );
+        mmglue::verifyCompare( dstBuf.buf, (int) dstBuf.stride, (int) width, (int) height, "xPredInterBlk (alternative half-pel filter)" );
+      }
       return;
     }
-    if( mmglue::enabled() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf
+    if( mmglue::enabled() && !mmglue::inVerify() && mmglue::classicOnGpu() && !isIBC && !bioApplied && !bilinearMC && !dmvrWidth && !srcPadBuf
         && ( !useAltHpelIf || compID != COMPONENT_Y ) && width >= 4""")
     # ---- classic DMVR (xProcessDMVR): integer search of all sub-PUs in one batch, final MC of a sub-PU in one batch
     t = sub(t, """    if (*(pSADsArray + sadOffset) == MAX_UINT64)
@@ -535,6 +580,12 @@ def edit_intersearch(t):
     {
       mmglue::meSetup( m_cDistParam, m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD() );
       mmglue::meEval( %s, m_cDistParam, rcMvBaseI, MV_PRECISION_INT );
+      if( mmglue::verifying() )
+      {
+        xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, rcMvBaseI, MV_PRECISION_INT,
+                                     m_tmpMMStorage, cStruct.motionModel, m_lumaClpRng, cStruct.curPOC, cStruct.refPOC);
+        mmglue::meVerify( m_cDistParam );
+      }
     }
     else
     xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, rcMvBaseI, MV_PRECISION_INT,
@@ -574,6 +625,12 @@ def edit_intersearch(t):
     if( mmglue::enabled() )
     {
       mmglue::meEval( %s, m_cDistParam, cMvTest, refinementPrecision );
+      if( mmglue::verifying() )
+      {
+        xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, cMvTest, refinementPrecision,
+                                     m_tmpMMStorage, cStruct.motionModel, m_lumaClpRng, cStruct.curPOC, cStruct.refPOC);
+        mmglue::meVerify( m_cDistParam );
+      }
     }
     else
     xMVReprojectionInterpolation(cStruct.blkPos, cStruct.blkSize, *cStruct.pcRefBuf, cMvTest, refinementPrecision,
@@ -604,6 +661,11 @@ def edit_intersearch(t):
 """, """  else if( mmglue::enabled() )
   {
     mmglue::meEval( %s, m_cDistParam, rMv, mvPrec );
+    if( mmglue::verifying() )
+    {
+      xMVReprojectionInterpolation(rcStruct.blkPos, rcStruct.blkSize, *rcStruct.pcRefBuf, rMv, mvPrec, m_tmpMMStorage, rcStruct.motionModel, m_lumaClpRng, rcStruct.curPOC, rcStruct.refPOC);
+      mmglue::meVerify( m_cDistParam );
+    }
   }
   else
   {
@@ -666,7 +728,11 @@ def edit_intersearch(t):
     if( mmgpuFrac )
     {
       const Mv absQ = mmglue::classicFracMv( Mv( horVal, verVal ) );
-      if( mmglue::enabled() ) mmglue::meEval( mmglue::classicFracBlock(), m_cDistParam, absQ, MV_PRECISION_QUARTER );
+      if( mmglue::enabled() )
+      {
+        mmglue::meEval( mmglue::classicFracBlock(), m_cDistParam, absQ, MV_PRECISION_QUARTER );
+        if( mmglue::verifying() ) mmglue::meVerify( m_cDistParam );   // cur.buf = piRefPos: the reference's up-sampled view
+      }
       else mmglue::meDumpCandidate( mmglue::classicFracBlock(), absQ, MV_PRECISION_QUARTER );
     }
     dist                   = m_cDistParam.distFunc(m_cDistParam);

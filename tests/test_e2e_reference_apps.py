@@ -234,3 +234,27 @@ def test_decoder_app_random_access_verify_mode(tmp_path):
     n_sub = int(line[0].split("classic DMVR:")[1].split()[0])
     if n_sub:
         assert "VERIFY:" in line[0] and int(line[0].split("VERIFY:")[1].split()[0]) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("MMGPU_E2E_VERIFY_ENCODE", "0") != "1",
+                    reason="a CPU-speed encode: MMGPU_E2E_VERIFY_ENCODE=1 (run once per round, log under profiles/)")
+def test_encoder_app_verify_mode_every_hooked_call_against_the_reference(tmp_path):
+    """MMGPU_VERIFY=1 on a whole low-delay encode: every hooked call (xPredInterBlkMM, classic xPredInterBlk incl. BDOF ring and
+    alternative half-pel filter, every motion-search candidate's distortion, every MM-MVP conversion, classic DMVR) is computed on
+    the device AND by the reference's own code in the same process and compared value by value; the first difference aborts."""
+    _, enc, cfg = _apps()
+    yuv = _yuv(str(tmp_path))
+    bit = str(tmp_path / "enc.bin")
+    env = dict(os.environ, MMGPU_VERIFY="1")
+    r = subprocess.run([enc, "-c", cfg, "-i", yuv, "-b", bit] + ENC_ARGS, capture_output=True, text=True, timeout=3000, env=env)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-3000:]
+    lines = [l for l in log.splitlines() if l.startswith("[mmgpu]")]
+    print("\n".join(lines))
+    ver = [l for l in lines if "VERIFY (device vs" in l]
+    assert ver, log[-2000:]
+    n_mc = int(ver[0].split("all equal):")[1].split()[0])
+    n_dist = int(ver[0].split("samples,")[1].split()[0])
+    assert n_mc > 10000 and n_dist > 100000, ver[0]
+    assert open(bit, "rb").read() == open(os.path.join(GOLD, "mm_ldp_q37.bin"), "rb").read(), log[-3000:]

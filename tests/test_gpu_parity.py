@@ -775,6 +775,19 @@ def test_device_side_unpadded_registration_single_and_batched(env):
                                [[t.shape[1] for t in un]] * 2, keep=(un, other))
     assert np.array_equal(g.me_batch(b2, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)
     assert not np.array_equal(g.me_batch(b1, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)      # slot 1 now holds the other picture
+    # the multi-GPU form (mmgpu_pull_refs_unpadded: persistent pull kernels, here from local addresses): same planes, margins
+    # included -- distortions at the picture border and MC deep inside every margin
+    for ctas in (3, 24):
+        g.pull_refs_unpadded([2, 1], [6, 7], [[t.data_ptr() for t in other], [t.data_ptr() for t in un]], [[t.shape[1] for t in un]] * 2,
+                             max_ctas=ctas, keep=(un, other))
+        assert np.array_equal(g.me_batch(b1, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)
+        assert not np.array_equal(g.me_batch(b2, mvs, mv_prec_shift=prec, dist=mm.DIST_SAD), exp)
+        for (x, y, mv) in [(0, 0, (-4000, -4100)), (W - 64, 0, (4000, -4000)), (0, H - 64, (-3900, 4000)), (W - 64, H - 64, (4000, 4000)),
+                           (1024, 0, (5, -4200)), (0, 512, (-4200, 7))]:
+            for comp, pos, size in ((0, (x, y), (64, 64)), (1, (x // 2, y // 2), (32, 32)), (2, (x // 2, y // 2), (32, 32))):
+                assert np.array_equal(g.mc(0, comp, 1, pos, size, mv, 0), g.mc(1, comp, 1, pos, size, mv, 0)), (ctas, x, y, mv, comp)
+        g.set_refs_unpadded_device([2, 1], [6, 7], [[t.data_ptr() for t in un], [t.data_ptr() for t in other]], [[t.shape[1] for t in un]] * 2,
+                                   keep=(un, other))
     # wrapped border: batched device padding == host-side extendWrapBorder of the oracle
     wr = []
     for p in ref:

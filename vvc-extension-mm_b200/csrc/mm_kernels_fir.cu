@@ -260,6 +260,91 @@ __global__ void __launch_bounds__(256) k_pad_planes(MmPadJobs J)
   *reinterpret_cast<uint4*>(drow) = v;
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_pull_rows / k_pad_tb: the multi-GPU reference-picture exchange fused with the border extension.  The source planes are the
+// OWNERS' un-padded pictures in peer memory (NVLink / NVSwitch mapped addresses; the rank's own picture is a local address):
+// each source row crosses NVLink exactly once, as 16-byte loads of a few persistent CTAs (gridDim.x is the SM budget of the
+// exchange: the kernels of the current step keep the other SMs), and is written into the slot's padded plane together with its
+// left / right margin (Picture::extendPicBorder, replicate).  One warp per (plane, row): 8 loads in flight per lane.  k_pad_tb then
+// replicates the first / last padded row into the top / bottom margins from local memory.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 mm_ld_peer(const uint4* p)
+{
+  uint4 v;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(512) k_pull_rows(MmPadJobs J, int nPlanes, int totalRows)
+{
+  const int lane = threadIdx.x & 31;
+  const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+  for (int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < totalRows; unit += warpsPerGrid)
+  {
+    int k = 0, y = unit;
+    while (k < nPlanes - 1 && y >= J.p[k].h) { y -= J.p[k].h; ++k; }
+    const MmPadPlane& p = J.p[k];
+    const int G = p.w >> 3;
+    const uint4* srow = reinterpret_cast<const uint4*>(p.src + (long)y * p.srcStride);
+    int16_t* drow = p.dst00 + (long)y * p.dstStride;
+    uint32_t first = 0, last = 0;
+    for (int base = 0; base < G; base += 256)
+    {
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+      {
+        const int g = base + lane + 32 * i;
+        if (g < G) v[i] = mm_ld_peer(srow + g);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+      {
+        const int g = base + lane + 32 * i;
+        if (g < G)
+        {
+          *reinterpret_cast<uint4*>(drow + 8 * g) = v[i];
+          if (g == 0) first = v[i].x & 0xffffu;
+          if (g == G - 1) last = v[i].w >> 16;
+        }
+      }
+    }
+    first = __shfl_sync(0xffffffffu, first, 0);
+    last = __shfl_sync(0xffffffffu, last, (G - 1) & 31);
+    const uint32_t f2 = first | (first << 16), l2 = last | (last << 16);
+    const uint4 fv = make_uint4(f2, f2, f2, f2), lv = make_uint4(l2, l2, l2, l2);
+    const int mg = p.mx >> 3;
+    for (int m = lane; m < mg; m += 32)
+    {
+      *reinterpret_cast<uint4*>(drow - p.mx + 8 * m) = fv;
+      *reinterpret_cast<uint4*>(drow + p.w + 8 * m) = lv;
+    }
+  }
+}
+__global__ void __launch_bounds__(512) k_pad_tb(MmPadJobs J, int nPlanes, int totalRows)
+{
+  const int lane = threadIdx.x & 31;
+  const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+  for (int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < totalRows; unit += warpsPerGrid)
+  {
+    int k = 0, r = unit;
+    while (k < nPlanes - 1 && r >= 2 * J.p[k].my) { r -= 2 * J.p[k].my; ++k; }
+    const MmPadPlane& p = J.p[k];
+    const int Y = (r < p.my) ? (r - p.my) : (p.h + r - p.my);      // margin row
+    const int sy = (r < p.my) ? 0 : (p.h - 1);
+    const int G = (p.w + 2 * p.mx) >> 3;
+    const uint4* srow = reinterpret_cast<const uint4*>(p.dst00 + (long)sy * p.dstStride - p.mx);
+    uint4* drow = reinterpret_cast<uint4*>(p.dst00 + (long)Y * p.dstStride - p.mx);
+    for (int g = lane; g < G; g += 32) drow[g] = srow[g];
+  }
+}
+void mmk_pull_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxCtas)
+{
+  int rows = 0, mrows = 0;
+  for (int k = 0; k < nPlanes; ++k) { rows += J.p[k].h; mrows += 2 * J.p[k].my; }
+  k_pull_rows<<<maxCtas, 512, 0, s>>>(J, nPlanes, rows);
+  k_pad_tb<<<maxCtas, 512, 0, s>>>(J, nPlanes, mrows);
+}
+
 __global__ void k_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                           int shift, int offset, int lo, int hi)
 {

@@ -683,8 +683,8 @@ extern "C" int mmgpu_set_ref_unpadded_device(mmgpu_ctx* ctx, int slot, int poc, 
   return MMGPU_OK;
 }
 
-extern "C" int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs,
-                                              const int16_t* const* d_plane, const int32_t* stride, int wrap_offset, void* stream)
+static int setRefsUnpadded(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs, const int16_t* const* d_plane,
+                           const int32_t* stride, int wrap_offset, void* stream, int pullCtas)
 {
   if (!ctx || !slots || !pocs || !d_plane || !stride || n <= 0) return MMGPU_ERR_ARG;
   const int nc = numComps(ctx);
@@ -730,10 +730,31 @@ extern "C" int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32
     }
     else ctx->hRefs[slot].poc = pocs[i];
   }
-  mmk_pad_planes(st, J, k, maxGroups, maxRows);
-  ctx->launches++;
+  if (pullCtas > 0)
+  {
+    mmk_pull_pad_planes(st, J, k, pullCtas);
+    ctx->launches += 2;
+  }
+  else
+  {
+    mmk_pad_planes(st, J, k, maxGroups, maxRows);
+    ctx->launches++;
+  }
   CU(cudaGetLastError());
   return MMGPU_OK;
+}
+
+extern "C" int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs,
+                                              const int16_t* const* d_plane, const int32_t* stride, int wrap_offset, void* stream)
+{
+  return setRefsUnpadded(ctx, n, slots, pocs, d_plane, stride, wrap_offset, stream, 0);
+}
+
+extern "C" int mmgpu_pull_refs_unpadded(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs, const int16_t* const* d_plane,
+                                        const int32_t* stride, int max_ctas, void* stream)
+{
+  if (max_ctas < 1 || max_ctas > 1024) return ctx ? fail(ctx, MMGPU_ERR_ARG, "max_ctas must be 1..1024") : MMGPU_ERR_ARG;
+  return setRefsUnpadded(ctx, n, slots, pocs, d_plane, stride, 0, stream, max_ctas);
 }
 
 extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9])

@@ -48,19 +48,22 @@ class PictureExchange:
         self.n = int(pic_bytes)
         self.mode = "nccl"
         want = (mode or os.environ.get("MMGPU_EXCHANGE", "nccl")).lower()
-        if want == "p2p" and self.world > 1 and torch.device(device).type == "cuda":
+        if want in ("p2p", "pull") and self.world > 1 and torch.device(device).type == "cuda":
             ok = 1
             try:
                 import torch.distributed._symmetric_memory as symm
-                self.stage = symm.empty(self.n, dtype=torch.uint8, device=device)
+                # pull: two staging pictures (step parity), read in place by the peers' pull kernels
+                self.stage = symm.empty(self.n * (2 if want == "pull" else 1), dtype=torch.uint8, device=device)
                 self.hdl = symm.rendezvous(self.stage, group if group is not None else dist.group.WORLD)
-                self.peers = [self.hdl.get_buffer(r, (self.n,), torch.uint8) for r in range(self.world)]
+                self.peers = [self.hdl.get_buffer(r, (self.stage.numel(),), torch.uint8) for r in range(self.world)]
             except Exception as e:  # noqa: BLE001 -- any failure means: use the NCCL path on every rank
                 self.err = repr(e)
                 ok = 0
             flag = torch.tensor([ok], dtype=torch.int32, device=device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 1:
+            if int(flag.item()) == 1 and want == "pull":
+                self.mode = "pull"
+            elif int(flag.item()) == 1:
                 self.mode = "p2p"
                 # one copy engine moves ~280 GB/s over NVLink (measured: 7 pulls of 12.6 MB in 0.32 ms); several pull
                 # streams keep several engines busy
@@ -84,11 +87,28 @@ class PictureExchange:
             with torch.cuda.stream(st):
                 for step in range(1 + i, self.world, len(self.side)):
                     r = (self.rank - step) % self.world
-                    landing[r * self.n:(r + 1) * self.n].copy_(self.peers[r], non_blocking=True)
+                    landing[r * self.n:(r + 1) * self.n].copy_(self.peers[r][:self.n], non_blocking=True)
                 self.join[i].record(st)
         for ev in self.join:
             cur.wait_event(ev)
         self.hdl.barrier(channel=0)                     # every rank has pulled: staging buffers may be rewritten
+
+
+    # ---- mode "pull" (MMGPU_EXCHANGE=pull): exchange fused with the border extension --------------------------------------
+    # The owner publishes its UN-PADDED picture in symmetric memory; every rank's mmgpu_pull_refs_unpadded kernels read the
+    # peers' pictures in place over NVLink (SM loads of a few persistent CTAs) and write the padded reference planes directly:
+    # half the NVLink bytes of the padded all-gather, no landing buffer, no separate padding pass, and an SM budget the caller
+    # chooses.  publish() -> [pull kernels, enqueued by the caller on the same stream] -> done().
+    def publish(self, parity, mine):
+        self.stage[parity * self.n:(parity + 1) * self.n].copy_(mine, non_blocking=True)
+        self.hdl.barrier(channel=0)                     # every rank's picture of this step is in place
+
+    def peer_ptr(self, r, parity):
+        """device address (peer-mapped for r != rank) of rank r's published picture of that parity"""
+        return self.peers[r].data_ptr() + parity * self.n
+
+    def done(self):
+        self.hdl.barrier(channel=0)                     # every rank has pulled: the staging picture may be rewritten
 
 
 def shard_blocks(blocks, rank, world, ctu=128, pic_h=None):
