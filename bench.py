@@ -311,9 +311,24 @@ def main():
     # padded planes of its reference slot and its borders are extended on the device (mmgpu_set_ref_unpadded_device)
     # MMGPU_EXCHANGE_PADDED=1: round-1 form for comparison -- the padded pictures themselves are all-gathered straight into
     # the registered reference slots (twice the NVLink bytes, no padding kernel)
-    padded_x = os.environ.get("MMGPU_EXCHANGE_PADDED", "0") == "1"
+    # Exchange of the step's reference pictures.  Default: up to 4 GPUs the NVLS multicast push of padded pictures
+    # (MMGPU_EXCHANGE=push) where symmetric memory has a multicast mapping, else ONE ncclAllGather of the padded pictures.  Other forms, for comparison:
+    # MMGPU_EXCHANGE=nccl with MMGPU_EXCHANGE_PADDED=0 (un-padded all-gather + k_pad_planes), =pull (un-padded, SM / TMA pulls
+    # fused with the border extension), =p2p (copy-engine pulls).
+    explicit_x = "MMGPU_EXCHANGE" in os.environ
+    # measured on B200 boxes: push wins at N = 2 (408 vs 396 G/s), ties at N = 4, loses at N = 8 where every form is bound
+    # by the ~400 GB/s each GPU can take in over NVLink (1050 vs 1285 G/s for the all-gather, which spreads the arrivals better)
+    want_x = os.environ.get("MMGPU_EXCHANGE", "push" if N <= 4 else "nccl").lower()
+    padded_x = os.environ.get("MMGPU_EXCHANGE_PADDED", "1" if want_x in ("push", "nccl") and not explicit_x else "0") == "1" or want_x == "push"
     xbytes = pic_bytes if padded_x else upic_bytes
-    comm = [torch.zeros(N * xbytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
+    exchange = shard.PictureExchange(xbytes, dev, mode=want_x) if N > 1 else None
+    push = exchange is not None and exchange.mode == "push"
+    if N > 1 and want_x == "push" and not push and explicit_x:
+        raise SystemExit("MMGPU_EXCHANGE=push needs symmetric memory with a multicast mapping (%s)" % getattr(exchange, "err", "?"))
+    if push:
+        comm = [exchange.landing(p) for p in range(2)]      # the landing slots live in the multicast-mapped symmetric allocation
+    else:
+        comm = [torch.zeros(N * xbytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
     for p, big in enumerate(comm):     # allocate + publish the planes of every landing slot once (addresses stay fixed)
         for f in range(N):
             if padded_x:
@@ -354,7 +369,11 @@ def main():
     gpu.set_org_device(d_org.data_ptr(), W, W, N * H, keep=d_org)
     plans = {}
     stream = torch.cuda.ExternalStream(gpu.stream, device=dev)
-    comm_stream = torch.cuda.Stream(device=dev) if N > 1 else None
+    # the exchange stream of the hand-written forms has the higher priority: their few CTAs become resident as soon as CTAs of the
+    # running step retire instead of queueing behind the step's 65 k pending CTAs; NCCL measured slower with it (MMGPU_COMM_PRIORITY)
+    hand_written = exchange is not None and exchange.mode in ("push", "pull")
+    comm_prio = int(os.environ.get("MMGPU_COMM_PRIORITY", "-1" if hand_written else "0"))
+    comm_stream = torch.cuda.Stream(device=dev, priority=comm_prio) if N > 1 else None
     ready = [torch.cuda.Event() for _ in range(2)]   # landing buffers of parity p hold the references of a step
     freed = [torch.cuda.Event() for _ in range(2)]   # the step that read parity p has finished
 
@@ -372,8 +391,8 @@ def main():
             plans[key] = (gpu.plan(b, n_cands), b)
         return plans[key]
 
-    exchange = shard.PictureExchange(xbytes, dev) if N > 1 else None
     pull = exchange is not None and exchange.mode == "pull"
+    push_ctas = int(os.environ.get("MMGPU_PUSH_CTAS", "16"))
     pull_ctas = int(os.environ.get("MMGPU_PULL_CTAS", "24"))
     if exchange is not None and os.environ.get("MMGPU_EXCHANGE", "nccl").lower() == "pull" and (not pull or padded_x):
         raise SystemExit("MMGPU_EXCHANGE=pull needs symmetric memory and the un-padded exchange (%s)" % getattr(exchange, "err", "padded form selected"))
@@ -384,6 +403,12 @@ def main():
         if N == 1:
             return
         p = s % 2
+        if push:
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(freed[p])
+                exchange.push(gpu, p, pool_ref[(s * N + rank) % POOL], max_ctas=push_ctas)
+                ready[p].record(comm_stream)
+            return
         if pull:
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(freed[p])
@@ -610,6 +635,7 @@ def main():
                                        (" un-padded; pulled row by row from the owners' symmetric memory by %d persistent CTAs that write the padded planes directly (k_pull_rows + k_pad_tb)" % pull_ctas
                                         if pull else " un-padded; margins rebuilt on arrival by one k_pad_planes launch"),
                                        "by SM loads over NVLink (mmgpu_pull_refs_unpadded)" if pull else
+                                       ("by ONE multicast copy per owner (mmgpu_multicast_copy: multimem.st to the NVLS mapping of the landing slots, %d CTAs; the NVSwitch fans out)" % push_ctas) if push else
                                        ("by copy-engine pulls from symmetric (peer) memory over NVLink" if exchange.mode == "p2p" else "by one ncclAllGather")))
                                    if N > 1 else "1 gpu"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

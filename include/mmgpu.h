@@ -119,6 +119,13 @@ int mmgpu_set_refs_unpadded_device(mmgpu_ctx* ctx, int n, const int32_t* slots, 
 int mmgpu_pull_refs_unpadded(mmgpu_ctx* ctx, int n, const int32_t* slots, const int32_t* pocs, const int16_t* const* d_plane,
                              const int32_t* stride, int max_ctas, void* stream);
 
+/* PUSH form of the same exchange: d_dst_multicast is a multicast address of symmetric memory (NVLS: the NVSwitch replicates one
+ * store into the same offset of every GPU's buffer, e.g. torch symmetric memory's multicast_ptr + offset of a landing reference
+ * slot registered with mmgpu_set_ref_device).  The owner reads its padded picture once and writes it once (`multimem.st`);
+ * per GPU and step that is ONE picture of SM work and NVLink egress.  Asynchronous on `stream`; the caller brackets it with its
+ * cross-rank barriers (slot free everywhere / pushes landed). */
+int mmgpu_multicast_copy(mmgpu_ctx* ctx, const void* d_src, void* d_dst_multicast, size_t bytes, int max_ctas, void* stream);
+
 /* ---- geodesic epipole: GeodesicMotionModel::setEpipole (GeodesicMotionModel.cpp:14-46) ------------ */
 void mmgpu_rodrigues(const float epipole[3], float R[9]);          /* host helper, row-major R */
 float mmgpu_fixed_to_float(int32_t fixed, int32_t precision);     /* Coordinate.cpp:75-77 (EPIPOLE_PRECISION_FIXED=24) */

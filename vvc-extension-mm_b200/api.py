@@ -22,7 +22,7 @@ EXPORTS = [
     "mmgpu_set_rotation", "mmgpu_reproject", "mmgpu_mc", "mmgpu_add_avg", "mmgpu_set_org", "mmgpu_set_org_device",
     "mmgpu_set_ref_unpadded_wrap", "mmgpu_me_batch", "mmgpu_me_batch_submit", "mmgpu_me_batch_wait", "mmgpu_plan_create", "mmgpu_plan_destroy", "mmgpu_me_batch_device", "mmgpu_plan_samples",
     "mmgpu_mc_batch_device", "mmgpu_dmvr_costs", "mmgpu_dmvr_decide", "mmgpu_mc_jobs", "mmgpu_selftest_tan_sincos", "mmgpu_me_batch_device_multiref", "mmgpu_set_ref_unpadded_device", "mmgpu_set_dist_oob_mode", "mmgpu_mc_jobs_device", "mmgpu_set_refs_unpadded_device", "mmgpu_mvp_convert", "mmgpu_mc_bdof",
-    "mmgpu_dmvr_classic_costs", "mmgpu_dmvr_final_mc", "mmgpu_mc_alt_hpel", "mmgpu_pull_refs_unpadded",
+    "mmgpu_dmvr_classic_costs", "mmgpu_dmvr_final_mc", "mmgpu_mc_alt_hpel", "mmgpu_pull_refs_unpadded", "mmgpu_multicast_copy",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
     L.mmgpu_set_rotation.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.mmgpu_reproject.argtypes = [vp, i32, i32, i32, i32, i32, i32, Mv, i32, i32, vp, vp]
     L.mmgpu_pull_refs_unpadded.argtypes = [vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32), i32, vp]
+    L.mmgpu_multicast_copy.argtypes = [vp, vp, vp, C.c_size_t, i32, vp]
     L.mmgpu_mvp_convert.argtypes = [vp, i32, i32, Mv] + [i32] * 14 + [C.POINTER(Mv)]
     L.mmgpu_mc.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, Mv, i32, i32, i32, i32, i32, i32, vp, i32]
     L.mmgpu_add_avg.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32]
@@ -302,6 +303,11 @@ class MmGpu:
         ss = (C.c_int32 * (3 * n))(*flat_s)
         self._keep[("refus", tuple(slots))] = keep
         self._chk(self.L.mmgpu_pull_refs_unpadded(self.h, n, sl, pc, pp, ss, int(max_ctas), C.c_void_p(stream) if stream else None))
+
+    def multicast_copy(self, src_ptr, dst_multicast_ptr, nbytes, max_ctas=16, stream=None):
+        """local device memory -> multicast address of symmetric memory (one multimem.st per 16 bytes; the switch fans out)"""
+        self._chk(self.L.mmgpu_multicast_copy(self.h, C.c_void_p(int(src_ptr)), C.c_void_p(int(dst_multicast_ptr)), int(nbytes), int(max_ctas),
+                                              C.c_void_p(stream) if stream else None))
 
     def mvp_convert(self, pos, mv, model_orig, model_desired, cand, cur, shift=(4, 4), rot_slots=(0, 0)):
         """MVReprojection::motionVectorInDesiredMotionModel; cand / cur = (x, y, w, h) of the candidate's / the current block."""

@@ -207,6 +207,7 @@ struct MmPadPlane
 struct MmPadJobs { MmPadPlane p[MM_PAD_MAX]; };
 void mmk_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxGroups, int maxRows);
 void mmk_pull_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxCtas);
+void mmk_multicast_copy(cudaStream_t s, const void* src, void* dstMulticast, size_t bytes, int maxCtas);
 void mmk_extend_border(cudaStream_t s, int16_t* plane00, int stride, int w, int h, int mx, int my, int xoff);
 void mmk_add_avg(cudaStream_t s, const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                  int shift, int offset, int lo, int hi);

@@ -320,31 +320,221 @@ __global__ void __launch_bounds__(512) k_pull_rows(MmPadJobs J, int nPlanes, int
     }
   }
 }
-__global__ void __launch_bounds__(512) k_pad_tb(MmPadJobs J, int nPlanes, int totalRows)
+#define MM_TB_ROWS 16   // margin rows written per unit of k_pad_tb: the source row is loaded once and stored 16 times
+__global__ void __launch_bounds__(512) k_pad_tb(MmPadJobs J, int nPlanes, int totalUnits)
 {
   const int lane = threadIdx.x & 31;
   const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
-  for (int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < totalRows; unit += warpsPerGrid)
+  for (int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < totalUnits; unit += warpsPerGrid)
   {
-    int k = 0, r = unit;
-    while (k < nPlanes - 1 && r >= 2 * J.p[k].my) { r -= 2 * J.p[k].my; ++k; }
+    int k = 0, u = unit;
+    for (;;)
+    {
+      const int nu = 2 * ((J.p[k].my + MM_TB_ROWS - 1) / MM_TB_ROWS);
+      if (k == nPlanes - 1 || u < nu) break;
+      u -= nu;
+      ++k;
+    }
     const MmPadPlane& p = J.p[k];
-    const int Y = (r < p.my) ? (r - p.my) : (p.h + r - p.my);      // margin row
-    const int sy = (r < p.my) ? 0 : (p.h - 1);
+    const int chunks = (p.my + MM_TB_ROWS - 1) / MM_TB_ROWS;
+    const bool bottom = u >= chunks;
+    const int r0 = (bottom ? u - chunks : u) * MM_TB_ROWS, r1 = min(r0 + MM_TB_ROWS, p.my);
+    const int sy = bottom ? (p.h - 1) : 0;
+    const int Y0 = bottom ? p.h : -p.my;                       // first margin row of the side
     const int G = (p.w + 2 * p.mx) >> 3;
     const uint4* srow = reinterpret_cast<const uint4*>(p.dst00 + (long)sy * p.dstStride - p.mx);
-    uint4* drow = reinterpret_cast<uint4*>(p.dst00 + (long)Y * p.dstStride - p.mx);
-    for (int g = lane; g < G; g += 32) drow[g] = srow[g];
+    for (int base = 0; base < G; base += 256)
+    {
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+      {
+        const int g = base + lane + 32 * i;
+        if (g < G) v[i] = srow[g];
+      }
+      for (int r = r0; r < r1; ++r)
+      {
+        uint4* drow = reinterpret_cast<uint4*>(p.dst00 + (long)(Y0 + r) * p.dstStride - p.mx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+          const int g = base + lane + 32 * i;
+          if (g < G) drow[g] = v[i];
+        }
+      }
+    }
   }
 }
-void mmk_pull_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxCtas)
+// k_pull_tma: the same pull with the bulk-copy engine of the SM (TMA, 1-D cp.async.bulk) instead of register loads.  One thread
+// per warp runs a ring of `stages` shared-memory rows: bulk load of a row from PEER memory (completion on the stage's mbarrier) ->
+// bulk store of the arrived row to its place in the padded plane -> refill once the store has read the stage.  No block-wide
+// synchronisation, tens to hundreds of KB in flight per CTA: a handful of CTAs (SMs) carries the whole exchange.  The left /
+// right margins are written afterwards from local memory (k_pad_lr), then the top / bottom rows (k_pad_tb).
+#define MM_PULL_LAG 2        // bulk stores that may still be reading their stage when the next load is issued
+__device__ __forceinline__ void mm_bulk_load(void* smemDst, const void* gsrc, uint32_t bytes, unsigned long long* bar)
 {
-  int rows = 0, mrows = 0;
-  for (int k = 0; k < nPlanes; ++k) { rows += J.p[k].h; mrows += 2 * J.p[k].my; }
-  k_pull_rows<<<maxCtas, 512, 0, s>>>(J, nPlanes, rows);
-  k_pad_tb<<<maxCtas, 512, 0, s>>>(J, nPlanes, mrows);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(mm_smem_u32(smemDst)), "l"(gsrc), "r"(bytes), "r"(mm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mm_bulk_store(void* gdst, const void* smemSrc, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(mm_smem_u32(smemSrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+struct MmRowCursor   // walks the rows blockIdx.x, + gridDim.x, ... of the concatenated planes
+{
+  int k, y;
+  __device__ __forceinline__ void init(const MmPadJobs& J, int nPlanes, int unit)
+  {
+    k = 0; y = unit;
+    while (k < nPlanes - 1 && y >= J.p[k].h) { y -= J.p[k].h; ++k; }
+  }
+  __device__ __forceinline__ void advance(const MmPadJobs& J, int nPlanes, int step)
+  {
+    y += step;
+    while (k < nPlanes - 1 && y >= J.p[k].h) { y -= J.p[k].h; ++k; }
+  }
+};
+#define MM_PULL_RINGS 8      // independent rings (warps, lane 0 active) per CTA: the per-thread issue latency of the bulk operations
+                             // (~1000 cycles per row measured with one ring), not the copy engine, limits a single ring
+__global__ void __launch_bounds__(32 * MM_PULL_RINGS) k_pull_tma(const __grid_constant__ MmPadJobs J, int nPlanes, int totalRows, int stages,
+                                                                  int stageBytes)
+{
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  if ((threadIdx.x & 31) != 0) return;
+  const int ring = threadIdx.x >> 5;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_dyn) + ring * stages;          // [rings][stages]
+  unsigned char* buf = s_dyn + ((MM_PULL_RINGS * stages * 8 + 127) & ~127) + (size_t)ring * stages * stageBytes;
+  for (int i = 0; i < stages; ++i) mm_mbar_init(&bars[i], 1);
+  const int first = blockIdx.x * MM_PULL_RINGS + ring, step = gridDim.x * MM_PULL_RINGS;
+  const int nMine = (totalRows - first + step - 1) / step;
+  if (nMine <= 0) return;
+  MmRowCursor ld, st;
+  ld.init(J, nPlanes, first);
+  st = ld;
+  int issued = 0;
+  for (; issued < min(stages, nMine); ++issued)
+  {
+    const uint32_t bytes = (uint32_t)J.p[ld.k].w * 2u;
+    mm_mbar_expect_tx(&bars[issued], bytes);
+    mm_bulk_load(buf + (size_t)issued * stageBytes, J.p[ld.k].src + (long)ld.y * J.p[ld.k].srcStride, bytes, &bars[issued]);
+    ld.advance(J, nPlanes, step);
+  }
+  for (int j = 0; j < nMine; ++j)
+  {
+    const int sg = j % stages;
+    mm_mbar_wait(&bars[sg], (uint32_t)((j / stages) & 1));
+    mm_bulk_store(J.p[st.k].dst00 + (long)st.y * J.p[st.k].dstStride, buf + (size_t)sg * stageBytes, (uint32_t)J.p[st.k].w * 2u);
+    st.advance(J, nPlanes, step);
+    // refill the stage of row j - LAG: its bulk store has read it once at most LAG younger stores are pending
+    if (j >= MM_PULL_LAG && issued < nMine)
+    {
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(MM_PULL_LAG) : "memory");
+      const int s2 = (j - MM_PULL_LAG) % stages;
+      const uint32_t bytes = (uint32_t)J.p[ld.k].w * 2u;
+      mm_mbar_expect_tx(&bars[s2], bytes);
+      mm_bulk_load(buf + (size_t)s2 * stageBytes, J.p[ld.k].src + (long)ld.y * J.p[ld.k].srcStride, bytes, &bars[s2]);
+      ld.advance(J, nPlanes, step);
+      ++issued;
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA (and its shared memory) goes away
+}
+// left / right margins of every row from the row's own edge samples (local memory): a warp takes 32 rows, lane r reads the two
+// edge samples of row r, then the warp writes the 32 x 2 x (mx / 8) margin groups
+__global__ void __launch_bounds__(512) k_pad_lr(MmPadJobs J, int nPlanes, int totalUnits)
+{
+  const int lane = threadIdx.x & 31;
+  const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+  for (int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < totalUnits; unit += warpsPerGrid)
+  {
+    int k = 0, u = unit;
+    for (;;)
+    {
+      const int nu = (J.p[k].h + 31) >> 5;
+      if (k == nPlanes - 1 || u < nu) break;
+      u -= nu;
+      ++k;
+    }
+    const MmPadPlane& p = J.p[k];
+    const int y = u * 32 + lane;
+    uint32_t first = 0, last = 0;
+    if (y < p.h)
+    {
+      const int16_t* row = p.dst00 + (long)y * p.dstStride;
+      first = (uint16_t)row[0];
+      last = (uint16_t)row[p.w - 1];
+    }
+    const int mg = p.mx >> 3, rows = min(32, p.h - u * 32);
+    for (int r = 0; r < rows; ++r)
+    {
+      const uint32_t f = __shfl_sync(0xffffffffu, first, r), l = __shfl_sync(0xffffffffu, last, r);
+      const uint32_t f2 = f | (f << 16), l2 = l | (l << 16);
+      int16_t* drow = p.dst00 + (long)(u * 32 + r) * p.dstStride;
+      for (int m = lane; m < 2 * mg; m += 32)
+      {
+        if (m < mg) *reinterpret_cast<uint4*>(drow - p.mx + 8 * m) = make_uint4(f2, f2, f2, f2);
+        else *reinterpret_cast<uint4*>(drow + p.w + 8 * (m - mg)) = make_uint4(l2, l2, l2, l2);
+      }
+    }
+  }
 }
 
+// k_multicast_copy: the PUSH form of the exchange.  dst is a MULTICAST address of symmetric memory (NVLink SHARP / NVLS: one store
+// is replicated by the NVSwitch into the same offset of every GPU's buffer, the writer's included): the owner of a picture reads
+// it once from local memory and writes it once; the switch fans it out.  Per GPU and step that is one picture of SM work and
+// NVLink egress instead of N - 1 pictures pulled or all-gathered.
+__global__ void __launch_bounds__(512) k_multicast_copy(const uint4* __restrict__ src, uint4* dst, long n16)
+{
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += 4 * stride)
+  {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i + k * stride < n16) v[k] = __ldg(src + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i + k * stride < n16)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i + k * stride), "f"(__uint_as_float(v[k].x)),
+                     "f"(__uint_as_float(v[k].y)), "f"(__uint_as_float(v[k].z)), "f"(__uint_as_float(v[k].w)) : "memory");
+  }
+  __threadfence_system();
+}
+void mmk_multicast_copy(cudaStream_t s, const void* src, void* dstMulticast, size_t bytes, int maxCtas)
+{
+  k_multicast_copy<<<maxCtas, 512, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dstMulticast), (long)(bytes >> 4));
+}
+
+void mmk_pull_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int maxCtas)
+{
+  int rows = 0, units = 0, maxW = 0;
+  for (int k = 0; k < nPlanes; ++k)
+  {
+    rows += J.p[k].h;
+    units += 2 * ((J.p[k].my + MM_TB_ROWS - 1) / MM_TB_ROWS);
+    maxW = max(maxW, J.p[k].w);
+  }
+  static int mode = -1;   // MMGPU_PULL_KERNEL=ld: register-load variant (k_pull_rows); default: TMA bulk copies
+  if (mode < 0) { const char* e = getenv("MMGPU_PULL_KERNEL"); mode = (e && e[0] == 'l') ? 1 : 0; }
+  if (mode == 1) k_pull_rows<<<maxCtas, 512, 0, s>>>(J, nPlanes, rows);
+  else
+  {
+    const int stageBytes = (maxW * 2 + 127) & ~127;
+    static int wantStages = 0;   // MMGPU_PULL_STAGES: rows in flight per CTA (default 48: ~200 KB of shared memory for 2048-wide luma)
+    if (!wantStages) { const char* e = getenv("MMGPU_PULL_STAGES"); wantStages = e ? atoi(e) : 48; if (wantStages <= 0) wantStages = 48; }
+    int stages = min(wantStages, (200 * 1024) / stageBytes) / MM_PULL_RINGS;     // per ring
+    stages = max(2 * MM_PULL_LAG, min(stages, 16));
+    const int smem = ((MM_PULL_RINGS * stages * 8 + 127) & ~127) + MM_PULL_RINGS * stages * stageBytes;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_pull_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+    k_pull_tma<<<maxCtas, 32 * MM_PULL_RINGS, smem, s>>>(J, nPlanes, rows, stages, stageBytes);
+    int lrUnits = 0;
+    for (int k = 0; k < nPlanes; ++k) lrUnits += (J.p[k].h + 31) >> 5;
+    k_pad_lr<<<maxCtas, 512, 0, s>>>(J, nPlanes, lrUnits);
+  }
+  k_pad_tb<<<maxCtas, 512, 0, s>>>(J, nPlanes, units);
+}
 __global__ void k_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1, int16_t* dst, int ds, int w, int h,
                           int shift, int offset, int lo, int hi)
 {

@@ -733,7 +733,7 @@ static int setRefsUnpadded(mmgpu_ctx* ctx, int n, const int32_t* slots, const in
   if (pullCtas > 0)
   {
     mmk_pull_pad_planes(st, J, k, pullCtas);
-    ctx->launches += 2;
+    ctx->launches += 3;
   }
   else
   {
@@ -755,6 +755,18 @@ extern "C" int mmgpu_pull_refs_unpadded(mmgpu_ctx* ctx, int n, const int32_t* sl
 {
   if (max_ctas < 1 || max_ctas > 1024) return ctx ? fail(ctx, MMGPU_ERR_ARG, "max_ctas must be 1..1024") : MMGPU_ERR_ARG;
   return setRefsUnpadded(ctx, n, slots, pocs, d_plane, stride, 0, stream, max_ctas);
+}
+
+extern "C" int mmgpu_multicast_copy(mmgpu_ctx* ctx, const void* d_src, void* d_dst_multicast, size_t bytes, int max_ctas, void* stream)
+{
+  if (!ctx || !d_src || !d_dst_multicast || bytes == 0) return MMGPU_ERR_ARG;
+  if (((uintptr_t)d_src & 15) || ((uintptr_t)d_dst_multicast & 15) || (bytes & 15)) return fail(ctx, MMGPU_ERR_ARG, "multicast_copy: 16-byte alignment");
+  if (max_ctas < 1 || max_ctas > 1024) return fail(ctx, MMGPU_ERR_ARG, "max_ctas must be 1..1024");
+  cudaSetDevice(ctx->cfg.device);
+  mmk_multicast_copy(stream ? (cudaStream_t)stream : ctx->stream, d_src, d_dst_multicast, bytes, max_ctas);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return MMGPU_OK;
 }
 
 extern "C" int mmgpu_set_rotation(mmgpu_ctx* ctx, int rot_slot, const float R[9])

@@ -48,21 +48,24 @@ class PictureExchange:
         self.n = int(pic_bytes)
         self.mode = "nccl"
         want = (mode or os.environ.get("MMGPU_EXCHANGE", "nccl")).lower()
-        if want in ("p2p", "pull") and self.world > 1 and torch.device(device).type == "cuda":
+        if want in ("p2p", "pull", "push") and self.world > 1 and torch.device(device).type == "cuda":
             ok = 1
             try:
                 import torch.distributed._symmetric_memory as symm
                 # pull: two staging pictures (step parity), read in place by the peers' pull kernels
-                self.stage = symm.empty(self.n * (2 if want == "pull" else 1), dtype=torch.uint8, device=device)
+                # push: the landing slots themselves (two parities x world pictures) are symmetric + multicast-mapped
+                self.stage = symm.empty(self.n * (2 if want == "pull" else 2 * self.world if want == "push" else 1), dtype=torch.uint8, device=device)
                 self.hdl = symm.rendezvous(self.stage, group if group is not None else dist.group.WORLD)
                 self.peers = [self.hdl.get_buffer(r, (self.stage.numel(),), torch.uint8) for r in range(self.world)]
+                if want == "push" and not self.hdl.multicast_ptr:
+                    raise RuntimeError("no multicast (NVLS) mapping for symmetric memory on this box")
             except Exception as e:  # noqa: BLE001 -- any failure means: use the NCCL path on every rank
                 self.err = repr(e)
                 ok = 0
             flag = torch.tensor([ok], dtype=torch.int32, device=device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 1 and want == "pull":
-                self.mode = "pull"
+            if int(flag.item()) == 1 and want in ("pull", "push"):
+                self.mode = want
             elif int(flag.item()) == 1:
                 self.mode = "p2p"
                 # one copy engine moves ~280 GB/s over NVLink (measured: 7 pulls of 12.6 MB in 0.32 ms); several pull
@@ -109,6 +112,23 @@ class PictureExchange:
 
     def done(self):
         self.hdl.barrier(channel=0)                     # every rank has pulled: the staging picture may be rewritten
+
+
+    # ---- mode "push" (MMGPU_EXCHANGE=push): NVLS multicast -------------------------------------------------------------------
+    # The landing reference slots of every rank (2 parities x world padded pictures) are one symmetric allocation with a multicast
+    # mapping.  The owner of a picture copies it ONCE to multicast_ptr + slot offset (mmgpu_multicast_copy, multimem.st): the
+    # NVSwitch writes it into the slot of all ranks, the owner's included.  Per rank and step: one picture read, one picture of
+    # NVLink egress, a few CTAs for a few microseconds -- instead of world - 1 pictures gathered by collective kernels.
+    def landing(self, parity):
+        """local view of the world landing pictures of that parity (register them as reference slots once)"""
+        return self.stage[parity * self.world * self.n:(parity + 1) * self.world * self.n]
+
+    def push(self, gpu, parity, mine, max_ctas=16):
+        """Enqueue on the current stream: [all ranks done with the parity's slots] -> multicast copy -> [all pushes landed]."""
+        self.hdl.barrier(channel=0)
+        gpu.multicast_copy(mine.data_ptr(), self.hdl.multicast_ptr + (parity * self.world + self.rank) * self.n, self.n, max_ctas=max_ctas,
+                           stream=torch.cuda.current_stream().cuda_stream)
+        self.hdl.barrier(channel=0)
 
 
 def shard_blocks(blocks, rank, world, ctu=128, pic_h=None):
