@@ -218,8 +218,11 @@ def kernel_source_hash():
     import hashlib
     d = os.path.join(ROOT, "vvc-extension-mm_b200", "csrc")
     h = hashlib.sha256()
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
+    # the translation units and headers k_map / k_fir are compiled from (the host ABI, MC / DMVR kernels do not change their SASS)
+    files = ("mm_kernels_map.cu", "mm_kernels_fir.cu", "mm_fir.cuh", "mm_map.cuh", "mm_libm.cuh", "mm_sbpos.cuh", "mm_common.cuh", "mm_htaps.h",
+             "mm_tan_exceptions.h")
+    for f in files:
+        if os.path.exists(os.path.join(d, f)):
             h.update(f.encode())
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()

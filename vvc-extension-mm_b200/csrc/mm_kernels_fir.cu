@@ -526,8 +526,7 @@ void mmk_pull_pad_planes(cudaStream_t s, const MmPadJobs& J, int nPlanes, int ma
     int stages = min(wantStages, (200 * 1024) / stageBytes) / MM_PULL_RINGS;     // per ring
     stages = max(2 * MM_PULL_LAG, min(stages, 16));
     const int smem = ((MM_PULL_RINGS * stages * 8 + 127) & ~127) + MM_PULL_RINGS * stages * stageBytes;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_pull_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+    cudaFuncSetAttribute(k_pull_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);   // per device: set on every call
     k_pull_tma<<<maxCtas, 32 * MM_PULL_RINGS, smem, s>>>(J, nPlanes, rows, stages, stageBytes);
     int lrUnits = 0;
     for (int k = 0; k < nPlanes; ++k) lrUnits += (J.p[k].h + 31) >> 5;
