@@ -756,12 +756,17 @@ EDITS = {"Lib/CommonLib/InterPrediction.cpp": edit_interprediction, "Lib/CommonL
          "Lib/CommonLib/Picture.cpp": edit_picture, "Lib/EncoderLib/InterSearch.cpp": edit_intersearch}
 
 
-def main():
+def build_patch():
     out = []
     for f in FILES:
         a = open(os.path.join(SRC, f), encoding="latin-1").read()
         b = EDITS[f](a)
         out += difflib.unified_diff(a.splitlines(True), b.splitlines(True), "a/" + f, "b/" + f, n=3)
+    return out
+
+
+def main():
+    out = build_patch()
     with open(os.path.join(HERE, "mmgpu.patch"), "w", encoding="latin-1") as fh:
         fh.writelines(out)
     print("wrote mmgpu.patch: %d lines" % len(out))

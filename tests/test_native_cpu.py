@@ -276,3 +276,22 @@ def test_mvp_conversion_host_build_equals_reference_source():
                             print("MVP mismatch", W, mo, md, pos, mv, shift, (cx, cy, cw, chh), (ux, uy, uw, uh), exp, out)
         assert bad == 0, (bad, n)
         assert nz > n // 2
+
+
+def test_committed_integration_patch_is_what_the_documented_edits_produce():
+    """oracle/patches/mmgpu.patch (what oracle/vtm.mk applies to the build-time copy of four reference units) must be exactly the
+    diff that make_patch.py's asserted, documented edits produce from the reference sources -- no hand-edited patch, no stale one."""
+    if not os.path.isdir("/root/reference/source/Lib/CommonLib"):
+        pytest.skip("reference sources absent")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_patch", os.path.join(ROOT, "oracle", "patches", "make_patch.py"))
+    mp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mp)
+    want = "".join(mp.build_patch())
+    have = open(os.path.join(ROOT, "oracle", "patches", "mmgpu.patch"), encoding="latin-1").read()
+    assert want == have
+    # every hook family is in it
+    for hook in ("mmglue::predInterBlkMM", "mmglue::predInterBlkClassic", "mmglue::predInterBlkClassicBdof", "mmglue::predInterBlkClassicAltHpel",
+                 "mmglue::mvpConvert", "mmglue::meEval", "mmglue::endCollect", "mmglue::dmvrRun", "mmglue::dmvrFinalRun", "mmglue::verifyCompare",
+                 "mmglue::meVerify", "mmglue::invalidate", "mmglue::init"):
+        assert hook in have, hook

@@ -291,6 +291,47 @@ public:
     tzReplay(pts, d.data(), mvCost, best);
   }
 
+  // InterPrediction::xPredInterBlk (classic translational MC, InterPrediction.cpp:928-1096): plain, with the alternative half-pel
+  // filter (pu.cu->imv == IMV_HPEL, luma) or with bioApplied (luma: prediction + ring into the (w + 4)-stride BDOF work buffer)
+  void xPredInterBlk(int compID, const Position& blockPos, const Size& blockSize, int refSlot, const Mv& mv, PelBuf& dstBuf, bool bi,
+                     const ClpRng& clpRng, bool useAltHpelIf = false)
+  {
+    const mmgpu_mv m = {mv.hor, mv.ver};
+    if (useAltHpelIf && compID == 0)
+      chk(mmgpu_mc_alt_hpel(m_ctx, refSlot, blockPos.x, blockPos.y, (int)blockSize.width, (int)blockSize.height, m, bi ? 1 : 0, clpRng.min,
+                            clpRng.max, dstBuf.buf, dstBuf.stride));
+    else
+      chk(mmgpu_mc(m_ctx, refSlot, compID, m_chFmt, blockPos.x, blockPos.y, (int)blockSize.width, (int)blockSize.height, m, MMGPU_CLASSIC, 0,
+                   bi ? 1 : 0, clpRng.min, clpRng.max, MMGPU_OOB_PRED, dstBuf.buf, dstBuf.stride));
+  }
+  void xPredInterBlkBdof(const Position& blockPos, const Size& blockSize, int refSlot, const Mv& mv, const ClpRng& clpRng, int16_t* bdofBuf)
+  {
+    const mmgpu_mv m = {mv.hor, mv.ver};
+    chk(mmgpu_mc_bdof(m_ctx, refSlot, blockPos.x, blockPos.y, (int)blockSize.width, (int)blockSize.height, m, clpRng.min, clpRng.max, bdofBuf));
+  }
+  // MVReprojection::motionVectorInDesiredMotionModel (MVReprojection.cpp:168-217)
+  Mv motionVectorInDesiredMotionModel(const Position& position, const Mv& mvOrig, int modelOrig, int modelDesired, int shiftHor, int shiftVer,
+                                      int rotSlotOrig, int rotSlotDesired, const Position& candPos, const Size& candSize,
+                                      const Position& curPos, const Size& curSize)
+  {
+    const mmgpu_mv m = {mvOrig.hor, mvOrig.ver};
+    mmgpu_mv out = {0, 0};
+    chk(mmgpu_mvp_convert(m_ctx, position.x, position.y, m, modelOrig, modelDesired, shiftHor, shiftVer, rotSlotOrig, rotSlotDesired, candPos.x,
+                          candPos.y, (int)candSize.width, (int)candSize.height, curPos.x, curPos.y, (int)curSize.width, (int)curSize.height, &out));
+    return Mv{out.hor, out.ver};
+  }
+  // InterPrediction::xProcessDMVR (classic, InterPrediction.cpp:2239-2439): the integer search of a PU's sub-PUs in one call
+  // (costs[i * 25 + k], then mmgpu_dmvr_decide per sub-PU) and the final MC of the (list, component) jobs of a sub-PU
+  void dmvrClassicCosts(const std::vector<mmgpu_dmvr_classic_subpu>& subPus, std::vector<uint64_t>& costs)
+  {
+    costs.assign(subPus.size() * 25, 0);
+    if (!subPus.empty()) chk(mmgpu_dmvr_classic_costs(m_ctx, (int)subPus.size(), subPus.data(), costs.data()));
+  }
+  void dmvrFinalMc(const std::vector<mmgpu_dmvr_mc_job>& jobs, std::vector<int16_t>& out)
+  {
+    if (!jobs.empty()) chk(mmgpu_dmvr_final_mc(m_ctx, (int)jobs.size(), jobs.data(), out.data(), (int)out.size()));
+  }
+
   mmgpu_ctx* ctx() { return m_ctx; }
 
 private:
