@@ -274,8 +274,14 @@ def main():
 
     # ---- resident data -------------------------------------------------------------------------------------
     # A picture = one contiguous byte buffer holding the padded Y, Cb, Cr planes (one NCCL broadcast per picture).
-    n_comm = 2 * N if N > 1 else 0     # double-buffered landing slots: the next step's references arrive while
-    gpu = mm.MmGpu(W, H, max_refs=POOL + n_comm, device=local)   # the current step computes
+    # Ring of landing slots: the references of the next RING - 1 steps arrive while the current step computes.  With 2 the exchange
+    # of step s + 1 can only start when step s - 1 has finished on EVERY rank and must end before step s ends: its whole chain
+    # (barrier, transfer, barrier) has to fit one step; with 3 it has two steps (MMGPU_RING).
+    # Default: 3 for the multicast push (measured at N = 2 and 4: same device figure, e2e 374 instead of 312 G/s at N = 2), 2 for
+    # the NCCL forms (the configuration their N = 8 numbers were measured with).
+    RING_MAX = max(2, int(os.environ.get("MMGPU_RING", "3")))
+    n_comm = RING_MAX * N if N > 1 else 0
+    gpu = mm.MmGpu(W, H, max_refs=POOL + n_comm, device=local)
     gpu.set_rotation(0, mm.rodrigues(EPIPOLE))
     geo = wl.pad_frame(wl.synth_frame(W, H, seed=100), 288, 1)
     plane_bytes = [p.buf.nbytes for p in geo]
@@ -324,14 +330,16 @@ def main():
     want_x = os.environ.get("MMGPU_EXCHANGE", "push" if N <= 4 else "nccl").lower()
     padded_x = os.environ.get("MMGPU_EXCHANGE_PADDED", "1" if want_x in ("push", "nccl") and not explicit_x else "0") == "1" or want_x == "push"
     xbytes = pic_bytes if padded_x else upic_bytes
-    exchange = shard.PictureExchange(xbytes, dev, mode=want_x) if N > 1 else None
+    exchange = shard.PictureExchange(xbytes, dev, mode=want_x, ring=RING_MAX) if N > 1 else None
     push = exchange is not None and exchange.mode == "push"
+    RING = RING_MAX if ("MMGPU_RING" in os.environ or push) else 2
+    LOOK = RING - 1
     if N > 1 and want_x == "push" and not push and explicit_x:
         raise SystemExit("MMGPU_EXCHANGE=push needs symmetric memory with a multicast mapping (%s)" % getattr(exchange, "err", "?"))
     if push:
-        comm = [exchange.landing(p) for p in range(2)]      # the landing slots live in the multicast-mapped symmetric allocation
+        comm = [exchange.landing(p) for p in range(RING)]      # the landing slots live in the multicast-mapped symmetric allocation
     else:
-        comm = [torch.zeros(N * xbytes, dtype=torch.uint8, device=dev) for _ in range(2 if N > 1 else 0)]
+        comm = [torch.zeros(N * xbytes, dtype=torch.uint8, device=dev) for _ in range(RING if N > 1 else 0)]
     for p, big in enumerate(comm):     # allocate + publish the planes of every landing slot once (addresses stay fixed)
         for f in range(N):
             if padded_x:
@@ -377,17 +385,17 @@ def main():
     hand_written = exchange is not None and exchange.mode in ("push", "pull")
     comm_prio = int(os.environ.get("MMGPU_COMM_PRIORITY", "-1" if hand_written else "0"))
     comm_stream = torch.cuda.Stream(device=dev, priority=comm_prio) if N > 1 else None
-    ready = [torch.cuda.Event() for _ in range(2)]   # landing buffers of parity p hold the references of a step
-    freed = [torch.cuda.Event() for _ in range(2)]   # the step that read parity p has finished
+    ready = [torch.cuda.Event() for _ in range(RING)]   # landing buffers of ring position p hold the references of a step
+    freed = [torch.cuda.Event() for _ in range(RING)]   # the step that read ring position p has finished
 
     def slots_of(s):
         """reference slot of frame f of step s"""
         if N == 1:
             return np.array([s % POOL])
-        return POOL + (s % 2) * N + np.arange(N)
+        return POOL + (s % RING) * N + np.arange(N)
 
     def step_plan(s):
-        key = (s % POOL) if N == 1 else (s % 2)
+        key = (s % POOL) if N == 1 else (s % RING)
         if key not in plans:
             b = blocks.copy()
             b["ref_slot"] = slots_of(s)[blocks["ref_slot"]]
@@ -405,7 +413,7 @@ def main():
         Runs on the communication stream, one step ahead of the compute stream."""
         if N == 1:
             return
-        p = s % 2
+        p = s % RING
         if push:
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(freed[p])
@@ -431,19 +439,26 @@ def main():
                                            [[w_ for w_, _ in uw]] * N, stream=comm_stream.cuda_stream, keep=comm[p])
             ready[p].record(comm_stream)
 
+    def prime():
+        """every ring position free, then the exchanges of the first LOOK steps"""
+        for p in range(RING):
+            freed[p].record(stream)
+        for k in range(LOOK):
+            prefetch(k)
+
     def load_orgs(s, tgt, src_pool):
         for f in range(N):
             tgt[f * H:(f + 1) * H].copy_(src_pool[(s * N + f + 1) % POOL], non_blocking=True)
 
     def device_step(s):
-        prefetch(s + 1)
+        prefetch(s + LOOK)
         with torch.cuda.stream(stream):
             if N > 1:
-                stream.wait_event(ready[s % 2])
+                stream.wait_event(ready[s % RING])
             plan, _ = step_plan(s)
             gpu.me_batch_device(plan, d_mvs.data_ptr(), d_dist.data_ptr(), mv_prec_shift=prec, dist=mm.DIST_HAD)
             if N > 1:
-                freed[s % 2].record(stream)
+                freed[s % RING].record(stream)
 
     # e2e: the host-facing call with every input in pinned HOST memory -- original picture, blocks and MVs go up, the
     # distortions come back, every step.  NSLOT batches are kept in flight (mmgpu_me_batch_submit / _wait) so that the
@@ -454,9 +469,9 @@ def main():
     h_blocks2 = [h_blocks] + [h_blocks.clone().pin_memory() for _ in range(NSLOT - 1)]
 
     def e2e_submit(s):
-        prefetch(s + 1)
+        prefetch(s + LOOK)
         if N > 1:
-            ready[s % 2].synchronize()
+            ready[s % RING].synchronize()
         _, b = step_plan(s)
         hb = h_blocks2[s % NSLOT].numpy().view(mm.api.BLOCK_DTYPE).reshape(-1)
         hb["ref_slot"] = b["ref_slot"]
@@ -464,7 +479,7 @@ def main():
         gpu.me_batch_submit(s % NSLOT, h_org.numpy(), hb, h_mvs.numpy().view(mm.api.MV_DTYPE).reshape(-1),
                             h_dist2[s % NSLOT].numpy().view(np.uint64), mv_prec_shift=prec, dist=mm.DIST_HAD)
         if N > 1:
-            freed[s % 2].record(stream)
+            freed[s % RING].record(stream)
 
     def e2e_step(s):
         if s >= NSLOT:
@@ -483,9 +498,7 @@ def main():
 
     def timed(fn, k, prep, drain=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for p in range(2):
-            freed[p].record(stream)
-        prefetch(0)                      # prologue: references of step 0 (steady state prefetches one step ahead)
+        prime()                          # prologue: references of the first LOOK steps (steady state prefetches LOOK steps ahead)
         barrier()
         t0 = time.perf_counter()
         ev0.record(stream)
@@ -507,13 +520,11 @@ def main():
         for k, r in enumerate(rows):
             h_org[(f * n_rows + k) * CTU:(f * n_rows + k + 1) * CTU].copy_(pool_org_h[(f + 1) % POOL][r * CTU:(r + 1) * CTU])
 
-    for s in range(POOL if N == 1 else 2):
+    for s in range(POOL if N == 1 else RING):
         step_plan(s)          # plans (device-resident block / work lists) are built once, outside any timed region
     sampler = ClockSampler(local)
     sampler.start()
-    for p in range(2):
-        freed[p].record(stream)
-    prefetch(0)
+    prime()
     for s in range(args.warmup):
         device_step(s)
     barrier()
@@ -528,9 +539,7 @@ def main():
     e2e_drain(2 * NSLOT)
     # self-check: the host-facing call and the device-resident call evaluate the same batch -> identical distortions;
     # with N > 1 the exchanged pictures are what their owners hold (every rank can regenerate every synthetic picture)
-    for p in range(2):
-        freed[p].record(stream)
-    prefetch(0)
+    prime()
     if N > 1:
         barrier()
         for f in range(N if not pull else 0):    # pull mode has no landing buffer: the oracle check of step 0 below covers every exchanged picture
@@ -539,9 +548,7 @@ def main():
     device_step(0)
     barrier()
     chk_dev = d_dist.cpu().numpy().view(np.uint64).copy()
-    for p in range(2):
-        freed[p].record(stream)
-    prefetch(0)
+    prime()
     e2e_submit(0)
     gpu.me_batch_wait(0)
     if not np.array_equal(chk_dev, h_dist2[0].numpy().view(np.uint64)):
@@ -633,13 +640,13 @@ def main():
             "dtype": "f32 mapping + s16/s32 FIR/SATD", "data": "synthetic",
             "config": bench_config(N, int(len(blocks)), int(n_cands), samples_all,
                                    ("ctu-rows x%d; the %d reference pictures of a step (%.1f MB each%s, one owner rank each) reach every GPU %s, "
-                                    "prefetched one step ahead on a second stream"
+                                    "prefetched %d step(s) ahead on a second stream"
                                     % (N, N, xbytes / 1e6, " with margins" if padded_x else
                                        (" un-padded; pulled row by row from the owners' symmetric memory by %d persistent CTAs that write the padded planes directly (k_pull_rows + k_pad_tb)" % pull_ctas
                                         if pull else " un-padded; margins rebuilt on arrival by one k_pad_planes launch"),
                                        "by SM loads over NVLink (mmgpu_pull_refs_unpadded)" if pull else
                                        ("by ONE multicast copy per owner (mmgpu_multicast_copy: multimem.st to the NVLS mapping of the landing slots, %d CTAs; the NVSwitch fans out)" % push_ctas) if push else
-                                       ("by copy-engine pulls from symmetric (peer) memory over NVLink" if exchange.mode == "p2p" else "by one ncclAllGather")))
+                                       ("by copy-engine pulls from symmetric (peer) memory over NVLink" if exchange.mode == "p2p" else "by one ncclAllGather"), LOOK))
                                    if N > 1 else "1 gpu"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": counts["k_fir"]["dram_bytes"] if counts else None, "kernel": "k_fir<DIST>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,

@@ -11,6 +11,7 @@ for v in "$@"; do
     nccl) MMGPU_EXCHANGE=nccl MMGPU_EXCHANGE_PADDED=0 run nccl_unpadded ;;
     padded) MMGPU_EXCHANGE=nccl MMGPU_EXCHANGE_PADDED=1 run nccl_padded ;;
     default) run default ;;
+    ring2) MMGPU_RING=2 run ring2 ;;
     pull*) MMGPU_EXCHANGE=pull MMGPU_PULL_CTAS=${v#pull} run $v ;;
     push*) MMGPU_EXCHANGE=push MMGPU_PUSH_CTAS=${v#push} run $v ;;
   esac

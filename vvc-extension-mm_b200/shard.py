@@ -40,7 +40,7 @@ class PictureExchange:
     almost alone (0.108 / 0.077 ms) but move only ~280 GB/s per GPU whether issued on 1, 4 or 7 streams, so the step
     becomes exchange-bound (0.31 ms, 847 G/s).  At 2 GPUs both are equal (360 vs 357 G/s).  Hence the default."""
 
-    def __init__(self, pic_bytes, device, group=None, mode=None):
+    def __init__(self, pic_bytes, device, group=None, mode=None, ring=2):
         import os
         self.group = group
         self.world = dist.get_world_size(group)
@@ -52,9 +52,9 @@ class PictureExchange:
             ok = 1
             try:
                 import torch.distributed._symmetric_memory as symm
-                # pull: two staging pictures (step parity), read in place by the peers' pull kernels
-                # push: the landing slots themselves (two parities x world pictures) are symmetric + multicast-mapped
-                self.stage = symm.empty(self.n * (2 if want == "pull" else 2 * self.world if want == "push" else 1), dtype=torch.uint8, device=device)
+                # pull: `ring` staging pictures (ring position of the step), read in place by the peers' pull kernels
+                # push: the landing slots themselves (ring x world pictures) are symmetric + multicast-mapped
+                self.stage = symm.empty(self.n * (ring if want == "pull" else ring * self.world if want == "push" else 1), dtype=torch.uint8, device=device)
                 self.hdl = symm.rendezvous(self.stage, group if group is not None else dist.group.WORLD)
                 self.peers = [self.hdl.get_buffer(r, (self.stage.numel(),), torch.uint8) for r in range(self.world)]
                 if want == "push" and not self.hdl.multicast_ptr:
