@@ -173,6 +173,8 @@ typedef struct {
   mmgpu_mv mv1;
 } mmgpu_mc_job;
 /* dst[c]: HOST planes of the (un-padded) picture being reconstructed; every job writes its block at (x,y). */
+/* (dst planes in page-locked host memory -- cudaHostRegister or a pinned allocation -- are read back by one direct copy per plane:
+ * 0.43 instead of 0.76-1.04 ms per 2048x1024 4:2:0 picture) */
 int mmgpu_mc_jobs(mmgpu_ctx* ctx, int n_jobs, const mmgpu_mc_job* jobs, int clp_min, int clp_max, int16_t* const dst[3],
                   const int32_t dst_stride[3]);
 
