@@ -229,3 +229,71 @@ def test_classic_dmvr_final_mc_and_alt_hpel_equal_reference_filters():
         for bi in (False, True):
             exp = _ref_mc(ref, 40 + (mv[0] >> 4), 32 + (mv[1] >> 4), 16, 8, mv[0] & 15, mv[1] & 15, bi, alt=True)
             assert np.array_equal(exp, ol.mc_block_classic_alt(pl, (40, 32), (16, 8), mv, bi=bi)), (mv, bi)
+
+
+def test_dmvr_decision_error_surface_equals_reference_object_code():
+    """The sub-pel step of the DMVR decision -- xDMVRSubPixelErrorSurface -> xSubPelErrorSrfc -> div_for_maxq7
+    (InterPrediction.cpp:1958-2048, 2157-2175) -- runs here as the REFERENCE'S OWN compiled code (oracle/_ref/vtm/libvtmdmvr.so: the
+    whole-reference build's objects behind one C entry point).  The integer stage in front of it is spelled out in the test
+    (xProcessDMVR :2364-2394, xBIPMVRefine :2050-2073); oracle's orc_dmvr_decide and the library's host-side mmgpu_dmvr_decide must give the
+    same delta MV and minimum cost for random and degenerate cost surfaces."""
+    import ctypes as C
+    import os
+    import subprocess
+    so = os.path.join(rl.ROOT, "oracle", "_ref", "vtm", "libvtmdmvr.so")
+    if not os.path.exists(so) and os.path.isdir("/root/reference/source/Lib/CommonLib"):
+        subprocess.call(["make", "-C", os.path.join(rl.ROOT, "oracle"), "-f", "vtm.mk", "-j", "8", "dmvr"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/vtm/libvtmdmvr.so not built (reference sources absent)")
+    L = C.CDLL(so)
+    L.ref_dmvr_subpel.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    offs = [(ox, oy) for oy in range(-2, 3) for ox in range(-2, 3)]
+    MAXU = np.uint64(0xFFFFFFFFFFFFFFFF)
+    rng = np.random.default_rng(2157)
+    import vvc_extension_mm_b200 as mm
+    n_sub = n_moved = 0
+    for rep in range(4000):
+        dx, dy = [(16, 16), (8, 16), (16, 8), (8, 8)][rep % 4]
+        kind = rep % 5
+        if kind == 0:
+            costs = rng.integers(0, 40000, size=25).astype(np.uint64)
+        elif kind == 1:      # smooth bowl around a random minimum (what real surfaces look like)
+            cx, cy = rng.uniform(-2.5, 2.5, size=2)
+            costs = np.array([int(300 + 900 * ((ox - cx) ** 2 + 0.7 * (oy - cy) ** 2) + rng.integers(0, 40)) for ox, oy in offs], dtype=np.uint64)
+        elif kind == 2:      # ties and plateaus
+            costs = rng.integers(0, 4, size=25).astype(np.uint64) * 500 + 1000
+        elif kind == 3:      # centre below the early-exit threshold / zero
+            costs = rng.integers(0, 3000, size=25).astype(np.uint64)
+            costs[12] = [0, 1, dx * dy - 1, dx * dy, dx * dy + 40][rep // 5 % 5]
+        else:                # large values
+            costs = rng.integers(0, 1 << 22, size=25).astype(np.uint64)
+        # integer stage, spelled out
+        sads = np.full(25, MAXU, dtype=np.uint64)
+        centre, not_zero, total, delta = 12, 1, [0, 0], [0, 0]
+        min_cost = int(costs[12]) - (int(costs[12]) >> 2)
+        if min_cost < dx * dy:
+            not_zero = 0
+        else:
+            sads[12] = min_cost
+            if min_cost == 0:
+                not_zero = 0
+            else:
+                for k, (ox, oy) in enumerate(offs):
+                    idx = 12 + oy * 5 + ox
+                    if sads[idx] == MAXU:
+                        sads[idx] = costs[k]
+                    if int(sads[idx]) < min_cost:
+                        min_cost, delta = int(sads[idx]), [ox, oy]
+                if delta != [0, 0]:
+                    total = [delta[0], delta[1]]
+                    centre = 12 + delta[1] * 5 + delta[0]
+        t16 = np.array([total[0] * 16, total[1] * 16], dtype=np.int16)
+        d16 = np.array(delta, dtype=np.int16)
+        buf = np.concatenate([np.full(8, MAXU, dtype=np.uint64), sads, np.full(8, MAXU, dtype=np.uint64)])   # guard cells around the 5x5
+        L.ref_dmvr_subpel(not_zero, t16.ctypes.data, d16.ctypes.data, buf.ctypes.data + 8 * 8, centre)
+        exp = (not_zero, (int(t16[0]), int(t16[1])), min_cost)
+        assert ol.dmvr_decide(costs, dx, dy) == exp, (rep, costs.tolist())
+        assert mm.dmvr_decide(costs, dx, dy) == exp, (rep, costs.tolist())
+        n_sub += int((t16[0] % 16 != 0) or (t16[1] % 16 != 0))
+        n_moved += int(total != [0, 0])
+    assert n_sub > 300 and n_moved > 1000
