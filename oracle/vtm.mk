@@ -40,7 +40,7 @@ DECOBJ := $(call obj,$(DEC))
 # the reference's DMVR error-surface functions behind a C entry point (tests/test_oracle_vs_reference_objects.py)
 dmvr: $(OUT)/libvtmdmvr.so
 $(OUT)/libvtmdmvr.so: $(LIBOBJ) ref_wrap_dmvr.cpp
-	$(CXX) -std=c++11 -O2 -fPIC -shared -o $@ ref_wrap_dmvr.cpp $(LIBOBJ) -lm -lpthread
+	$(CXX) $(CXXF) -shared -o $@ ref_wrap_dmvr.cpp $(LIBOBJ) -lm -lpthread
 stock: $(OUT)/EncoderApp $(OUT)/DecoderApp
 
 $(O)/Lib/CommonLib/x86/sse41/%.o: $(LIB)/CommonLib/x86/sse41/%.cpp

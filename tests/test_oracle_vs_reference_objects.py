@@ -297,3 +297,40 @@ def test_dmvr_decision_error_surface_equals_reference_object_code():
         n_sub += int((t16[0] % 16 != 0) or (t16[1] % 16 != 0))
         n_moved += int(total != [0, 0])
     assert n_sub > 300 and n_moved > 1000
+
+
+def test_add_avg_and_padding_equal_reference_object_code():
+    """PelBuf::addAvg (Buffer.cpp:551-587, scalar defaults and the x86 table the apps install) == orc_add_avg for 8/10-bit and every
+    width class; paddingCore (xPad's padding, Buffer.cpp:372-396) == edge replication, the form the classic-DMVR tests and kernels use."""
+    import ctypes as C
+    import os
+    so = os.path.join(rl.ROOT, "oracle", "_ref", "vtm", "libvtmdmvr.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/vtm/libvtmdmvr.so not built (reference sources absent)")
+    L = C.CDLL(so)
+    L.ref_add_avg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 5
+    L.ref_padding.argtypes = [C.c_void_p] + [C.c_int] * 4
+    rng = np.random.default_rng(551)
+    for simd in (0, 1):
+        L.ref_pelbuf_simd(simd)
+        for bd, hi in ((10, 1023), (8, 255)):
+            for (w, h) in [(4, 4), (8, 4), (4, 16), (16, 16), (12, 8), (24, 8), (64, 32), (128, 128), (2, 2), (6, 4)]:
+                a = rng.integers(-8192, 8191, size=(h, w)).astype(np.int16)
+                b = rng.integers(-8192, 8191, size=(h, w)).astype(np.int16)
+                a[0, 0], b[0, 0] = 8191, 8191
+                a[-1, -1], b[-1, -1] = -8192, -8192
+                exp = np.zeros((h, w), dtype=np.int16)
+                got = np.zeros((h, w), dtype=np.int16)
+                L.ref_add_avg(a.ctypes.data, w, b.ctypes.data, w, exp.ctypes.data, w, w, h, bd, 0, hi)
+                ol.lib().orc_add_avg(a.ctypes.data, w, b.ctypes.data, w, got.ctypes.data, w, w, h, bd, 0, hi)
+                assert np.array_equal(exp, got), (simd, bd, w, h)
+    L.ref_pelbuf_simd(1)
+    for (w, h, pad) in [(23, 23, 2), (15, 23, 2), (11, 11, 1), (7, 11, 1), (23, 15, 2)]:
+        win = rng.integers(0, 1024, size=(h, w)).astype(np.int16)
+        S = w + 12
+        buf = np.full((h + 12, S), -7, dtype=np.int16)
+        buf[2:2 + h, 2:2 + w] = win
+        L.ref_padding(buf.ctypes.data + 2 * (2 * S + 2), S, w, h, pad)
+        exp = np.full((h + 12, S), -7, dtype=np.int16)
+        exp[2 - pad:2 + h + pad, 2 - pad:2 + w + pad] = np.pad(win, pad, mode="edge")
+        assert np.array_equal(buf, exp), (w, h, pad)
