@@ -2,7 +2,8 @@
 """bench.py -- multi-model MC + SATD throughput of the B200 path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm
-    python bench.py --impl reference --gpus N --steps K ...   # reference CPU arm (oracle port, all host threads)
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU arm (the reference's compiled AVX2 FIR / Hadamard
+                                                              # objects driven like its per-candidate loop, all host threads)
 
 A "step" is one pass of the hot path over one frame-wide batch: every block of a 2048x1024 ERP frame
 (mixed VVC partition) x 16 candidate MVs, per block: map (MPA_FB/LR/TB, GED_CAMPOSE epipole (1,0,0), ROT)
@@ -11,7 +12,8 @@ A "step" is one pass of the hot path over one frame-wide batch: every block of a
 `e2e`    : the same through the host C ABI (mmgpu_set_org + mmgpu_me_batch) from pinned host buffers,
            H2D of the original picture / blocks / MVs and D2H of the distortions inside the timed region.
 N > 1    : weak scaling -- each step covers N frames; rank r evaluates CTU rows r, r+N, ... of all N frames;
-           the reference picture of frame f is NCCL-broadcast from rank f inside the timed region.
+           the reference picture of frame f reaches every GPU from rank f inside the timed region (NVLS multicast push up to
+           4 GPUs, one ncclAllGather beyond; other forms by MMGPU_EXCHANGE).
 """
 import argparse
 import json

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: the path shards by CTU rows of a frame against shared reference pictures.
 
 One process per GPU; torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests) moves the only
-data that has to cross GPUs: a newly reconstructed, padded reference picture (broadcast once per frame from the
-rank that holds it) and, optionally, the per-candidate distortions (all-gather).  No collective sits inside the
+data that has to cross GPUs: a newly reconstructed reference picture (once per frame from the rank that holds it:
+PictureExchange -- NCCL all-gather, NVLS multicast push, fused pull or copy-engine pulls over symmetric memory) and,
+optionally, the per-candidate distortions (all-gather).  No collective sits inside the
 MC/distortion kernels: blocks of different CTU rows are independent.
 """
 import numpy as np
